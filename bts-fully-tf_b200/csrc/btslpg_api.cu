@@ -1,0 +1,507 @@
+// btslpg_api.cu -- the C ABI of libbtslpg.so (declared in include/btslpg.h): argument
+// validation, variant selection and kernel launches.  No allocation, no synchronisation, no
+// CPU fallback: a host pointer or an unsupported layout is an error, never a slow path on the CPU.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/btslpg.h"
+#include "head_kernels.cuh"
+#include "lpg_kernels.cuh"
+
+using namespace btslpg;
+
+namespace {
+
+thread_local char tl_error[512] = "";
+thread_local char tl_kernel[128] = "";
+std::atomic<uint64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
+std::atomic<int> g_fwd_threads{0}, g_bwd_threads{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+enum DType { kF32 = 0, kBF16 = 1 };
+
+// A tensor viewed as (B, H, W, C) with element strides.
+struct View {
+    char *ptr = nullptr;
+    int dtype = -1;
+    int dev = -1;
+    int64_t B = 0, H = 0, W = 0, C = 0;
+    int64_t sB = 0, sH = 0, sW = 0, sC = 0;
+    int esize() const { return dtype == kF32 ? 4 : 2; }
+    bool aligned(int bytes) const { return (reinterpret_cast<uintptr_t>(ptr) % bytes) == 0; }
+};
+
+int parse_common(const BtsTensor *t, const char *name, View &v) {
+    if (!t) return fail(BTSLPG_EINVAL, "%s: tensor is NULL", name);
+    if (!t->data && t->ndim > 0) {
+        int64_t n = 1;
+        for (int k = 0; k < t->ndim; ++k) n *= t->shape[k];
+        if (n != 0) return fail(BTSLPG_EINVAL, "%s: data pointer is NULL", name);
+    }
+    if (t->device.device_type != 2 && t->device.device_type != 13)
+        return fail(BTSLPG_EDEVICE, "%s: not a CUDA tensor (DLPack device_type %d); host tensors are not accepted -- "
+                                    "there is no CPU fallback", name, (int)t->device.device_type);
+    if (t->dtype.lanes != 1) return fail(BTSLPG_EDTYPE, "%s: dtype lanes must be 1", name);
+    if (t->dtype.code == 2 && t->dtype.bits == 32) v.dtype = kF32;
+    else if (t->dtype.code == 4 && t->dtype.bits == 16) v.dtype = kBF16;
+    else return fail(BTSLPG_EDTYPE, "%s: dtype (code %d, bits %d) is not float32 or bfloat16", name, (int)t->dtype.code, (int)t->dtype.bits);
+    v.dev = t->device.device_id;
+    v.ptr = static_cast<char *>(t->data) + t->byte_offset;
+    if (!t->shape) return fail(BTSLPG_ESHAPE, "%s: shape is NULL", name);
+    return 0;
+}
+
+void strides_of(const BtsTensor *t, int64_t *s) {
+    if (t->strides) {
+        for (int k = 0; k < t->ndim; ++k) s[k] = t->strides[k];
+    } else {
+        int64_t acc = 1;
+        for (int k = t->ndim - 1; k >= 0; --k) { s[k] = acc; acc *= t->shape[k]; }
+    }
+}
+
+// (B,h,w,C) NHWC tensor
+int parse_nhwc(const BtsTensor *t, const char *name, View &v) {
+    if (int e = parse_common(t, name, v)) return e;
+    if (t->ndim != 4) return fail(BTSLPG_ESHAPE, "%s: expected a rank-4 NHWC tensor, got rank %d", name, (int)t->ndim);
+    int64_t s[4];
+    strides_of(t, s);
+    v.B = t->shape[0]; v.H = t->shape[1]; v.W = t->shape[2]; v.C = t->shape[3];
+    v.sB = s[0]; v.sH = s[1]; v.sW = s[2]; v.sC = s[3];
+    if (v.B < 0 || v.H < 0 || v.W < 0 || v.C < 0) return fail(BTSLPG_ESHAPE, "%s: negative extent", name);
+    return 0;
+}
+
+// single-channel map given as (B,H,W,1) or (B,H,W)
+int parse_map(const BtsTensor *t, const char *name, View &v) {
+    if (int e = parse_common(t, name, v)) return e;
+    if (t->ndim != 3 && t->ndim != 4)
+        return fail(BTSLPG_ESHAPE, "%s: expected (B,H,W,1) or (B,H,W), got rank %d", name, (int)t->ndim);
+    if (t->ndim == 4 && t->shape[3] != 1)
+        return fail(BTSLPG_ESHAPE, "%s: last dimension must be 1, got %lld", name, (long long)t->shape[3]);
+    int64_t s[4];
+    strides_of(t, s);
+    v.B = t->shape[0]; v.H = t->shape[1]; v.W = t->shape[2]; v.C = 1;
+    v.sB = s[0]; v.sH = s[1]; v.sW = s[2]; v.sC = 1;
+    return 0;
+}
+
+bool is_contig_nhwc(const View &v) {
+    return v.sC == 1 && v.sW == v.C && v.sH == v.W * v.C && v.sB == v.H * v.W * v.C;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BTSLPG_ECUDA, "%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int block_threads(bool fwd, int r) {
+    int t = fwd ? g_fwd_threads.load() : g_bwd_threads.load();
+    if (t <= 0) t = (r == 8) ? 64 : 128;
+    if (t > 256) t = 256;
+    t = (t + 31) / 32 * 32;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shape / layout checks shared by forward and backward.
+// ---------------------------------------------------------------------------------------------
+struct LayerGeom {
+    View coef, full, ds;
+    bool has_full = false, has_ds = false;
+    int r = 0, d = 0;
+};
+
+int check_geom(LayerGeom &g, const char *coef_name, const char *full_name, const char *ds_name) {
+    if (g.r < 1 || g.r > 64) return fail(BTSLPG_EINVAL, "upratio must be in [1, 64], got %d", g.r);
+    if (g.coef.C != 3) return fail(BTSLPG_ESHAPE, "%s: last dimension must be 3 [phi, theta, dist], got %lld", coef_name, (long long)g.coef.C);
+    const int64_t H = g.coef.H * g.r, W = g.coef.W * g.r;
+    if (g.has_full) {
+        if (g.full.B != g.coef.B || g.full.H != H || g.full.W != W)
+            return fail(BTSLPG_ESHAPE, "%s: expected (%lld,%lld,%lld[,1]) = (B, h*%d, w*%d), got (%lld,%lld,%lld)", full_name,
+                        (long long)g.coef.B, (long long)H, (long long)W, g.r, g.r, (long long)g.full.B, (long long)g.full.H, (long long)g.full.W);
+        if (g.full.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", full_name, coef_name);
+        if (g.full.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", full_name, coef_name);
+    }
+    if (g.has_ds) {
+        if (g.d < 1 || g.r % g.d != 0) return fail(BTSLPG_EINVAL, "ds_stride %d must be >= 1 and divide upratio %d", g.d, g.r);
+        if (g.ds.B != g.coef.B || g.ds.H != H / g.d || g.ds.W != W / g.d)
+            return fail(BTSLPG_ESHAPE, "%s: expected (%lld,%lld,%lld[,1]) = full[:, ::%d, ::%d], got (%lld,%lld,%lld)", ds_name,
+                        (long long)g.coef.B, (long long)(H / g.d), (long long)(W / g.d), g.d, g.d, (long long)g.ds.B, (long long)g.ds.H, (long long)g.ds.W);
+        if (g.ds.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", ds_name, coef_name);
+        if (g.ds.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", ds_name, coef_name);
+    } else {
+        g.d = 0;
+    }
+    if (g.coef.B * g.coef.H * g.coef.W >= (int64_t)1 << 31) return fail(BTSLPG_ESHAPE, "%s: more than 2^31 coarse pixels", coef_name);
+    return 0;
+}
+
+// Largest PX (coarse pixels per thread) the vectorised kernels can use for this layer, or 0.
+//  - r in {2,4,8}; ds absent or ds stride r/2 (the reference's two cases)
+//  - coef contiguous; maps with column stride 1; every vector access aligned
+int pick_px(const LayerGeom &g) {
+    const int r = g.r, es = g.coef.esize();
+    if (r != 2 && r != 4 && r != 8) return 0;
+    if (g.has_ds && (g.d != r / 2 || r == 2)) return 0;
+    if (!is_contig_nhwc(g.coef) || !g.coef.aligned(16)) return 0;
+    if (g.has_full && g.full.sW != 1) return 0;
+    if (g.has_ds && g.ds.sW != 1) return 0;
+    const int nds = g.has_ds ? 2 : 0;
+    for (int px = 32 / (r * es); px >= 1; px /= 2) {
+        if (px < 32 / (r * es) / 4) break;                       // instantiated: PXmax, PXmax/2, PXmax/4
+        if (g.coef.W % px) continue;
+        if ((px * 3 * es) % 4) continue;                          // whole 32-bit words of coefficients
+        const int row_bytes = px * r * es;                        // 32, 16 or 8
+        if (row_bytes % 4) continue;
+        if (g.has_full) {
+            if (!g.full.aligned(row_bytes) || (g.full.sH * es) % row_bytes || (g.full.sB * es) % row_bytes) continue;
+        }
+        if (g.has_ds) {
+            const int ds_bytes = px * nds * es;
+            if (ds_bytes % 4) continue;
+            if (!g.ds.aligned(ds_bytes) || (g.ds.sH * es) % ds_bytes || (g.ds.sB * es) % ds_bytes) continue;
+        }
+        return px;
+    }
+    return 0;
+}
+
+template <typename T> LpgFwdParams<T> make_fwd_params(const LayerGeom &g, int px) {
+    LpgFwdParams<T> p;
+    p.coef = reinterpret_cast<const T *>(g.coef.ptr);
+    p.out = reinterpret_cast<T *>(g.full.ptr);
+    p.ds = g.has_ds ? reinterpret_cast<T *>(g.ds.ptr) : nullptr;
+    p.out_sB = g.full.sB; p.out_sH = g.full.sH;
+    p.ds_sB = g.has_ds ? g.ds.sB : 0; p.ds_sH = g.has_ds ? g.ds.sH : 0;
+    const uint32_t wg = (uint32_t)(g.coef.W / px);
+    p.units = (uint32_t)(g.coef.B * g.coef.H * wg);
+    p.wg = FastDiv(wg);
+    p.h = FastDiv((uint32_t)g.coef.H);
+    return p;
+}
+
+template <typename T> LpgBwdParams<T> make_bwd_params(const LayerGeom &g, const View &gcoef, int px) {
+    LpgBwdParams<T> p;
+    p.coef = reinterpret_cast<const T *>(g.coef.ptr);
+    p.g_full = g.has_full ? reinterpret_cast<const T *>(g.full.ptr) : nullptr;
+    p.g_ds = g.has_ds ? reinterpret_cast<const T *>(g.ds.ptr) : nullptr;
+    p.g_coef = reinterpret_cast<T *>(gcoef.ptr);
+    p.gf_sB = g.has_full ? g.full.sB : 0; p.gf_sH = g.has_full ? g.full.sH : 0;
+    p.gd_sB = g.has_ds ? g.ds.sB : 0; p.gd_sH = g.has_ds ? g.ds.sH : 0;
+    const uint32_t wg = (uint32_t)(g.coef.W / px);
+    p.units = (uint32_t)(g.coef.B * g.coef.H * wg);
+    p.wg = FastDiv(wg);
+    p.h = FastDiv((uint32_t)g.coef.H);
+    return p;
+}
+
+template <typename T> LpgGenericParams<T> make_generic_params(const LayerGeom &g, const View *gcoef) {
+    LpgGenericParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.coef = reinterpret_cast<const T *>(g.coef.ptr);
+    p.c_sB = g.coef.sB; p.c_sH = g.coef.sH; p.c_sW = g.coef.sW; p.c_sC = g.coef.sC;
+    if (g.has_full) { p.o_sB = g.full.sB; p.o_sH = g.full.sH; p.o_sW = g.full.sW; }
+    if (g.has_ds) { p.d_sB = g.ds.sB; p.d_sH = g.ds.sH; p.d_sW = g.ds.sW; }
+    if (gcoef) {
+        p.g_full = g.has_full ? reinterpret_cast<const T *>(g.full.ptr) : nullptr;
+        p.g_ds = g.has_ds ? reinterpret_cast<const T *>(g.ds.ptr) : nullptr;
+        p.g_coef = reinterpret_cast<T *>(gcoef->ptr);
+        p.gc_sB = gcoef->sB; p.gc_sH = gcoef->sH; p.gc_sW = gcoef->sW; p.gc_sC = gcoef->sC;
+    } else {
+        p.out = reinterpret_cast<T *>(g.full.ptr);
+        p.ds = g.has_ds ? reinterpret_cast<T *>(g.ds.ptr) : nullptr;
+    }
+    p.B = g.coef.B; p.h = g.coef.H; p.w = g.coef.W;
+    p.r = g.r; p.d = g.has_ds ? g.d : 0;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant dispatch for the vectorised kernels: (T, R, PX, D) are compile-time.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int R, int PX, int D>
+void launch_fwd_variant(const LpgFwdParams<T> &p, int threads, cudaStream_t st) {
+    const uint32_t blocks = (p.units + threads - 1) / threads;
+    lpg_fwd_vec_kernel<T, R, PX, D><<<blocks, threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,ds%d>", ElemTraits<T>::kName, R, PX, D);
+}
+template <typename T, int R, int PX, int D>
+void launch_bwd_variant(const LpgBwdParams<T> &p, int threads, cudaStream_t st) {
+    const uint32_t blocks = (p.units + threads - 1) / threads;
+    lpg_bwd_vec_kernel<T, R, PX, D><<<blocks, threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,ds%d>", ElemTraits<T>::kName, R, PX, D);
+}
+
+#define BTSLPG_DISPATCH_PX(LAUNCH, T, R, PXMAX, D, ...)                                          \
+    do {                                                                                         \
+        if (px == (PXMAX)) LAUNCH<T, R, (PXMAX), D>(__VA_ARGS__);                                \
+        else if constexpr ((PXMAX) / 2 >= 1 && (((PXMAX) / 2) * 3 * sizeof(T)) % 4 == 0) {       \
+            if (px == (PXMAX) / 2) LAUNCH<T, R, (PXMAX) / 2, D>(__VA_ARGS__);                    \
+            else if constexpr ((PXMAX) / 4 >= 1 && (((PXMAX) / 4) * 3 * sizeof(T)) % 4 == 0) {   \
+                if (px == (PXMAX) / 4) LAUNCH<T, R, (PXMAX) / 4, D>(__VA_ARGS__);                \
+            }                                                                                    \
+        }                                                                                        \
+    } while (0)
+
+template <typename T, typename P, bool FWD> void dispatch_vec(const P &p, int r, int px, bool has_ds, int threads, cudaStream_t st) {
+#define BTSLPG_CASE(R)                                                                                       \
+    case R:                                                                                                  \
+        if (has_ds) {                                                                                        \
+            if constexpr (R > 2) {                                                                           \
+                if constexpr (FWD) BTSLPG_DISPATCH_PX(launch_fwd_variant, T, R, px_max<T>(R), R / 2, p, threads, st); \
+                else BTSLPG_DISPATCH_PX(launch_bwd_variant, T, R, px_max<T>(R), R / 2, p, threads, st);      \
+            }                                                                                                \
+        } else {                                                                                             \
+            if constexpr (FWD) BTSLPG_DISPATCH_PX(launch_fwd_variant, T, R, px_max<T>(R), 0, p, threads, st); \
+            else BTSLPG_DISPATCH_PX(launch_bwd_variant, T, R, px_max<T>(R), 0, p, threads, st);              \
+        }                                                                                                    \
+        break;
+    switch (r) {
+        BTSLPG_CASE(8)
+        BTSLPG_CASE(4)
+        BTSLPG_CASE(2)
+        default: break;
+    }
+#undef BTSLPG_CASE
+}
+
+int parse_layer_fwd(const BtsTensor *coef, int upratio, BtsTensor *out_full, BtsTensor *out_ds, int ds_stride, LayerGeom &g) {
+    if (int e = parse_nhwc(coef, "coef", g.coef)) return e;
+    if (int e = parse_map(out_full, "out_full", g.full)) return e;
+    g.has_full = true;
+    g.has_ds = out_ds != nullptr;
+    if (g.has_ds) {
+        if (int e = parse_map(out_ds, "out_ds", g.ds)) return e;
+    }
+    g.r = upratio;
+    g.d = ds_stride;
+    return check_geom(g, "coef", "out_full", "out_ds");
+}
+
+int parse_layer_bwd(const BtsTensor *coef, const BtsTensor *g_full, const BtsTensor *g_ds, int upratio, int ds_stride,
+                    BtsTensor *g_coef, LayerGeom &g, View &gc) {
+    if (int e = parse_nhwc(coef, "coef", g.coef)) return e;
+    g.has_full = g_full != nullptr;
+    g.has_ds = g_ds != nullptr;
+    if (g.has_full) {
+        if (int e = parse_map(g_full, "g_full", g.full)) return e;
+    }
+    if (g.has_ds) {
+        if (int e = parse_map(g_ds, "g_ds", g.ds)) return e;
+    }
+    g.r = upratio;
+    g.d = ds_stride;
+    if (int e = check_geom(g, "coef", "g_full", "g_ds")) return e;
+    if (g_coef) {
+        if (int e = parse_nhwc(g_coef, "g_coef", gc)) return e;
+        if (gc.B != g.coef.B || gc.H != g.coef.H || gc.W != g.coef.W || gc.C != 3)
+            return fail(BTSLPG_ESHAPE, "g_coef: shape must equal coef's (B,h,w,3)");
+        if (gc.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "g_coef: dtype differs from coef");
+        if (gc.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "g_coef: on a different device than coef");
+    }
+    return 0;
+}
+
+template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
+    const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
+    if (npix == 0) return 0;
+    const int px = pick_px(g);
+    if (px > 0) {
+        auto p = make_fwd_params<T>(g, px);
+        tl_kernel[0] = 0;
+        dispatch_vec<T, LpgFwdParams<T>, true>(p, g.r, px, g.has_ds, block_threads(true, g.r), st);
+        if (tl_kernel[0]) return check_launch("btslpg_forward");
+    }
+    auto p = make_generic_params<T>(g, nullptr);
+    const int threads = 128;
+    lpg_fwd_generic_kernel<T><<<(unsigned)((npix + threads - 1) / threads), threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_generic<%s,r%d,ds%d>", ElemTraits<T>::kName, g.r, g.d);
+    return check_launch("btslpg_forward");
+}
+
+template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaStream_t st) {
+    const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
+    if (npix == 0) return 0;
+    int px = pick_px(g);
+    if (px > 0 && !(is_contig_nhwc(gc) && gc.aligned(16))) px = 0;
+    if (px > 0) {
+        auto p = make_bwd_params<T>(g, gc, px);
+        tl_kernel[0] = 0;
+        dispatch_vec<T, LpgBwdParams<T>, false>(p, g.r, px, g.has_ds, block_threads(false, g.r), st);
+        if (tl_kernel[0]) return check_launch("btslpg_backward");
+    }
+    auto p = make_generic_params<T>(g, &gc);
+    const int threads = 128;
+    lpg_bwd_generic_kernel<T><<<(unsigned)((npix + threads - 1) / threads), threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_generic<%s,r%d,ds%d>", ElemTraits<T>::kName, g.r, g.d);
+    return check_launch("btslpg_backward");
+}
+
+// multi-launch eligibility: the max-PX vector variant with the reference's ds stride (or none)
+bool multi_eligible(const LayerGeom &g) {
+    if (g.r != 2 && g.r != 4 && g.r != 8) return false;
+    const int pxm = 32 / (g.r * g.coef.esize());
+    return pick_px(g) == pxm;
+}
+
+}  // namespace
+
+// =============================================================================================
+// exported C ABI
+// =============================================================================================
+extern "C" {
+
+int btslpg_version(void) { return BTSLPG_VERSION; }
+const char *btslpg_last_error(void) { return tl_error; }
+const char *btslpg_last_kernel(void) { return tl_kernel; }
+uint64_t btslpg_launch_count(void) { return g_launches.load(); }
+void btslpg_reset_launch_count(void) { g_launches.store(0); }
+void btslpg_set_block_threads(int fwd_threads, int bwd_threads) {
+    g_fwd_threads.store(fwd_threads);
+    g_bwd_threads.store(bwd_threads);
+}
+
+const char *btslpg_status_string(int status) {
+    switch (status) {
+        case BTSLPG_OK: return "ok";
+        case BTSLPG_EINVAL: return "invalid argument";
+        case BTSLPG_EDTYPE: return "unsupported or mismatched dtype";
+        case BTSLPG_ESHAPE: return "shape mismatch";
+        case BTSLPG_EDEVICE: return "not a CUDA tensor / device mismatch";
+        case BTSLPG_ELAYOUT: return "unsupported memory layout";
+        case BTSLPG_EWORKSPACE: return "workspace missing or too small";
+        case BTSLPG_ECUDA: return "CUDA error";
+        default: return "unknown status";
+    }
+}
+
+int btslpg_forward(const BtsTensor *coef, int upratio, BtsTensor *out_full, BtsTensor *out_ds, int ds_stride, void *stream) {
+    LayerGeom g;
+    if (int e = parse_layer_fwd(coef, upratio, out_full, out_ds, ds_stride, g)) return e;
+    DeviceGuard guard(g.coef.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g.coef.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return g.coef.dtype == kF32 ? run_forward<float>(g, st) : run_forward<__nv_bfloat16>(g, st);
+}
+
+int btslpg_backward(const BtsTensor *coef, const BtsTensor *g_full, const BtsTensor *g_ds, int upratio, int ds_stride,
+                    BtsTensor *g_coef, void *stream) {
+    if (!g_coef) return fail(BTSLPG_EINVAL, "g_coef: tensor is NULL");
+    LayerGeom g;
+    View gc;
+    if (int e = parse_layer_bwd(coef, g_full, g_ds, upratio, ds_stride, g_coef, g, gc)) return e;
+    DeviceGuard guard(g.coef.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g.coef.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return g.coef.dtype == kF32 ? run_backward<float>(g, gc, st) : run_backward<__nv_bfloat16>(g, gc, st);
+}
+
+int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
+    if (!layers || n < 1 || n > BTSLPG_MAX_MULTI) return fail(BTSLPG_EINVAL, "forward_multi: n must be in [1, %d]", BTSLPG_MAX_MULTI);
+    LayerGeom g[BTSLPG_MAX_MULTI];
+    bool fused = true;
+    for (int k = 0; k < n; ++k) {
+        if (int e = parse_layer_fwd(layers[k].coef, layers[k].upratio, layers[k].out_full, layers[k].out_ds, layers[k].ds_stride, g[k])) return e;
+        fused = fused && multi_eligible(g[k]) && g[k].coef.dtype == g[0].coef.dtype && g[k].coef.dev == g[0].coef.dev &&
+                g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!fused) {
+        for (int k = 0; k < n; ++k)
+            if (int e = btslpg_forward(layers[k].coef, layers[k].upratio, layers[k].out_full, layers[k].out_ds, layers[k].ds_stride, stream)) return e;
+        return 0;
+    }
+    DeviceGuard guard(g[0].coef.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
+    const int threads = block_threads(true, 4);
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        LpgFwdMulti<T> m;
+        memset(&m, 0, sizeof(m));
+        uint32_t blocks = 0;
+        for (int k = 0; k < n; ++k) {
+            m.layer[k] = make_fwd_params<T>(g[k], 32 / (g[k].r * (int)sizeof(T)));
+            m.upratio[k] = g[k].r;
+            blocks += (m.layer[k].units + threads - 1) / threads;
+            m.block_end[k] = blocks;
+        }
+        m.n = n;
+        lpg_fwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
+        snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
+        return check_launch("btslpg_forward_multi");
+    };
+    return g[0].coef.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream) {
+    if (!layers || n < 1 || n > BTSLPG_MAX_MULTI) return fail(BTSLPG_EINVAL, "backward_multi: n must be in [1, %d]", BTSLPG_MAX_MULTI);
+    LayerGeom g[BTSLPG_MAX_MULTI];
+    View gc[BTSLPG_MAX_MULTI];
+    bool fused = true;
+    for (int k = 0; k < n; ++k) {
+        if (!layers[k].g_coef) return fail(BTSLPG_EINVAL, "g_coef: tensor is NULL");
+        if (int e = parse_layer_bwd(layers[k].coef, layers[k].g_full, layers[k].g_ds, layers[k].upratio, layers[k].ds_stride, layers[k].g_coef, g[k], gc[k])) return e;
+        fused = fused && multi_eligible(g[k]) && is_contig_nhwc(gc[k]) && gc[k].aligned(16) && g[k].coef.dtype == g[0].coef.dtype &&
+                g[k].coef.dev == g[0].coef.dev && g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!fused) {
+        for (int k = 0; k < n; ++k)
+            if (int e = btslpg_backward(layers[k].coef, layers[k].g_full, layers[k].g_ds, layers[k].upratio, layers[k].ds_stride, layers[k].g_coef, stream)) return e;
+        return 0;
+    }
+    DeviceGuard guard(g[0].coef.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
+    const int threads = block_threads(false, 4);
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        LpgBwdMulti<T> m;
+        memset(&m, 0, sizeof(m));
+        uint32_t blocks = 0;
+        for (int k = 0; k < n; ++k) {
+            m.layer[k] = make_bwd_params<T>(g[k], gc[k], 32 / (g[k].r * (int)sizeof(T)));
+            m.upratio[k] = g[k].r;
+            blocks += (m.layer[k].units + threads - 1) / threads;
+            m.block_end[k] = blocks;
+        }
+        m.n = n;
+        lpg_bwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
+        snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
+        return check_launch("btslpg_backward_multi");
+    };
+    return g[0].coef.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+}  // extern "C"
+
+#include "head_api.inl"

@@ -1,0 +1,241 @@
+"""Operator layer above the C ABI: thin, allocation + autograd glue only.
+
+Every function here ends in a call into libbtslpg.so on the tensor's CUDA device and the
+caller's current stream; nothing is computed in Python or PyTorch.  Layout follows the
+reference (Keras channels_last): coefficients (B,h,w,3), depth maps (B,H,W,1).
+
+Reference lines replaced:
+  lpg_forward / LpgFunction     custom_layers.py:47-56 (+ the slices bts_decoder.py:81,88)
+  reduce_lpg / ReduceLpgFunction bts_decoder.py:79-81, 86-88, 93-94
+  lpg_forward_multi / lpg_backward_multi   the three layers of one decoder in one launch
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from ._cabi import as_ref, check, current_stream_ptr, load, ptr_or_null
+
+
+def _out_shape(coef, upratio):
+    B, h, w, _ = coef.shape
+    return B, h * upratio, w * upratio
+
+
+def lpg_forward(coef, upratio, ds_stride=0, out_full=None, out_ds=None):
+    """depth = LPG_r(coef) and, if ds_stride, depth[:, ::ds_stride, ::ds_stride].
+
+    out_full / out_ds may be preallocated (e.g. a channel plane of a concat buffer); strides are
+    honoured.  Returns (out_full, out_ds-or-None)."""
+    lib = load()
+    B, H, W = _out_shape(coef, upratio)
+    if out_full is None:
+        out_full = torch.empty((B, H, W, 1), dtype=coef.dtype, device=coef.device)
+    if ds_stride and out_ds is None:
+        out_ds = torch.empty((B, H // ds_stride, W // ds_stride, 1), dtype=coef.dtype, device=coef.device)
+    rc, rf, rd = as_ref(coef), as_ref(out_full), as_ref(out_ds if ds_stride else None)
+    check(lib.btslpg_forward(rc.ptr, int(upratio), rf.ptr, ptr_or_null(rd), int(ds_stride), current_stream_ptr(coef.device)))
+    return out_full, (out_ds if ds_stride else None)
+
+
+def lpg_backward(coef, g_full, g_ds, upratio, ds_stride=0, g_coef=None):
+    """d loss / d coef from d loss / d depth (g_full) and d loss / d depth_ds (g_ds); either may be None."""
+    lib = load()
+    if g_coef is None:
+        g_coef = torch.empty_like(coef, memory_format=torch.contiguous_format)
+    rc, rf, rd, rg = as_ref(coef), as_ref(g_full), as_ref(g_ds), as_ref(g_coef)
+    check(lib.btslpg_backward(rc.ptr, ptr_or_null(rf), ptr_or_null(rd), int(upratio), int(ds_stride if g_ds is not None else 0),
+                              rg.ptr, current_stream_ptr(coef.device)))
+    return g_coef
+
+
+def lpg_forward_multi(layers):
+    """layers: list of dicts(coef, upratio, ds_stride, out_full, out_ds) -> one launch when all
+    layers qualify for the vectorised kernels (else one launch per layer)."""
+    lib = load()
+    n = len(layers)
+    args = (_cabi.BtsLpgForwardArgs * n)()
+    keep = []
+    for k, L in enumerate(layers):
+        rc, rf = as_ref(L["coef"]), as_ref(L["out_full"])
+        rd = as_ref(L.get("out_ds")) if L.get("ds_stride") else None
+        keep += [rc, rf, rd]
+        args[k].coef, args[k].upratio, args[k].ds_stride = rc.ptr, int(L["upratio"]), int(L.get("ds_stride") or 0)
+        args[k].out_full = rf.ptr
+        args[k].out_ds = rd.ptr if rd is not None else None
+    check(lib.btslpg_forward_multi(args, n, current_stream_ptr(layers[0]["coef"].device)))
+
+
+def lpg_backward_multi(layers):
+    """layers: list of dicts(coef, g_full, g_ds, upratio, ds_stride, g_coef)."""
+    lib = load()
+    n = len(layers)
+    args = (_cabi.BtsLpgBackwardArgs * n)()
+    keep = []
+    for k, L in enumerate(layers):
+        rc, rg = as_ref(L["coef"]), as_ref(L["g_coef"])
+        rf, rd = as_ref(L.get("g_full")), as_ref(L.get("g_ds"))
+        keep += [rc, rg, rf, rd]
+        args[k].coef, args[k].g_coef = rc.ptr, rg.ptr
+        args[k].g_full = rf.ptr if rf is not None else None
+        args[k].g_ds = rd.ptr if rd is not None else None
+        args[k].upratio, args[k].ds_stride = int(L["upratio"]), int(L.get("ds_stride") or 0) if rd is not None else 0
+    check(lib.btslpg_backward_multi(args, n, current_stream_ptr(layers[0]["coef"].device)))
+
+
+class LpgFunction(torch.autograd.Function):
+    """Differentiable LPG layer: (coef) -> (depth, depth_ds)."""
+
+    @staticmethod
+    def forward(ctx, coef, upratio, ds_stride):
+        coef_c = coef.contiguous()
+        full, ds = lpg_forward(coef_c, upratio, ds_stride)
+        ctx.save_for_backward(coef_c)
+        ctx.upratio, ctx.ds_stride = upratio, ds_stride
+        ctx.set_materialize_grads(False)
+        if ds is None:
+            ds = full.new_empty(0)
+            ctx.mark_non_differentiable(ds)
+        return full, ds
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_full, g_ds):
+        (coef,) = ctx.saved_tensors
+        if not ctx.ds_stride:
+            g_ds = None
+        if g_full is None and g_ds is None:
+            return torch.zeros_like(coef), None, None
+        return lpg_backward(coef, g_full, g_ds, ctx.upratio, ctx.ds_stride), None, None
+
+
+def local_planar_guidance(coef, upratio, ds_stride=0):
+    """Functional form with autograd.  Returns depth, or (depth, depth_ds) when ds_stride > 0."""
+    full, ds = LpgFunction.apply(coef, int(upratio), int(ds_stride))
+    return (full, ds) if ds_stride else full
+
+
+# ---------------------------------------------------------------------------------------------
+# fused reduction head + LPG
+# ---------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Per (device, stream) scratch for the deterministic g_kernel reduction; its 256-byte header
+    is zeroed once here and left zero by every launch."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _kernel2d(kernel):
+    """Keras Conv2D kernel (1,1,C,3) HWIO or [C][3] -> contiguous float32 [C][3] view."""
+    k = kernel.reshape(kernel.shape[-2], 3) if kernel.dim() == 4 else kernel
+    if k.dtype != torch.float32 or not k.is_contiguous():
+        k = k.float().contiguous()
+    return k
+
+
+def reduce_lpg_forward(feat, kernel, upratio, ds_stride=0, out_full=None, out_ds=None, coef_out=None):
+    """coef = sigmoid(feat @ kernel); depth = LPG_r(coef); depth_ds = depth[:, ::d, ::d] in one kernel.
+    Returns (coef, depth, depth_ds-or-None)."""
+    lib = load()
+    B, h, w, _ = feat.shape
+    H, W = h * upratio, w * upratio
+    if coef_out is None:
+        coef_out = torch.empty((B, h, w, 3), dtype=feat.dtype, device=feat.device)
+    if out_full is None:
+        out_full = torch.empty((B, H, W, 1), dtype=feat.dtype, device=feat.device)
+    if ds_stride and out_ds is None:
+        out_ds = torch.empty((B, H // ds_stride, W // ds_stride, 1), dtype=feat.dtype, device=feat.device)
+    k2 = _kernel2d(kernel)
+    rf, rk, rc, ro = as_ref(feat), as_ref(k2), as_ref(coef_out), as_ref(out_full)
+    rd = as_ref(out_ds) if ds_stride else None
+    check(lib.btslpg_reduce_forward(rf.ptr, rk.ptr, int(upratio), rc.ptr, ro.ptr, ptr_or_null(rd), int(ds_stride),
+                                    current_stream_ptr(feat.device)))
+    return coef_out, out_full, (out_ds if ds_stride else None)
+
+
+def reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, upratio, ds_stride=0, need_g_feat=True, need_g_kernel=True,
+                        g_kernel_out=None, need_g_coef=False):
+    """Gradients of the fused op.  g_kernel_out may be a [C][3] float32 view into a flat gradient
+    bucket (data-parallel training hands that bucket to the NCCL all-reduce).
+    Returns (g_feat-or-None, g_kernel-or-None, g_coef-or-None)."""
+    lib = load()
+    C = feat.shape[-1]
+    k2 = _kernel2d(kernel)
+    g_feat = torch.empty_like(feat, memory_format=torch.contiguous_format) if need_g_feat else None
+    g_kernel = None
+    if need_g_kernel:
+        g_kernel = g_kernel_out if g_kernel_out is not None else torch.empty((C, 3), dtype=torch.float32, device=feat.device)
+    g_coef = torch.empty_like(coef) if need_g_coef else None
+    npix = feat.numel() // C
+    nbytes = lib.btslpg_reduce_backward_workspace_bytes(npix, C)
+    ws = _workspace(feat.device, nbytes)
+    refs = [as_ref(feat), as_ref(k2), as_ref(coef), as_ref(g_full), as_ref(g_ds if ds_stride else None),
+            as_ref(g_feat), as_ref(g_kernel), as_ref(g_coef)]
+    check(lib.btslpg_reduce_backward(refs[0].ptr, refs[1].ptr, refs[2].ptr, ptr_or_null(refs[3]), ptr_or_null(refs[4]),
+                                     int(upratio), int(ds_stride if refs[4] is not None else 0),
+                                     ptr_or_null(refs[5]), ptr_or_null(refs[6]), ptr_or_null(refs[7]),
+                                     ctypes.c_void_p(ws.data_ptr()), ws.numel(), current_stream_ptr(feat.device)))
+    return g_feat, g_kernel, g_coef
+
+
+class ReduceLpgFunction(torch.autograd.Function):
+    """Differentiable fused head: (feat, kernel) -> (reduction, depth, depth_ds)."""
+
+    @staticmethod
+    def forward(ctx, feat, kernel, upratio, ds_stride):
+        feat_c = feat.contiguous()
+        coef, full, ds = reduce_lpg_forward(feat_c, kernel, upratio, ds_stride)
+        ctx.save_for_backward(feat_c, kernel, coef)
+        ctx.upratio, ctx.ds_stride = upratio, ds_stride
+        ctx.set_materialize_grads(False)
+        if ds is None:
+            ds = full.new_empty(0)
+            ctx.mark_non_differentiable(ds)
+        # `reduction` is returned for inspection (layer name reduction_NxN); gradients flowing into it
+        # directly are not part of the reference graph and are not supported.
+        ctx.mark_non_differentiable(coef)
+        return coef, full, ds
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _g_coef, g_full, g_ds):
+        feat, kernel, coef = ctx.saved_tensors
+        if not ctx.ds_stride:
+            g_ds = None
+        need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if (g_full is None and g_ds is None) or not (need_f or need_k):
+            return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None
+        g_feat, g_kernel, _ = reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, ctx.upratio, ctx.ds_stride,
+                                                  need_g_feat=need_f, need_g_kernel=need_k)
+        if g_kernel is not None:
+            g_kernel = g_kernel.reshape(kernel.shape).to(kernel.dtype)
+        return g_feat, g_kernel, None, None
+
+
+def reduce_lpg(feat, kernel, upratio, ds_stride=0):
+    """Functional fused head with autograd.  Returns (reduction, depth[, depth_ds])."""
+    coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride))
+    return (coef, full, ds) if ds_stride else (coef, full)
+
+
+def launch_count():
+    return int(load().btslpg_launch_count())
+
+
+def reset_launch_count():
+    load().btslpg_reset_launch_count()
+
+
+def last_kernel():
+    return load().btslpg_last_kernel().decode()
+
+
+def set_block_threads(fwd=0, bwd=0):
+    load().btslpg_set_block_threads(int(fwd), int(bwd))

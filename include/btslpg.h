@@ -1,0 +1,183 @@
+/*
+ * btslpg.h -- C ABI of libbtslpg.so: the B200 (sm_100a) implementation of the BTS decoder's
+ * Local-Planar-Guidance hot path.
+ *
+ * The reference (clarencechen/bts-fully-tf) is pure tf.keras and has NO FFI: the boundary it
+ * exposes for this path is the Keras Layer protocol.  Each entry point below therefore cites
+ * the reference Python it replaces; INTEGRATION.md shows the ctypes / tf.custom_gradient stub
+ * a maintainer adds to custom_layers.py and bts_decoder.py to bind them.
+ *
+ * Conventions
+ *  - Tensors are described by BtsTensor, which is layout-compatible with DLPack's DLTensor
+ *    (dlpack.h, ABI v0.8/v1.0), so a DLPack capsule from TensorFlow
+ *    (tf.experimental.dlpack.to_dlpack), PyTorch or CuPy maps 1:1 with zero copies.
+ *  - All tensors are CUDA device tensors (device_type kDLCUDA=2) on ONE device; host pointers
+ *    are an error.  There is no CPU fallback.
+ *  - Layout is the reference's NHWC (Keras channels_last).  Single-channel maps may be passed
+ *    as (B,H,W,1) or (B,H,W); any batch/row/column strides are honoured (strides in ELEMENTS,
+ *    NULL strides = contiguous), so an output can be a slot of a larger concat buffer.
+ *  - dtype: float32 (kDLFloat,32) or bfloat16 (kDLBfloat,16) -- all tensors of a call share it,
+ *    except `kernel`/`g_kernel` of the reduce entry points, which are always float32.
+ *    Arithmetic is float32 in both cases.
+ *  - The caller owns every buffer (outputs and workspace included).  The library never
+ *    allocates, frees or retains a pointer past return, never synchronises, and is safe to
+ *    capture into a CUDA Graph.  `stream` is a cudaStream_t (NULL = legacy default stream).
+ *  - Return value: BTSLPG_OK (0) or a negative BtsLpgStatus; btslpg_last_error() returns a
+ *    thread-local human-readable message for the last failure on the calling thread.
+ *  - Re-entrant; no global mutable state apart from the thread-local error string.
+ */
+#ifndef BTSLPG_H_
+#define BTSLPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BTSLPG_API __declspec(dllexport)
+#else
+#define BTSLPG_API __attribute__((visibility("default")))
+#endif
+
+#define BTSLPG_VERSION 100 /* 0.1.0 */
+
+/* == DLDevice */
+typedef struct {
+    int32_t device_type; /* 2 = kDLCUDA (13 = kDLCUDAManaged also accepted) */
+    int32_t device_id;
+} BtsDevice;
+
+/* == DLDataType */
+typedef struct {
+    uint8_t code;  /* 2 = kDLFloat, 4 = kDLBfloat */
+    uint8_t bits;  /* 32 or 16 */
+    uint16_t lanes; /* 1 */
+} BtsDataType;
+
+/* == DLTensor */
+typedef struct {
+    void *data;
+    BtsDevice device;
+    int32_t ndim;
+    BtsDataType dtype;
+    int64_t *shape;
+    int64_t *strides; /* in elements; NULL = compact row-major */
+    uint64_t byte_offset;
+} BtsTensor;
+
+typedef enum {
+    BTSLPG_OK = 0,
+    BTSLPG_EINVAL = -1,   /* NULL where a tensor is required, bad upratio / ds_stride */
+    BTSLPG_EDTYPE = -2,   /* dtype not float32/bfloat16, or tensors of one call disagree */
+    BTSLPG_ESHAPE = -3,   /* rank/extent mismatch, e.g. out is not (B, h*r, w*r[,1]) */
+    BTSLPG_EDEVICE = -4,  /* not a CUDA tensor / tensors on different devices */
+    BTSLPG_ELAYOUT = -5,  /* stride pattern the kernels cannot address (e.g. coef channel stride != 1) */
+    BTSLPG_EWORKSPACE = -6, /* workspace NULL or too small */
+    BTSLPG_ECUDA = -7     /* CUDA runtime error at launch (message carries cudaGetErrorString) */
+} BtsLpgStatus;
+
+BTSLPG_API int btslpg_version(void);
+BTSLPG_API const char *btslpg_last_error(void);
+BTSLPG_API const char *btslpg_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------
+ * LocalPlanarGuidance.call  -- replaces reference custom_layers.py:47-56 (with the constant of
+ * build(), custom_layers.py:30-45, held in __constant__ memory instead of a (1,H,W,3) tensor)
+ * and, when out_ds != NULL, the down-sampling Lambda of bts_decoder.py:81 / :88.
+ *
+ *   coef      (B, h, w, 3)         [phi_raw, theta_raw, dist]  (output of reduction_NxN)
+ *   out_full  (B, h*r, w*r[, 1])   depth_{r}x{r}_scaled; may be a strided concat slot (bts_decoder.py:99)
+ *   out_ds    (B, h*r/d, w*r/d[,1]) = out_full[:, ::d, ::d]; NULL to skip; d = ds_stride must divide r
+ *   upratio   r >= 1.  r in {2,4,8} with d in {0, r/2} run the vectorised kernels.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_forward(const BtsTensor *coef, int upratio, BtsTensor *out_full,
+                              BtsTensor *out_ds, int ds_stride, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gradient of the above -- replaces what TF autodiff derives from custom_layers.py:49-56 and
+ * from the strided slices bts_decoder.py:81,88.  Deterministic: the r x r patch reduction is a
+ * fixed-order in-register sum, no atomics.
+ *
+ *   g_full (B, H, W[,1]) dL/d out_full, nullable;  g_ds (B, H/d, W/d[,1]) dL/d out_ds, nullable
+ *   g_coef (B, h, w, 3)  dL/d coef (written, not accumulated)
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_backward(const BtsTensor *coef, const BtsTensor *g_full, const BtsTensor *g_ds,
+                               int upratio, int ds_stride, BtsTensor *g_coef, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Several independent LPG layers in ONE launch (e.g. the three scales of the micro-benchmark, or
+ * the three d(concat1) gradients of bts_decoder.py:99 that arrive together in backward).
+ * Semantics identical to n calls of btslpg_forward / btslpg_backward.  n <= BTSLPG_MAX_MULTI.
+ * ------------------------------------------------------------------------------------------- */
+#define BTSLPG_MAX_MULTI 4
+typedef struct {
+    const BtsTensor *coef;
+    int32_t upratio;
+    int32_t ds_stride;
+    BtsTensor *out_full;
+    BtsTensor *out_ds; /* nullable */
+} BtsLpgForwardArgs;
+
+typedef struct {
+    const BtsTensor *coef;
+    const BtsTensor *g_full; /* nullable */
+    const BtsTensor *g_ds;   /* nullable */
+    int32_t upratio;
+    int32_t ds_stride;
+    BtsTensor *g_coef;
+} BtsLpgBackwardArgs;
+
+BTSLPG_API int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream);
+BTSLPG_API int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * reduction_NxN + LocalPlanarGuidance fused -- replaces bts_decoder.py:79-81 / 86-88 / 93-94:
+ *   coef = sigmoid(Conv2D(3, 1x1, use_bias=False)(feat)) ; out_full = LPG_r(coef) ; out_ds = slice
+ *
+ *   feat     (B, h, w, C)   NHWC, channel stride 1
+ *   kernel   [C][3] float32 == the Keras HWIO kernel (1,1,C,3) squeezed (any of ndim 2 or 4)
+ *   coef_out (B, h, w, 3)   the sigmoid output, saved for backward (and for callers that need
+ *                           the reduction tensor itself); required
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_reduce_forward(const BtsTensor *feat, const BtsTensor *kernel, int upratio,
+                                     BtsTensor *coef_out, BtsTensor *out_full, BtsTensor *out_ds,
+                                     int ds_stride, void *stream);
+
+/* Gradient of the fused op (TF autodiff of bts_decoder.py:79-81 etc.):
+ *   g_coef = LPG backward ; dz = g_coef * coef * (1 - coef)
+ *   g_feat[b,i,j,c] = sum_k dz[b,i,j,k] * kernel[c,k]            (B,h,w,C), nullable to skip
+ *   g_kernel[c,k]   = sum_{b,i,j} feat[b,i,j,c] * dz[b,i,j,k]    [C][3] float32, nullable to skip
+ * g_kernel is reduced deterministically: per-CTA partial sums in `workspace`, summed in CTA
+ * order by the last CTA to finish (no float atomics).  g_kernel may point into a flat gradient
+ * bucket that is handed to ncclAllReduce afterwards (data-parallel training).
+ * g_coef_out (B,h,w,3), nullable, additionally receives the LPG coefficient gradient.
+ * workspace: btslpg_reduce_backward_workspace_bytes(npix, C) bytes of device memory; contents
+ * need no initialisation beyond a one-time zeroing of its first 256 bytes (done by
+ * the caller once after allocation; the kernel leaves them zero on exit).
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API size_t btslpg_reduce_backward_workspace_bytes(int64_t npix, int channels);
+BTSLPG_API int btslpg_reduce_backward(const BtsTensor *feat, const BtsTensor *kernel, const BtsTensor *coef,
+                                      const BtsTensor *g_full, const BtsTensor *g_ds, int upratio,
+                                      int ds_stride, BtsTensor *g_feat, BtsTensor *g_kernel,
+                                      BtsTensor *g_coef_out, void *workspace, size_t workspace_bytes,
+                                      void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
+ * through this library (process-wide) since the last reset, and the name of the
+ * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API uint64_t btslpg_launch_count(void);
+BTSLPG_API void btslpg_reset_launch_count(void);
+BTSLPG_API const char *btslpg_last_kernel(void);
+
+/* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default). */
+BTSLPG_API void btslpg_set_block_threads(int fwd_threads, int bwd_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTSLPG_H_ */
