@@ -1,0 +1,128 @@
+"""CPU tests of the boundary: the shared library loads, exports every symbol include/btslpg.h
+declares, validates arguments without touching a GPU, and the Python surface mirrors the
+reference layer protocol.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import bts_fully_tf_b200 as pkg
+from bts_fully_tf_b200 import _cabi, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_cabi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _cabi.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "btslpg.h")).read()
+    return sorted(set(re.findall(r"BTSLPG_API[^;(]*?\b(btslpg_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libbtslpg.so does not export %s" % n
+    assert sorted(_cabi.SYMBOLS) == names, "ctypes table and header disagree"
+
+
+def test_version_and_strings(lib):
+    assert lib.btslpg_version() == 100
+    assert lib.btslpg_status_string(0) == b"ok"
+    assert b"CUDA" in lib.btslpg_status_string(-7)
+
+
+def test_bts_tensor_is_dltensor_layout():
+    assert ctypes.sizeof(_cabi.BtsTensor) == 48
+    assert _cabi.BtsTensor.data.offset == 0 and _cabi.BtsTensor.device.offset == 8
+    assert _cabi.BtsTensor.ndim.offset == 16 and _cabi.BtsTensor.dtype.offset == 20
+    assert _cabi.BtsTensor.shape.offset == 24 and _cabi.BtsTensor.strides.offset == 32
+    assert _cabi.BtsTensor.byte_offset.offset == 40
+
+
+def test_dlpack_capsule_is_borrowed_zero_copy():
+    t = torch.arange(24, dtype=torch.float32).reshape(1, 2, 4, 3)
+    ref = _cabi.from_dlpack_capsule(torch.utils.dlpack.to_dlpack(t))
+    assert ref.struct.data == t.data_ptr() and ref.struct.ndim == 4
+    assert [ref.struct.shape[k] for k in range(4)] == [1, 2, 4, 3]
+    assert (ref.struct.dtype.code, ref.struct.dtype.bits) == (2, 32)
+    r2 = _cabi.as_ref(t)
+    assert r2.struct.data == t.data_ptr() and [r2.struct.strides[k] for k in range(4)] == [24, 12, 3, 1]
+
+
+def test_host_tensors_are_rejected_not_computed(lib):
+    """No CPU fallback: a host tensor is an error raised by the library itself."""
+    coef = torch.rand(1, 2, 2, 3)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ops.lpg_forward(coef, 8)
+    with pytest.raises(ValueError, match="not a CUDA tensor"):
+        ops.lpg_backward(coef, torch.rand(1, 16, 16, 1), None, 8)
+    with pytest.raises(ValueError, match="not a CUDA tensor"):
+        ops.reduce_lpg_forward(torch.rand(1, 2, 2, 32), torch.rand(32, 3), 8)
+
+
+def test_argument_validation_without_gpu(lib):
+    def fake_cuda(t):
+        ref = _cabi.from_torch(t)
+        ref.struct.device.device_type = 2       # pretend; validation fails before any launch
+        return ref
+    coef = fake_cuda(torch.rand(1, 2, 2, 4))
+    out = fake_cuda(torch.rand(1, 16, 16, 1))
+    assert lib.btslpg_forward(coef.ptr, 8, out.ptr, None, 0, None) == -3          # last dim must be 3
+    assert b"[phi, theta, dist]" in lib.btslpg_last_error()
+    coef = fake_cuda(torch.rand(1, 2, 2, 3))
+    bad = fake_cuda(torch.rand(1, 16, 15, 1))
+    assert lib.btslpg_forward(coef.ptr, 8, bad.ptr, None, 0, None) == -3
+    assert lib.btslpg_forward(coef.ptr, 0, out.ptr, None, 0, None) == -1          # upratio
+    ds = fake_cuda(torch.rand(1, 4, 4, 1))
+    assert lib.btslpg_forward(coef.ptr, 8, out.ptr, ds.ptr, 3, None) == -1        # ds stride must divide r
+    half = fake_cuda(torch.rand(1, 2, 2, 3).half())
+    assert lib.btslpg_forward(half.ptr, 8, out.ptr, None, 0, None) == -2          # fp16 unsupported
+    out_bf = fake_cuda(torch.rand(1, 16, 16, 1).bfloat16())
+    assert lib.btslpg_forward(coef.ptr, 8, out_bf.ptr, None, 0, None) == -2       # mixed dtypes
+    assert lib.btslpg_forward(None, 8, out.ptr, None, 0, None) == -1
+    assert lib.btslpg_backward(coef.ptr, out.ptr, None, 8, 0, None, None) == -1   # g_coef NULL
+    assert lib.btslpg_forward_multi(None, 0, None) == -1
+    assert lib.btslpg_reduce_backward_workspace_bytes(2457600, 64) >= 256 + 64 * 3 * 4
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libbtslpg.so")
+    with pytest.raises(pkg.BtsLpgLibraryMissing, match="no CPU or pure-PyTorch fallback"):
+        _cabi.load()
+
+
+def test_layer_protocol_mirrors_reference():
+    """custom_layers.py:25-61: ctor kwargs, build assert, get_config round trip, layer names."""
+    layer = pkg.LocalPlanarGuidance(upratio=8, name="depth_8x8_scaled")
+    assert layer.name == "depth_8x8_scaled" and layer.upratio == 8
+    cfg = layer.get_config()
+    assert cfg["upratio"] == 8 and cfg["name"] == "depth_8x8_scaled" and {"trainable", "dtype"} <= set(cfg)
+    again = pkg.LocalPlanarGuidance.from_config(cfg)
+    assert again.get_config() == cfg
+    with pytest.raises(AssertionError):
+        layer.build((4, 3))                                   # assert len(input_shape) > 2
+    layer.build((2, 60, 80, 3))
+    assert layer.built and layer.compute_output_shape((2, 60, 80, 3)) == (2, 480, 640, 1)
+    with pytest.raises(TypeError):
+        pkg.LocalPlanarGuidance(upratio=2, bogus=1)
+    assert list(layer.parameters()) == []                     # the layer has no weights
+    head = pkg.ReductionLPG(128, 8, ds_stride=4)
+    assert tuple(head.kernel.shape) == (1, 1, 128, 3) and head.name == "reduction_8x8"
+
+
+def test_golden_fixture_config(golden_dir):
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "lpg_r8.npz"))
+    layer = pkg.LocalPlanarGuidance(upratio=int(z["config_upratio"]), name=str(z["config_name"]))
+    assert layer.get_config()["upratio"] == 8 and layer.get_config()["name"] == "depth_8x8_scaled"
