@@ -113,7 +113,15 @@ def time_cpu_baseline(a, budget_s):
     t0 = time.perf_counter()
     run()
     one = time.perf_counter() - t0
-    reps = max(2, min(50, int(budget_s / max(one, 1e-3))))
+    # grow the sample towards the whole batch while a pass stays under ~0.6 s, then fill the budget
+    while sb < a.batch and one * 2 < 0.6:
+        sb = min(a.batch, sb * 2)
+        run, nbytes = cpu_reference_pass(sb, a.height, a.width)
+        run()
+        t0 = time.perf_counter()
+        run()
+        one = time.perf_counter() - t0
+    reps = max(3, min(200, int(budget_s / max(one, 1e-3))))
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()

@@ -66,6 +66,7 @@ SYMBOLS = {
     "btslpg_reset_launch_count": (None, []),
     "btslpg_last_kernel": (ctypes.c_char_p, []),
     "btslpg_set_block_threads": (None, [ctypes.c_int, ctypes.c_int]),
+    "btslpg_set_tuning": (None, [ctypes.c_int, ctypes.c_int]),
 }
 
 _lib = None

@@ -126,7 +126,8 @@ int check_launch(const char *what) {
 
 int block_threads(bool fwd, int r) {
     int t = fwd ? g_fwd_threads.load() : g_bwd_threads.load();
-    if (t <= 0) t = (r == 8) ? 64 : 128;
+    (void)r;
+    if (t <= 0) t = 128;
     if (t > 256) t = 256;
     t = (t + 31) / 32 * 32;
     return t;
@@ -166,34 +167,70 @@ int check_geom(LayerGeom &g, const char *coef_name, const char *full_name, const
     return 0;
 }
 
-// Largest PX (coarse pixels per thread) the vectorised kernels can use for this layer, or 0.
+// ---------------------------------------------------------------------------------------------
+// Variant selection for the vectorised kernels.  A variant is (PX coarse pixels per group, ROWS
+// patch rows per lane); candidates are tried in order of preference.  Requirements:
 //  - r in {2,4,8}; ds absent or ds stride r/2 (the reference's two cases)
-//  - coef contiguous; maps with column stride 1; every vector access aligned
-int pick_px(const LayerGeom &g) {
-    const int r = g.r, es = g.coef.esize();
-    if (r != 2 && r != 4 && r != 8) return 0;
-    if (g.has_ds && (g.d != r / 2 || r == 2)) return 0;
-    if (!is_contig_nhwc(g.coef) || !g.coef.aligned(16)) return 0;
-    if (g.has_full && g.full.sW != 1) return 0;
-    if (g.has_ds && g.ds.sW != 1) return 0;
-    const int nds = g.has_ds ? 2 : 0;
-    for (int px = 32 / (r * es); px >= 1; px /= 2) {
-        if (px < 32 / (r * es) / 4) break;                       // instantiated: PXmax, PXmax/2, PXmax/4
-        if (g.coef.W % px) continue;
-        if ((px * 3 * es) % 4) continue;                          // whole 32-bit words of coefficients
-        const int row_bytes = px * r * es;                        // 32, 16 or 8
-        if (row_bytes % 4) continue;
-        if (g.has_full) {
-            if (!g.full.aligned(row_bytes) || (g.full.sH * es) % row_bytes || (g.full.sB * es) % row_bytes) continue;
+//  - coef contiguous and 16-byte aligned; maps with column stride 1; every vector access aligned
+// ---------------------------------------------------------------------------------------------
+struct Variant {
+    int px = 0, rows = 0;
+    bool ok() const { return px > 0; }
+};
+std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0};
+
+int candidates(int dtype, int r, Variant *out) {
+    int n = 0;
+    auto add = [&](int px, int rows) { out[n].px = px; out[n].rows = rows; ++n; };
+    if (dtype == kF32) {
+        if (r == 8) {
+            const int t = g_tune_r8_rows.load();
+            if (t == 8 || t == 4 || t == 2) add(1, t);
+            add(1, 2); add(1, 4); add(1, 8);
+        } else if (r == 4) {
+            if (g_tune_r4_px.load() == 2) add(2, 4);
+            add(1, 4); add(2, 4);
+        } else if (r == 2) {
+            add(4, 2); add(2, 2); add(1, 2);
         }
-        if (g.has_ds) {
-            const int ds_bytes = px * nds * es;
-            if (ds_bytes % 4) continue;
-            if (!g.ds.aligned(ds_bytes) || (g.ds.sH * es) % ds_bytes || (g.ds.sB * es) % ds_bytes) continue;
-        }
-        return px;
+    } else {
+        if (r == 8) { add(2, 2); add(2, 4); }
+        else if (r == 4) { add(2, 4); }
+        else if (r == 2) { add(4, 2); add(2, 2); }
     }
-    return 0;
+    return n;
+}
+
+bool variant_fits(const LayerGeom &g, const Variant &v) {
+    const int r = g.r, es = g.coef.esize(), px = v.px;
+    if (g.coef.W % px) return false;
+    if ((px * 3 * es) % 4) return false;                          // whole 32-bit words of coefficients
+    const int row_bytes = px * r * es;                            // 32, 16 or 8
+    if (row_bytes % 4) return false;
+    if (g.has_full) {
+        if (!g.full.aligned(row_bytes) || (g.full.sH * es) % row_bytes || (g.full.sB * es) % row_bytes) return false;
+    }
+    if (g.has_ds) {
+        const int ds_bytes = px * 2 * es;
+        if (ds_bytes % 4) return false;
+        if (!g.ds.aligned(ds_bytes) || (g.ds.sH * es) % ds_bytes || (g.ds.sB * es) % ds_bytes) return false;
+    }
+    return true;
+}
+
+Variant pick_variant(const LayerGeom &g, bool first_only = false) {
+    const int r = g.r;
+    Variant none;
+    if (r != 2 && r != 4 && r != 8) return none;
+    if (g.has_ds && (g.d != r / 2 || r == 2)) return none;
+    if (!is_contig_nhwc(g.coef) || !g.coef.aligned(16)) return none;
+    if (g.has_full && g.full.sW != 1) return none;
+    if (g.has_ds && g.ds.sW != 1) return none;
+    Variant c[6];
+    const int n = candidates(g.coef.dtype, r, c);
+    for (int k = 0; k < (first_only ? 1 : n); ++k)
+        if (variant_fits(g, c[k])) return c[k];
+    return none;
 }
 
 template <typename T> LpgFwdParams<T> make_fwd_params(const LayerGeom &g, int px) {
@@ -204,7 +241,7 @@ template <typename T> LpgFwdParams<T> make_fwd_params(const LayerGeom &g, int px
     p.out_sB = g.full.sB; p.out_sH = g.full.sH;
     p.ds_sB = g.has_ds ? g.ds.sB : 0; p.ds_sH = g.has_ds ? g.ds.sH : 0;
     const uint32_t wg = (uint32_t)(g.coef.W / px);
-    p.units = (uint32_t)(g.coef.B * g.coef.H * wg);
+    p.groups = (uint32_t)(g.coef.B * g.coef.H * wg);
     p.wg = FastDiv(wg);
     p.h = FastDiv((uint32_t)g.coef.H);
     return p;
@@ -219,7 +256,7 @@ template <typename T> LpgBwdParams<T> make_bwd_params(const LayerGeom &g, const 
     p.gf_sB = g.has_full ? g.full.sB : 0; p.gf_sH = g.has_full ? g.full.sH : 0;
     p.gd_sB = g.has_ds ? g.ds.sB : 0; p.gd_sH = g.has_ds ? g.ds.sH : 0;
     const uint32_t wg = (uint32_t)(g.coef.W / px);
-    p.units = (uint32_t)(g.coef.B * g.coef.H * wg);
+    p.groups = (uint32_t)(g.coef.B * g.coef.H * wg);
     p.wg = FastDiv(wg);
     p.h = FastDiv((uint32_t)g.coef.H);
     return p;
@@ -247,52 +284,41 @@ template <typename T> LpgGenericParams<T> make_generic_params(const LayerGeom &g
 }
 
 // ---------------------------------------------------------------------------------------------
-// Variant dispatch for the vectorised kernels: (T, R, PX, D) are compile-time.
+// Variant dispatch: (T, R, PX, ROWS, D) are compile-time.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int R, int PX, int D>
+template <typename T, int R, int PX, int ROWS, int D>
 void launch_fwd_variant(const LpgFwdParams<T> &p, int threads, cudaStream_t st) {
-    const uint32_t blocks = (p.units + threads - 1) / threads;
-    lpg_fwd_vec_kernel<T, R, PX, D><<<blocks, threads, 0, st>>>(p);
-    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,ds%d>", ElemTraits<T>::kName, R, PX, D);
+    const uint32_t nthreads = threads_for(p.groups, R / ROWS);
+    lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
-template <typename T, int R, int PX, int D>
+template <typename T, int R, int PX, int ROWS, int D>
 void launch_bwd_variant(const LpgBwdParams<T> &p, int threads, cudaStream_t st) {
-    const uint32_t blocks = (p.units + threads - 1) / threads;
-    lpg_bwd_vec_kernel<T, R, PX, D><<<blocks, threads, 0, st>>>(p);
-    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,ds%d>", ElemTraits<T>::kName, R, PX, D);
+    const uint32_t nthreads = threads_for(p.groups, R / ROWS);
+    lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 
-#define BTSLPG_DISPATCH_PX(LAUNCH, T, R, PXMAX, D, ...)                                          \
-    do {                                                                                         \
-        if (px == (PXMAX)) LAUNCH<T, R, (PXMAX), D>(__VA_ARGS__);                                \
-        else if constexpr ((PXMAX) / 2 >= 1 && (((PXMAX) / 2) * 3 * sizeof(T)) % 4 == 0) {       \
-            if (px == (PXMAX) / 2) LAUNCH<T, R, (PXMAX) / 2, D>(__VA_ARGS__);                    \
-            else if constexpr ((PXMAX) / 4 >= 1 && (((PXMAX) / 4) * 3 * sizeof(T)) % 4 == 0) {   \
-                if (px == (PXMAX) / 4) LAUNCH<T, R, (PXMAX) / 4, D>(__VA_ARGS__);                \
-            }                                                                                    \
-        }                                                                                        \
-    } while (0)
+// every instantiated (R, PX, ROWS) per dtype
+#define BTSLPG_VARIANTS_F32(X) X(8, 1, 2) X(8, 1, 4) X(8, 1, 8) X(4, 1, 4) X(4, 2, 4) X(2, 4, 2) X(2, 2, 2) X(2, 1, 2)
+#define BTSLPG_VARIANTS_BF16(X) X(8, 2, 2) X(8, 2, 4) X(4, 2, 4) X(2, 4, 2) X(2, 2, 2)
 
-template <typename T, typename P, bool FWD> void dispatch_vec(const P &p, int r, int px, bool has_ds, int threads, cudaStream_t st) {
-#define BTSLPG_CASE(R)                                                                                       \
-    case R:                                                                                                  \
-        if (has_ds) {                                                                                        \
-            if constexpr (R > 2) {                                                                           \
-                if constexpr (FWD) BTSLPG_DISPATCH_PX(launch_fwd_variant, T, R, px_max<T>(R), R / 2, p, threads, st); \
-                else BTSLPG_DISPATCH_PX(launch_bwd_variant, T, R, px_max<T>(R), R / 2, p, threads, st);      \
-            }                                                                                                \
-        } else {                                                                                             \
-            if constexpr (FWD) BTSLPG_DISPATCH_PX(launch_fwd_variant, T, R, px_max<T>(R), 0, p, threads, st); \
-            else BTSLPG_DISPATCH_PX(launch_bwd_variant, T, R, px_max<T>(R), 0, p, threads, st);              \
-        }                                                                                                    \
-        break;
-    switch (r) {
-        BTSLPG_CASE(8)
-        BTSLPG_CASE(4)
-        BTSLPG_CASE(2)
-        default: break;
+template <typename T, typename P, bool FWD> void dispatch_vec(const P &p, int r, Variant v, bool has_ds, int threads, cudaStream_t st) {
+#define BTSLPG_TRY(R, PX, ROWS)                                                                   \
+    if (r == R && v.px == PX && v.rows == ROWS) {                                                 \
+        if (has_ds) {                                                                             \
+            if constexpr (R > 2) {                                                                \
+                if constexpr (FWD) launch_fwd_variant<T, R, PX, ROWS, R / 2>(p, threads, st);     \
+                else launch_bwd_variant<T, R, PX, ROWS, R / 2>(p, threads, st);                   \
+            }                                                                                     \
+        } else {                                                                                  \
+            if constexpr (FWD) launch_fwd_variant<T, R, PX, ROWS, 0>(p, threads, st);             \
+            else launch_bwd_variant<T, R, PX, ROWS, 0>(p, threads, st);                           \
+        }                                                                                         \
+        return;                                                                                   \
     }
-#undef BTSLPG_CASE
+    if constexpr (sizeof(T) == 4) { BTSLPG_VARIANTS_F32(BTSLPG_TRY) } else { BTSLPG_VARIANTS_BF16(BTSLPG_TRY) }
+#undef BTSLPG_TRY
 }
 
 int parse_layer_fwd(const BtsTensor *coef, int upratio, BtsTensor *out_full, BtsTensor *out_ds, int ds_stride, LayerGeom &g) {
@@ -335,11 +361,11 @@ int parse_layer_bwd(const BtsTensor *coef, const BtsTensor *g_full, const BtsTen
 template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
     const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
     if (npix == 0) return 0;
-    const int px = pick_px(g);
-    if (px > 0) {
-        auto p = make_fwd_params<T>(g, px);
+    const Variant v = pick_variant(g);
+    if (v.ok()) {
+        auto p = make_fwd_params<T>(g, v.px);
         tl_kernel[0] = 0;
-        dispatch_vec<T, LpgFwdParams<T>, true>(p, g.r, px, g.has_ds, block_threads(true, g.r), st);
+        dispatch_vec<T, LpgFwdParams<T>, true>(p, g.r, v, g.has_ds, block_threads(true, g.r), st);
         if (tl_kernel[0]) return check_launch("btslpg_forward");
     }
     auto p = make_generic_params<T>(g, nullptr);
@@ -352,12 +378,12 @@ template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
 template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaStream_t st) {
     const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
     if (npix == 0) return 0;
-    int px = pick_px(g);
-    if (px > 0 && !(is_contig_nhwc(gc) && gc.aligned(16))) px = 0;
-    if (px > 0) {
-        auto p = make_bwd_params<T>(g, gc, px);
+    Variant v = pick_variant(g);
+    if (v.ok() && !(is_contig_nhwc(gc) && gc.aligned(16))) v = Variant();
+    if (v.ok()) {
+        auto p = make_bwd_params<T>(g, gc, v.px);
         tl_kernel[0] = 0;
-        dispatch_vec<T, LpgBwdParams<T>, false>(p, g.r, px, g.has_ds, block_threads(false, g.r), st);
+        dispatch_vec<T, LpgBwdParams<T>, false>(p, g.r, v, g.has_ds, block_threads(false, g.r), st);
         if (tl_kernel[0]) return check_launch("btslpg_backward");
     }
     auto p = make_generic_params<T>(g, &gc);
@@ -367,11 +393,17 @@ template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaS
     return check_launch("btslpg_backward");
 }
 
-// multi-launch eligibility: the max-PX vector variant with the reference's ds stride (or none)
-bool multi_eligible(const LayerGeom &g) {
+// multi-launch eligibility: the default vector variant (VecCfg) with the reference's ds stride (or none)
+template <typename T> bool multi_eligible_t(const LayerGeom &g) {
     if (g.r != 2 && g.r != 4 && g.r != 8) return false;
-    const int pxm = 32 / (g.r * g.coef.esize());
-    return pick_px(g) == pxm;
+    Variant want;
+    want.px = px_max<T>(g.r);
+    want.rows = rows_default<T>(g.r);
+    if (!pick_variant(g).ok()) return false;      // layout / ds-stride preconditions
+    return variant_fits(g, want);
+}
+bool multi_eligible(const LayerGeom &g) {
+    return g.coef.dtype == kF32 ? multi_eligible_t<float>(g) : multi_eligible_t<__nv_bfloat16>(g);
 }
 
 }  // namespace
@@ -389,6 +421,15 @@ void btslpg_reset_launch_count(void) { g_launches.store(0); }
 void btslpg_set_block_threads(int fwd_threads, int bwd_threads) {
     g_fwd_threads.store(fwd_threads);
     g_bwd_threads.store(bwd_threads);
+}
+void btslpg_set_tuning(int key, int value) {
+    switch (key) {
+        case 0: g_fwd_threads.store(value); break;
+        case 1: g_bwd_threads.store(value); break;
+        case 2: g_tune_r8_rows.store(value); break;   // float32 r=8: patch rows per lane (2, 4 or 8)
+        case 3: g_tune_r4_px.store(value); break;     // float32 r=4: coarse pixels per thread (1 or 2)
+        default: break;
+    }
 }
 
 const char *btslpg_status_string(int status) {
@@ -450,9 +491,9 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
         memset(&m, 0, sizeof(m));
         uint32_t blocks = 0;
         for (int k = 0; k < n; ++k) {
-            m.layer[k] = make_fwd_params<T>(g[k], 32 / (g[k].r * (int)sizeof(T)));
+            m.layer[k] = make_fwd_params<T>(g[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (m.layer[k].units + threads - 1) / threads;
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r)) + threads - 1) / threads;
             m.block_end[k] = blocks;
         }
         m.n = n;
@@ -489,9 +530,9 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
         memset(&m, 0, sizeof(m));
         uint32_t blocks = 0;
         for (int k = 0; k < n; ++k) {
-            m.layer[k] = make_bwd_params<T>(g[k], gc[k], 32 / (g[k].r * (int)sizeof(T)));
+            m.layer[k] = make_bwd_params<T>(g[k], gc[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (m.layer[k].units + threads - 1) / threads;
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r)) + threads - 1) / threads;
             m.block_end[k] = blocks;
         }
         m.n = n;

@@ -5,21 +5,24 @@
 // (1,H,W,3) constant of unit pixel directions, sum, add eps, divide.  ~1.1 GB of HBM traffic for
 // 44-69 MB of algorithmic bytes at B=32, 480x640.
 //
-// What these kernels do: ONE thread owns PX horizontally adjacent coarse pixels.  It reads their
-// 3*PX coefficients once (vector load), decodes the plane once, and produces the whole r x r
-// patch row by row; each row of PX*r outputs is one 16- or 32-byte store, so a warp writes
-// 512-1024 contiguous bytes per instruction.  Because loops over the patch are fully unrolled and
-// every lane is at the same patch position, the direction table is read as constant-bank operands
-// of the FFMAs themselves (no table loads, no materialised (1,H,W,3) constant).  The strided
-// down-sampled copy (bts_decoder.py:81,88) is written from the same registers.
+// What these kernels do.  A "group" is PX horizontally adjacent coarse pixels; LPP = r/ROWS lanes
+// of one warp share a group, each owning ROWS rows of its r x r patches (LPP = 1 for r = 2, 4;
+// LPP = 4 for r = 8 so that every thread produces ~16 output pixels and the grid has several
+// waves of short threads).  A lane reads the group's 3*PX coefficients once, decodes the planes,
+// and produces its rows; each row of PX*r outputs is one 16- or 32-byte store, so a warp writes
+// 256-1024 contiguous bytes per row and instruction.  Loops over the patch are fully unrolled:
+// with LPP = 1 the direction table is read as constant-bank operands of the FFMAs themselves;
+// with LPP > 1 a lane keeps the weights of its rows in registers.  The (1,H,W,3) constant of the
+// reference is never materialised.  The strided down-sampled copy (bts_decoder.py:81,88) is
+// written from the same registers.
 //
-// Backward keeps the same ownership, so the r x r patch reduction of the gradient (SURVEY 8(a)
-// a6) happens entirely inside one thread in a fixed order: deterministic, no atomics, and no
-// cross-lane traffic at all.
+// Backward keeps the same ownership: the patch reduction is a fixed-order sum
+// inside each lane followed, for LPP > 1, by a fixed xor-shuffle tree over the LPP lanes:
+// deterministic, no atomics.
 //
-// Denominator:  den = w_pq * (a_p*n1 + b_q*n2 + n3) + eps   with (a_p*w_pq, b_q*w_pq, w_pq) the
-// float32 unit direction of custom_layers.py:43 -- the same value as the reference's
-// sum(pixel_dir_unit * n) + eps up to float32 rounding (2 FFMA per pixel instead of 3 FMUL/FADD+1).
+// Arithmetic:  den = w_pq * (a_p*n1 + b_q*n2 + n3) + eps   with (a_p*w_pq, b_q*w_pq, w_pq) the
+// float32 unit direction of custom_layers.py:43 -- the reference's sum(pixel_dir_unit * n) + eps
+// up to float32 rounding, in 2 FFMA per pixel; out = n4 * rcp(den) (MUFU.RCP, <= 1 ulp).
 #pragma once
 
 #include "common.cuh"
@@ -30,74 +33,224 @@ namespace btslpg {
 template <int R> struct DirTable;
 template <> struct DirTable<2> {
     static __device__ __forceinline__ float off(int p) { return c_off2[p]; }
-    static __device__ __forceinline__ float u(int k) { return c_u2[k]; }
-    static __device__ __forceinline__ float v(int k) { return c_v2[k]; }
     static __device__ __forceinline__ float w(int k) { return c_w2[k]; }
+    static __device__ __forceinline__ const float *gw() { return g_w2; }
 };
 template <> struct DirTable<4> {
     static __device__ __forceinline__ float off(int p) { return c_off4[p]; }
-    static __device__ __forceinline__ float u(int k) { return c_u4[k]; }
-    static __device__ __forceinline__ float v(int k) { return c_v4[k]; }
     static __device__ __forceinline__ float w(int k) { return c_w4[k]; }
+    static __device__ __forceinline__ const float *gw() { return g_w4; }
 };
 template <> struct DirTable<8> {
     static __device__ __forceinline__ float off(int p) { return c_off8[p]; }
-    static __device__ __forceinline__ float u(int k) { return c_u8[k]; }
-    static __device__ __forceinline__ float v(int k) { return c_v8[k]; }
     static __device__ __forceinline__ float w(int k) { return c_w8[k]; }
+    static __device__ __forceinline__ const float *gw() { return g_w8; }
 };
 
 struct Angles {
     float sp, cp, st, ct;
 };
 
-// custom_layers.py:49 -- phi = x0*2*pi ; theta = x1*pi/3 in float32, then full-precision sin/cos
-// (no fast-math intrinsics: __sinf is off by 1e-5 near 2*pi).
-__device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
-    float phi = (x0 * 2.0f) * BTSLPG_PI_F;
-    float theta = __fdiv_rn(x1 * BTSLPG_PI_F, 3.0f);
+// ------------------------------------------------------------------------------------------------
+// sin and cos of a float32 angle, accurate to < 0.6 ulp(1) (7e-8 abs) for |a| <= 1000:
+// quadrant reduction k = rint(a*2/pi) by the 1.5*2^23 trick, r = a - k*pi/2 with a two-term
+// Cody-Waite pi/2 (exact products inside the FMAs), degree-7 / degree-8 polynomials on |r| <= pi/4
+// (coefficients and the float32 error analysis: tools/fit_sincos.py), then the quadrant swap/sign.
+// ~21 instructions for both values; CUDA's sincosf costs ~2x that because of its conversions and
+// its large-argument path.  Angles outside the fast range (never produced by a sigmoid head) take
+// sincosf().
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_quadrant(float a, float &sn_out, float &cs_out) {
+    const float kf = fmaf(a, 0x1.45f306p-1f, 12582912.0f);          // a*2/pi + 1.5*2^23
+    const float q = kf - 12582912.0f;
+    const int n = __float_as_int(kf);
+    float r = fmaf(q, -0x1.921fb6p+0f, a);
+    r = fmaf(q, 0x1.777a5cp-25f, r);
+    const float s = r * r;
+    float ps = fmaf(-0x1.9ac9e4p-13f, s, 0x1.110c2ap-7f);
+    ps = fmaf(ps, s, -0x1.555552p-3f);
+    const float sn = fmaf(ps, r * s, r);
+    float pc = fmaf(0x1.9a6f38p-16f, s, -0x1.6c0e08p-10f);
+    pc = fmaf(pc, s, 0x1.55554cp-5f);
+    pc = fmaf(pc, s, -0.5f);
+    const float cs = fmaf(pc, s, 1.0f);
+    const bool swap = n & 1;
+    const float so = swap ? cs : sn;
+    const float co = swap ? sn : cs;
+    sn_out = __int_as_float(__float_as_int(so) ^ ((n << 30) & 0x80000000));
+    cs_out = __int_as_float(__float_as_int(co) ^ (((n + 1) << 30) & 0x80000000));
+}
+
+__device__ __noinline__ void decode_angles_slow(float phi, float theta, Angles &a) {
     sincosf(phi, &a.sp, &a.cp);
     sincosf(theta, &a.st, &a.ct);
 }
 
-// Expand PX decoded planes into their r x r patches and store them row by row; the strided
-// down-sampled copy (bts_decoder.py:81,88  x[:, ::d, ::d]) is written from the same registers.
-template <typename T, int R, int PX, int D>
-__device__ __forceinline__ void lpg_expand_store(const float (&n1)[PX], const float (&n2)[PX], const float (&n3)[PX],
-                                                 const float (&n4)[PX], T *orow, int64_t out_sH, T *drow, int64_t ds_sH) {
+// custom_layers.py:49 -- phi = x0*2*pi ; theta = x1*pi/3, both rounded to float32 exactly as the
+// reference rounds them: (x0*2)*pi == x0*(2*pi) bit for bit (scaling by 2 is exact), and x*pi/3 uses
+// a correctly rounded division by 3 in three instructions (q = t/3 approx, one exact residual
+// step; verified against IEEE division in tools/fit_sincos.py).
+__device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
+    const float phi = x0 * (2.0f * BTSLPG_PI_F);
+    const float t = x1 * BTSLPG_PI_F;
+    const float q0 = t * 0x1.555556p-2f;
+    const float theta = fmaf(fmaf(-3.0f, q0, t), 0x1.555556p-2f, q0);
+    if (fmaxf(fabsf(phi), fabsf(theta)) <= 1000.0f) {
+        sincos_quadrant(phi, a.sp, a.cp);
+        sincos_quadrant(theta, a.st, a.ct);
+    } else {   // huge, inf or NaN inputs: IEEE division for theta as well (the 3-instruction form assumes no overflow)
+        decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(t, 3.0f), a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direction weights of the ROWS patch rows a lane owns.
+//   LPP == 1 (ROWS == R): compile-time indices -> constant-bank operands, no registers.
+//   LPP  > 1: rows [sub*ROWS, sub*ROWS+ROWS) -> ROWS*R weights in registers (vector loads from the
+//             global copy of the table, L1-resident) and a per-lane row offset.
+// ------------------------------------------------------------------------------------------------
+template <int R, int ROWS> struct LaneDirs {
+    float wl[ROWS][R];
+    float a0;   // row offset of the lane's first row minus off(0)
+    __device__ __forceinline__ void init(int sub) {
+        a0 = (float)(sub * ROWS) * (1.0f / R);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(DirTable<R>::gw() + sub * ROWS * R);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&wl[0][0]);
+#pragma unroll
+        for (int i = 0; i < ROWS * R; i += 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + i));
+            dst[i] = v.x; dst[i + 1] = v.y; dst[i + 2] = v.z; dst[i + 3] = v.w;
+        }
+    }
+    __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
+    __device__ __forceinline__ float w(int k, int q) const { return wl[k][q]; }
+};
+template <int R> struct LaneDirs<R, R> {
+    __device__ __forceinline__ void init(int) {}
+    __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k); }
+    __device__ __forceinline__ float w(int k, int q) const { return DirTable<R>::w(k * R + q); }
+};
+
+// does patch row (sub*ROWS + k) carry a down-sampled sample (row % D == 0)?
+template <int ROWS, int D> __device__ __forceinline__ bool ds_row(int sub, int k) {
+    if constexpr (D == 0) return false;
+    else if constexpr (ROWS % D == 0) return k % D == 0;
+    else return k == 0 && (sub * ROWS) % D == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expand PX decoded planes into rows [sub*ROWS, sub*ROWS+ROWS) of their r x r patches and store
+// them; the down-sampled copy x[:, ::d, ::d] (bts_decoder.py:81,88) comes from the same registers.
+// orow / drow point at patch row 0 of the group (row stride out_sH / ds_sH).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, int sub, const float (&n1)[PX], const float (&n2)[PX],
+                                                 const float (&n3)[PX], const float (&n4)[PX], T *orow, int64_t out_sH, T *drow,
+                                                 int64_t ds_sH) {
     using Tab = DirTable<R>;
     constexpr int NDS = D ? R / D : 0;
 #pragma unroll
-    for (int p = 0; p < R; ++p) {
+    for (int k = 0; k < ROWS; ++k) {
         float o[PX * R];
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
-            const float A = fmaf(Tab::off(p), n1[px], n3[px]);            // a_p*n1 + n3   (rows pair with n1)
+            const float A = fmaf(dir.a(k), n1[px], n3[px]);               // a_p*n1 + n3   (rows pair with n1)
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const float s = fmaf(Tab::off(q), n2[px], A);            // + b_q*n2      (columns pair with n2)
-                const float den = fmaf(Tab::w(p * R + q), s, BTSLPG_EPS_F); // custom_layers.py:55
+                const float den = fmaf(dir.w(k, q), s, BTSLPG_EPS_F);    // custom_layers.py:55
                 o[px * R + q] = n4[px] * rcp_approx(den);                // custom_layers.py:56
             }
         }
+        const int p = sub * ROWS + k;
         store_elems<T, PX * R>(orow + (int64_t)p * out_sH, o);
         if constexpr (D > 0) {
-            if (p % D == 0) {
-                if (drow) {
-                    float dsv[PX * NDS];
+            if (drow && ds_row<ROWS, D>(sub, k)) {
+                float dsv[PX * NDS];
+#pragma unroll
+                for (int px = 0; px < PX; ++px)
+#pragma unroll
+                    for (int qq = 0; qq < NDS; ++qq) dsv[px * NDS + qq] = o[px * R + qq * D];
+                store_elems<T, PX * NDS>(drow + (int64_t)(p / D) * ds_sH, dsv);
+            }
+        }
+    }
+}
+
+// Gather G = g_full + scatter(g_ds) for rows [sub*ROWS, sub*ROWS+ROWS) of the patches of PX coarse pixels.
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, int64_t gf_sH, const T *drow, int64_t gd_sH, float (&G)[ROWS][PX * R]) {
+    constexpr int NDS = D ? R / D : 0;
+    if (grow) {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) load_elems<T, PX * R>(grow + (int64_t)(sub * ROWS + k) * gf_sH, G[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k)
+#pragma unroll
+            for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
+    }
+    if constexpr (D > 0) {
+        if (drow) {
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                if (ds_row<ROWS, D>(sub, k)) {
+                    float t[PX * NDS];
+                    load_elems<T, PX * NDS>(drow + (int64_t)((sub * ROWS + k) / D) * gd_sH, t);
 #pragma unroll
                     for (int px = 0; px < PX; ++px)
 #pragma unroll
-                        for (int qq = 0; qq < NDS; ++qq) dsv[px * NDS + qq] = o[px * R + qq * D];
-                    store_elems<T, PX * NDS>(drow + (int64_t)(p / D) * ds_sH, dsv);
+                        for (int qq = 0; qq < NDS; ++qq) G[k][px * R + qq * D] += t[px * NDS + qq];
                 }
             }
         }
     }
 }
 
+// Partial sums of one lane over its ROWS rows of the patch of coarse pixel `px`:
+//   u = G/den ; acc[3] += u ; z = u/den * w ; acc[2] += z ; acc[1] += b_q z ; acc[0] += a_p * (row sum of z)
+// so that, after the lanes of a group are added, g1..g3 = -n4 * acc[0..2] and g4 = acc[3].
+template <int R, int PX, int ROWS>
+__device__ __forceinline__ void lpg_patch_partial(const LaneDirs<R, ROWS> &dir, const float (&G)[ROWS][PX * R], int px, float n1,
+                                                  float n2, float n3, float (&acc)[4]) {
+    using Tab = DirTable<R>;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {            // fixed order: columns inside a row, then rows
+        const float ap = dir.a(k);
+        const float A = fmaf(ap, n1, n3);
+        float r2 = 0.f, r3 = 0.f, r4 = 0.f;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const float s = fmaf(Tab::off(q), n2, A);
+            const float w = dir.w(k, q);
+            const float inv = rcp_approx(fmaf(w, s, BTSLPG_EPS_F));
+            const float u = G[k][px * R + q] * inv;
+            const float z = (u * inv) * w;
+            r4 += u;
+            r3 += z;
+            r2 = fmaf(z, Tab::off(q), r2);
+        }
+        acc[0] = fmaf(ap, r3, acc[0]);
+        acc[1] += r2;
+        acc[2] += r3;
+        acc[3] += r4;
+    }
+}
+
+// acc (summed over the whole patch) -> d loss / d (x0, x1, x2)
+__device__ __forceinline__ void lpg_finish_grad(const Angles &a, float n4, const float (&acc)[4], float *gout) {
+    const float m = -n4;
+    const float g1 = acc[0] * m, g2 = acc[1] * m, g3 = acc[2] * m;
+    const float gph = a.st * (g2 * a.cp - g1 * a.sp);
+    const float gth = a.ct * (g1 * a.cp + g2 * a.sp) - g3 * a.st;
+    gout[0] = (2.0f * BTSLPG_PI_F) * gph;
+    gout[1] = (BTSLPG_PI_F / 3.0f) * gth;
+    gout[2] = acc[3];
+}
+
 // ------------------------------------------------------------------------------------------------
-// Vectorised forward.  units = B*h*(w/PX); unit -> (b, i, jg); contiguous coef.
+// Vectorised kernels.  groups = B*h*(w/PX); a warp covers 32/LPP consecutive groups.
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct LpgFwdParams {
     const T *coef;
@@ -105,19 +258,44 @@ template <typename T> struct LpgFwdParams {
     T *ds;                 // nullable
     int64_t out_sB, out_sH; // element strides of out (column stride 1)
     int64_t ds_sB, ds_sH;
-    uint32_t units;
-    FastDiv wg, h;          // units per coarse row, coarse rows per image
+    uint32_t groups;
+    FastDiv wg, h;          // groups per coarse row, coarse rows per image
 };
 
-template <typename T, int R, int PX, int D>
-__device__ __forceinline__ void lpg_fwd_unit(const LpgFwdParams<T> &prm, uint32_t unit) {
+template <typename T> struct LpgBwdParams {
+    const T *coef;
+    const T *g_full;  // nullable
+    const T *g_ds;    // nullable
+    T *g_coef;
+    int64_t gf_sB, gf_sH;
+    int64_t gd_sB, gd_sH;
+    uint32_t groups;
+    FastDiv wg, h;
+};
+
+template <int R, int ROWS> struct Split {
+    static constexpr int LPP = R / ROWS;      // lanes per group
+    static constexpr int GPW = 32 / LPP;      // groups per warp
+    static_assert(R % ROWS == 0 && (LPP == 1 || LPP == 2 || LPP == 4), "bad row split");
+};
+
+// `slot` = index of this thread among the threads of its layer (block-uniform base + threadIdx)
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
+    using S = Split<R, ROWS>;
     constexpr int NDS = D ? R / D : 0;
+    const int lane = slot & 31;
+    const int sub = S::LPP == 1 ? 0 : lane / S::GPW;
+    const uint32_t group = S::LPP == 1 ? slot : (slot >> 5) * S::GPW + (lane % S::GPW);
+    if (group >= prm.groups) return;
     uint32_t row, jg, b, i;
-    prm.wg.divmod(unit, row, jg);
+    prm.wg.divmod(group, row, jg);
     prm.h.divmod(row, b, i);
 
     float c[PX * 3];
-    load_elems<T, PX * 3, 4>(prm.coef + (size_t)unit * (PX * 3), c);
+    load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);
 
     float n1[PX], n2[PX], n3[PX], n4[PX];
 #pragma unroll
@@ -129,131 +307,93 @@ __device__ __forceinline__ void lpg_fwd_unit(const LpgFwdParams<T> &prm, uint32_
         n3[px] = a.ct;
         n4[px] = c[3 * px + 2];
     }
-
     T *orow = prm.out + (int64_t)b * prm.out_sB + (int64_t)(i * R) * prm.out_sH + (size_t)jg * (PX * R);
     T *drow = nullptr;
     if constexpr (D > 0) {
         if (prm.ds) drow = prm.ds + (int64_t)b * prm.ds_sB + (int64_t)(i * NDS) * prm.ds_sH + (size_t)jg * (PX * NDS);
     }
-    lpg_expand_store<T, R, PX, D>(n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+    lpg_expand_store<T, R, PX, ROWS, D>(dir, sub, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
 }
 
-template <typename T, int R, int PX, int D>
-__global__ void __launch_bounds__(256) lpg_fwd_vec_kernel(const __grid_constant__ LpgFwdParams<T> prm) {
-    const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (unit < prm.units) lpg_fwd_unit<T, R, PX, D>(prm, unit);
-}
-
-// Gather G = g_full + scatter(g_ds) for the r x r patches of PX coarse pixels into registers.
-template <typename T, int R, int PX, int D>
-__device__ __forceinline__ void lpg_load_patch(const T *grow, int64_t gf_sH, const T *drow, int64_t gd_sH, float (&G)[R][PX * R]) {
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot) {
+    using S = Split<R, ROWS>;
     constexpr int NDS = D ? R / D : 0;
-    if (grow) {
-#pragma unroll
-        for (int p = 0; p < R; ++p) load_elems<T, PX * R>(grow + (int64_t)p * gf_sH, G[p]);
+    const int lane = slot & 31;
+    const int sub = S::LPP == 1 ? 0 : lane / S::GPW;
+    const uint32_t group = S::LPP == 1 ? slot : (slot >> 5) * S::GPW + (lane % S::GPW);
+    const bool active = group < prm.groups;
+    if (S::LPP == 1 && !active) return;            // with LPP > 1 every lane takes part in the shuffles
+
+    float G[ROWS][PX * R];
+    float c[PX * 3];
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);
+    if (active) {
+        uint32_t row, jg, b, i;
+        prm.wg.divmod(group, row, jg);
+        prm.h.divmod(row, b, i);
+        // issue every load of the lane first (memory-level parallelism), then compute
+        const T *grow = prm.g_full ? prm.g_full + (int64_t)b * prm.gf_sB + (int64_t)(i * R) * prm.gf_sH + (size_t)jg * (PX * R) : nullptr;
+        const T *drow = nullptr;
+        if constexpr (D > 0) {
+            if (prm.g_ds) drow = prm.g_ds + (int64_t)b * prm.gd_sB + (int64_t)(i * NDS) * prm.gd_sH + (size_t)jg * (PX * NDS);
+        }
+        load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
+        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, G);
     } else {
 #pragma unroll
-        for (int p = 0; p < R; ++p)
+        for (int e = 0; e < PX * 3; ++e) c[e] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < PX * R; ++k) G[p][k] = 0.0f;
+        for (int k = 0; k < ROWS; ++k)
+#pragma unroll
+            for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
     }
-    if constexpr (D > 0) {
-        if (drow) {
-            float t[NDS][PX * NDS];
-#pragma unroll
-            for (int pp = 0; pp < NDS; ++pp) load_elems<T, PX * NDS>(drow + (int64_t)pp * gd_sH, t[pp]);
-#pragma unroll
-            for (int pp = 0; pp < NDS; ++pp)
-#pragma unroll
-                for (int px = 0; px < PX; ++px)
-#pragma unroll
-                    for (int qq = 0; qq < NDS; ++qq) G[pp * D][px * R + qq * D] += t[pp][px * NDS + qq];
-        }
-    }
-}
-
-// Fixed-order reduction of one r x r patch into the three coefficient gradients:
-// columns inside a row, then rows -- all in one thread, so no shuffles and no atomics are needed.
-template <int R, int PX>
-__device__ __forceinline__ void lpg_reduce_patch(const float (&G)[R][PX * R], int px, float x0, float x1, float x2, float *gout) {
-    using Tab = DirTable<R>;
-    Angles a;
-    decode_angles(x0, x1, a);
-    const float n1 = a.st * a.cp, n2 = a.st * a.sp, n3 = a.ct, n4 = x2;
-    float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
-#pragma unroll
-    for (int p = 0; p < R; ++p) {
-        const float A = fmaf(Tab::off(p), n1, n3);
-        float r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int k = p * R + q;
-            const float s = fmaf(Tab::off(q), n2, A);
-            const float den = fmaf(Tab::w(k), s, BTSLPG_EPS_F);
-            const float inv = rcp_approx(den);
-            const float u = G[p][px * R + q] * inv;
-            const float tq = u * inv;
-            r4 += u;
-            r1 = fmaf(tq, Tab::u(k), r1);
-            r2 = fmaf(tq, Tab::v(k), r2);
-            r3 = fmaf(tq, Tab::w(k), r3);
-        }
-        g1 += r1; g2 += r2; g3 += r3; g4 += r4;
-    }
-    const float m = -n4;
-    g1 *= m; g2 *= m; g3 *= m;
-    const float gph = a.st * (g2 * a.cp - g1 * a.sp);
-    const float gth = a.ct * (g1 * a.cp + g2 * a.sp) - g3 * a.st;
-    gout[0] = (2.0f * BTSLPG_PI_F) * gph;
-    gout[1] = (BTSLPG_PI_F / 3.0f) * gth;
-    gout[2] = g4;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Vectorised backward (SURVEY 8(a) a6 + a9).
-//   G = g_full + scatter(g_ds);  u = G/den;  g4 = sum u;  tq = u/den
-//   g1 = -n4 sum tq*u_pq ; g2 = -n4 sum tq*v_pq ; g3 = -n4 sum tq*w_pq
-//   d/dx0 = 2pi * st*(g2*cp - g1*sp) ; d/dx1 = (pi/3) * (ct*(g1*cp + g2*sp) - g3*st) ; d/dx2 = g4
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct LpgBwdParams {
-    const T *coef;
-    const T *g_full;  // nullable
-    const T *g_ds;    // nullable
-    T *g_coef;
-    int64_t gf_sB, gf_sH;
-    int64_t gd_sB, gd_sH;
-    uint32_t units;
-    FastDiv wg, h;
-};
-
-template <typename T, int R, int PX, int D>
-__device__ __forceinline__ void lpg_bwd_unit(const LpgBwdParams<T> &prm, uint32_t unit) {
-    constexpr int NDS = D ? R / D : 0;
-    uint32_t row, jg, b, i;
-    prm.wg.divmod(unit, row, jg);
-    prm.h.divmod(row, b, i);
-
-    // issue every load of the patch first (memory-level parallelism), then compute
-    float G[R][PX * R];
-    const T *grow = prm.g_full ? prm.g_full + (int64_t)b * prm.gf_sB + (int64_t)(i * R) * prm.gf_sH + (size_t)jg * (PX * R) : nullptr;
-    const T *drow = nullptr;
-    if constexpr (D > 0) {
-        if (prm.g_ds) drow = prm.g_ds + (int64_t)b * prm.gd_sB + (int64_t)(i * NDS) * prm.gd_sH + (size_t)jg * (PX * NDS);
-    }
-    float c[PX * 3];
-    load_elems<T, PX * 3, 4>(prm.coef + (size_t)unit * (PX * 3), c);
-    lpg_load_patch<T, R, PX, D>(grow, prm.gf_sH, drow, prm.gd_sH, G);
 
     float gout[PX * 3];
 #pragma unroll
-    for (int px = 0; px < PX; ++px) lpg_reduce_patch<R, PX>(G, px, c[3 * px], c[3 * px + 1], c[3 * px + 2], &gout[3 * px]);
-    store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)unit * (PX * 3), gout);
+    for (int px = 0; px < PX; ++px) {
+        Angles a;
+        decode_angles(c[3 * px], c[3 * px + 1], a);
+        float acc[4];
+        lpg_patch_partial<R, PX, ROWS>(dir, G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
+        if constexpr (S::LPP > 1) {                 // fixed xor tree over the lanes that share the group
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                for (int m = S::GPW; m < 32; m <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
+            }
+        }
+        lpg_finish_grad(a, c[3 * px + 2], acc, &gout[3 * px]);
+    }
+    if (active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
 }
 
-template <typename T, int R, int PX, int D>
+template <typename T, int R, int PX, int ROWS, int D>
+__global__ void __launch_bounds__(256) lpg_fwd_vec_kernel(const __grid_constant__ LpgFwdParams<T> prm) {
+    lpg_fwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <typename T, int R, int PX, int ROWS, int D>
 __global__ void __launch_bounds__(256) lpg_bwd_vec_kernel(const __grid_constant__ LpgBwdParams<T> prm) {
-    const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (unit < prm.units) lpg_bwd_unit<T, R, PX, D>(prm, unit);
+    lpg_bwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// default (PX, ROWS) of the vectorised variants: every thread produces 16-32 output pixels
+template <typename T> __host__ __device__ constexpr int px_max(int r) {
+    return sizeof(T) == 4 ? (r == 2 ? 4 : 1) : (r == 2 ? 4 : 2);
+}
+template <typename T> __host__ __device__ constexpr int rows_default(int r) {
+    return r == 8 ? 2 : r;
+}
+template <typename T, int R> struct VecCfg {
+    static constexpr int PX = px_max<T>(R);
+    static constexpr int ROWS = rows_default<T>(R);
+    static constexpr int LPP = R / ROWS;
+};
+// threads needed for `groups` groups
+__host__ __device__ inline uint32_t threads_for(uint32_t groups, int lpp) {
+    const uint32_t gpw = 32 / lpp;
+    return ((groups + gpw - 1) / gpw) * 32;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +401,6 @@ __global__ void __launch_bounds__(256) lpg_bwd_vec_kernel(const __grid_constant_
 // layer; the variant switch is block-uniform.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxMulti = 4;
-template <typename T> __host__ __device__ constexpr int px_max(int r) { return 32 / (r * (int)sizeof(T)); }
 
 template <typename T> struct LpgFwdMulti {
     LpgFwdParams<T> layer[kMaxMulti];
@@ -284,12 +423,11 @@ __global__ void __launch_bounds__(256) lpg_fwd_multi_kernel(const __grid_constan
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgFwdParams<T> &prm = m.layer[l];
-    const uint32_t unit = (blockIdx.x - first) * blockDim.x + threadIdx.x;
-    if (unit >= prm.units) return;
+    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_fwd_unit<T, 8, px_max<T>(8), 4>(prm, unit); break;
-        case 4: lpg_fwd_unit<T, 4, px_max<T>(4), 2>(prm, unit); break;
-        default: lpg_fwd_unit<T, 2, px_max<T>(2), 0>(prm, unit); break;
+        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8>::PX, VecCfg<T, 8>::ROWS, 4>(prm, slot); break;
+        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4>::PX, VecCfg<T, 4>::ROWS, 2>(prm, slot); break;
+        default: lpg_fwd_thread<T, 2, VecCfg<T, 2>::PX, VecCfg<T, 2>::ROWS, 0>(prm, slot); break;
     }
 }
 
@@ -301,30 +439,29 @@ __global__ void __launch_bounds__(256) lpg_bwd_multi_kernel(const __grid_constan
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgBwdParams<T> &prm = m.layer[l];
-    const uint32_t unit = (blockIdx.x - first) * blockDim.x + threadIdx.x;
-    if (unit >= prm.units) return;
+    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_bwd_unit<T, 8, px_max<T>(8), 4>(prm, unit); break;
-        case 4: lpg_bwd_unit<T, 4, px_max<T>(4), 2>(prm, unit); break;
-        default: lpg_bwd_unit<T, 2, px_max<T>(2), 0>(prm, unit); break;
+        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8>::PX, VecCfg<T, 8>::ROWS, 4>(prm, slot); break;
+        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4>::PX, VecCfg<T, 4>::ROWS, 2>(prm, slot); break;
+        default: lpg_bwd_thread<T, 2, VecCfg<T, 2>::PX, VecCfg<T, 2>::ROWS, 0>(prm, slot); break;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Generic kernels: any up-ratio r >= 1, any ds stride d | r, any element strides (e.g. an NHWC
 // concat slot whose column stride is the channel count).  One thread per coarse pixel, scalar
-// accesses.  Same arithmetic as the vectorised kernels (the direction is recomputed with the
-// float32 op sequence of custom_layers.py:38-43), so results are bit-identical between paths.
+// accesses.  Same per-pixel arithmetic as the vectorised kernels (the direction is recomputed
+// with the float32 op sequence of custom_layers.py:38-43), so the forward is bit-identical between
+// the two paths; the backward differs only in the association of the patch sum.
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct LpgGenericParams {
     const T *coef;
     int64_t c_sB, c_sH, c_sW, c_sC;
-    // forward
+    // forward: out / ds ; backward: o_s* describe g_full and d_s* describe g_ds
     T *out;
     T *ds;
     int64_t o_sB, o_sH, o_sW;
     int64_t d_sB, d_sH, d_sW;
-    // backward
     const T *g_full;
     const T *g_ds;
     T *g_coef;
@@ -374,38 +511,37 @@ template <typename T> __global__ void __launch_bounds__(128) lpg_bwd_generic_ker
     decode_angles(load1(c), load1(c + prm.c_sC), a);
     const float n1 = a.st * a.cp, n2 = a.st * a.sp, n3 = a.ct, n4 = load1(c + 2 * prm.c_sC);
     const int r = prm.r, d = prm.d;
-    float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int p = 0; p < r; ++p) {
         const float ap = dir_offset(p, r);
         const float A = fmaf(ap, n1, n3);
-        float r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+        float r2 = 0.f, r3 = 0.f, r4 = 0.f;
         for (int q = 0; q < r; ++q) {
             const float bq = dir_offset(q, r);
-            const float wpq = dir_w(ap, bq);
+            const float w = dir_w(ap, bq);
             float G = 0.f;
             if (prm.g_full) G = load1(prm.g_full + b * prm.o_sB + (i * r + p) * prm.o_sH + (j * r + q) * prm.o_sW);
             if (prm.g_ds && d > 0 && p % d == 0 && q % d == 0)
                 G += load1(prm.g_ds + b * prm.d_sB + ((i * r + p) / d) * prm.d_sH + ((j * r + q) / d) * prm.d_sW);
             const float s = fmaf(bq, n2, A);
-            const float den = fmaf(wpq, s, BTSLPG_EPS_F);
-            const float inv = rcp_approx(den);
+            const float inv = rcp_approx(fmaf(w, s, BTSLPG_EPS_F));
             const float u = G * inv;
-            const float tq = u * inv;
+            const float z = (u * inv) * w;
             r4 += u;
-            r1 = fmaf(tq, ap * wpq, r1);
-            r2 = fmaf(tq, bq * wpq, r2);
-            r3 = fmaf(tq, wpq, r3);
+            r3 += z;
+            r2 = fmaf(z, bq, r2);
         }
-        g1 += r1; g2 += r2; g3 += r3; g4 += r4;
+        acc[0] = fmaf(ap, r3, acc[0]);
+        acc[1] += r2;
+        acc[2] += r3;
+        acc[3] += r4;
     }
-    const float m = -n4;
-    g1 *= m; g2 *= m; g3 *= m;
-    const float gph = a.st * (g2 * a.cp - g1 * a.sp);
-    const float gth = a.ct * (g1 * a.cp + g2 * a.sp) - g3 * a.st;
+    float gout[3];
+    lpg_finish_grad(a, n4, acc, gout);
     T *o = prm.g_coef + b * prm.gc_sB + i * prm.gc_sH + j * prm.gc_sW;
-    store1(o, (2.0f * BTSLPG_PI_F) * gph);
-    store1(o + prm.gc_sC, (BTSLPG_PI_F / 3.0f) * gth);
-    store1(o + 2 * prm.gc_sC, g4);
+    store1(o, gout[0]);
+    store1(o + prm.gc_sC, gout[1]);
+    store1(o + 2 * prm.gc_sC, gout[2]);
 }
 
 }  // namespace btslpg

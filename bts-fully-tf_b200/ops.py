@@ -239,3 +239,8 @@ def last_kernel():
 
 def set_block_threads(fwd=0, bwd=0):
     load().btslpg_set_block_threads(int(fwd), int(bwd))
+
+
+def set_tuning(key, value):
+    """Experiment knobs of the library (see include/btslpg.h: btslpg_set_tuning)."""
+    load().btslpg_set_tuning(int(key), int(value))

@@ -174,8 +174,12 @@ BTSLPG_API uint64_t btslpg_launch_count(void);
 BTSLPG_API void btslpg_reset_launch_count(void);
 BTSLPG_API const char *btslpg_last_kernel(void);
 
-/* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default). */
+/* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default).
+ * btslpg_set_tuning keys: 0 forward block threads, 1 backward block threads, 2 float32 r=8 patch rows
+ * per lane (2/4/8), 3 float32 r=4 coarse pixels per thread (1/2).  Results do not depend on them,
+ * except that the r=8 backward sum is associated per lane group (still deterministic). */
 BTSLPG_API void btslpg_set_block_threads(int fwd_threads, int bwd_threads);
+BTSLPG_API void btslpg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
 }

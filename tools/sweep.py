@@ -52,8 +52,14 @@ def main():
         gen = torch.Generator(device=dev).manual_seed(0)
         sets = [DeviceSet(B, H, W, dtype, dev, generator=gen) for _ in range(4)]
         fwd_b, bwd_b, per = algorithmic_bytes(B, H, W, es)
-        for threads in (64, 128, 256):
+        configs = [(64, 0, 0), (128, 0, 0), (256, 0, 0)]
+        if name == "f32":
+            configs += [(128, 8, 0), (128, 4, 0), (128, 0, 2)]      # r8 rows-per-lane 8 / 4, r4 px 2
+        for threads, r8rows, r4px in configs:
             ops.set_block_threads(threads, threads)
+            ops.set_tuning(2, r8rows)
+            ops.set_tuning(3, r4px)
+            tag_cfg = "t%d" % threads + ("_r8rows%d" % r8rows if r8rows else "") + ("_r4px%d" % r4px if r4px else "")
             for idx, (r, fb, bb) in enumerate(per):
                 def f(s, idx=idx):
                     L = s.layers[idx]
@@ -64,14 +70,16 @@ def main():
                     ops.lpg_backward(L["coef"], L["g_full"], L["g_ds"], L["upratio"], L["ds_stride"], g_coef=L["g_coef"])
                 for tag, fn, nb in (("fwd", f, fb), ("bwd", b, bb)):
                     us = timed(fn, sets)
-                    out["points"].append(dict(dtype=name, kernel="%s_r%d" % (tag, r), threads=threads, us=round(us, 2),
+                    out["points"].append(dict(dtype=name, kernel="%s_r%d" % (tag, r), threads=tag_cfg, variant=ops.last_kernel(), us=round(us, 2),
                                               GBps=round(nb / us / 1e3, 1), frac=round(nb / us / 1e3 / peak, 3)))
             for tag, fn, nb in (("fwd_multi", lambda s: s.forward(True), fwd_b), ("bwd_multi", lambda s: s.backward(True), bwd_b),
                                 ("fwd_3launch", lambda s: s.forward(False), fwd_b), ("bwd_3launch", lambda s: s.backward(False), bwd_b)):
                 us = timed(fn, sets)
-                out["points"].append(dict(dtype=name, kernel=tag, threads=threads, us=round(us, 2),
+                out["points"].append(dict(dtype=name, kernel=tag, threads=tag_cfg, us=round(us, 2),
                                           GBps=round(nb / us / 1e3, 1), frac=round(nb / us / 1e3 / peak, 3)))
         ops.set_block_threads(0, 0)
+        ops.set_tuning(2, 0)
+        ops.set_tuning(3, 0)
         del sets
         torch.cuda.empty_cache()
     # plain device copy of the same size as a reference point for this timing method
