@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "multi", "per-layer"],
                     help="one launch for all three scales (multi) or one launch per layer")
     ap.add_argument("--no-graph", action="store_true", help="launch from Python every step instead of replaying CUDA graphs")
+    ap.add_argument("--graph-repeat", type=int, default=4, help="steps per CUDA graph = sets * graph_repeat")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
@@ -265,23 +266,24 @@ def main():
     sampler.start()
 
     gen = torch.Generator(device=device).manual_seed(rank)
-    sets = [DeviceSet(B, H, W, dtype, device, generator=gen) for _ in range(a.sets)]
+    all_sets = sets = [DeviceSet(B, H, W, dtype, device, generator=gen) for _ in range(a.sets)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def time_steps(step_fn, n_steps, n_warm):
-        """barrier+sync, n_steps of step_fn(k) between two CUDA events on the current stream, barrier+sync."""
-        for k in range(n_warm):
-            step_fn(k)
+    def time_steps(run, n_steps, n_warm):
+        """barrier+sync, exactly n_steps steps between two CUDA events on the current stream, barrier+sync."""
+        if hasattr(run, "prepare"):
+            run.prepare(n_steps)
+            run.prepare(n_warm)
+        run(n_warm)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.hot = True
         e0.record()
-        for k in range(n_steps):
-            step_fn(k)
+        run(n_steps)
         e1.record()
         barrier()
         sampler.hot = False
@@ -292,8 +294,11 @@ def main():
             ms = float(t.item())
         return ms
 
-    def make_runner(fused, what="both"):
-        """Returns (step_fn, launches_per_step): CUDA-graph replay of one step per buffer set."""
+    def make_runner(fused, what="both", sets=None):
+        sets = sets if sets is not None else all_sets
+        """Returns (run(n_steps), launches_per_step).  Steps rotate over the buffer sets.  With CUDA graphs
+        (default) a chunk of len(sets) consecutive steps is one graph, so the timed region holds
+        back-to-back kernels and not one host call per kernel."""
         def body(s):
             if what in ("both", "fwd"):
                 s.forward(fused)
@@ -303,19 +308,40 @@ def main():
         body(sets[0])
         per_step = ops.launch_count()
         if a.no_graph:
-            return (lambda k: body(sets[k % len(sets)])), per_step
-        graphs = []
+            def run_plain(n):
+                for k in range(n):
+                    body(sets[k % len(sets)])
+            return run_plain, per_step
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for s in sets:
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph, stream=side):
-                    body(s)
-                graphs.append(gph)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        return (lambda k: graphs[k % len(graphs)].replay()), per_step
+        cache = {}
+
+        def graph_of(n):
+            if n not in cache:
+                with torch.cuda.stream(side):
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph, stream=side):
+                        for k in range(n):
+                            body(sets[k % len(sets)])
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                cache[n] = gph
+            return cache[n]
+
+        chunk = len(sets) * a.graph_repeat
+
+        def prepare(n):
+            graph_of(chunk)
+            if n % chunk:
+                graph_of(n % chunk)
+
+        def run_graph(n):
+            for _ in range(n // chunk):
+                cache[chunk].replay()
+            if n % chunk:
+                cache[n % chunk].replay()
+        run_graph.prepare = prepare
+        return run_graph, per_step
 
     # ---- headline: device-resident fwd+bwd of the three scales
     results = {}
@@ -339,10 +365,7 @@ def main():
         only2 = [DeviceSet.__new__(DeviceSet) for _ in sets]
         for o, s in zip(only2, sets):
             o.layers = [L for L in s.layers if L["upratio"] == 2]
-        keep_sets = sets
-        sets = only2
-        fn_dom, _ = make_runner(False, "bwd")
-        sets = keep_sets
+        fn_dom, _ = make_runner(False, "bwd", only2)
     n_dom = max(K, 50)
     ms_dom = time_steps(fn_dom, n_dom, WU)
     achieved = dom_bytes / (ms_dom / n_dom * 1e-3) / 1e9
@@ -418,7 +441,7 @@ def main():
             "config": {"workload": workload_name(a), "launch_mode": best,
                        "cache": "%d disjoint buffer sets of %.0f MB rotated between steps (each exceeds the 126 MB L2)" % (
                            a.sets, (step_bytes) / 1e6),
-                       "cuda_graph": not a.no_graph, "parallelism": "dp%d (batch shards, no data-path collective)" % world,
+                       "cuda_graph": not a.no_graph, "steps_per_graph": (0 if a.no_graph else a.sets * a.graph_repeat), "parallelism": "dp%d (batch shards, no data-path collective)" % world,
                        "algorithmic_bytes_per_step": step_bytes},
             "clocks": sampler.summary(),
             "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,

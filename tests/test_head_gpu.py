@@ -57,7 +57,12 @@ def test_fused_head_f32(B, h, w, C, r, d):
 
     g_feat, g_kern, g_coef = ops.reduce_lpg_backward(f, k, coef, gf, gd, r, d, need_g_coef=True)
     assert ops.last_kernel().startswith("head_lpg_bwd<f32,r%d" % r), ops.last_kernel()
-    assert torch.equal(g_coef, ops.lpg_backward(coef, gf, gd, r, d))
+    # same per-pixel terms as the stand-alone kernel; at r=8 the latter adds the patch rows in a lane-group tree
+    alone = ops.lpg_backward(coef, gf, gd, r, d)
+    scale, _ = parity.backward_scale(npf(coef), npf(g_full), r, npf(g_ds) if d else None, d)
+    assert (np.abs(npf(g_coef) - npf(alone)) <= 4e-7 * scale + 1e-30).all()
+    if r != 8:
+        assert torch.equal(g_coef, alone)
     parity.check_backward(npf(g_coef), npf(coef), npf(g_full), r, npf(g_ds) if d else None, d)
     # g_feat / g_kernel: compare with the oracle chain fed by the kernel's own (float32) g_coef
     gf_o, gw_o = c_oracle.head_backward_f64(npf(feat), kern.numpy(), npf(coef), npf(g_coef))
