@@ -1,0 +1,192 @@
+"""decoder_model(...) of the reference (bts_decoder.py:26-105) wired around the fused LPG ops.
+
+Scope note: the 3x3 / dilated convolutions, BatchNorm and up-sampling of the
+decoder body are dense-conv, library territory -- they run on torch/cuDNN here exactly as they run
+on TF/cuDNN in the reference and are NOT part of the hand-written hot path.  What this module
+replaces is bts_decoder.py:79-81, 86-88, 93-94: each `reduction_NxN` Conv2D(3,1x1,sigmoid) +
+`LocalPlanarGuidance` + down-sampling Lambda becomes ONE kernel forward and ONE backward
+(layers.ReductionLPG -> libbtslpg.so), which also removes the ~thousand-node split/concat storm
+that K.repeat_elements generates.
+
+Interface = the reference's: `decoder_model(decoder_inputs, max_depth, num_filters, is_training)`
+with NHWC tensors `[dense_features, skip_2, skip_4, skip_8, skip_16]` -> depth_est (B,H,W,1).
+Internally activations are NCHW tensors in channels_last memory format, so the NHWC views the
+LPG kernels need are zero-copy.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .layers import ReductionLPG
+
+BN_EPS = 1.1e-5          # bts_decoder.py:27
+BN_MOMENTUM = 1 - 0.99   # Keras momentum 0.99 == torch momentum 0.01
+
+
+def _conv(cin, cout, k=3, dilation=1):
+    pad = dilation * (k - 1) // 2          # padding='same', stride 1
+    return nn.Conv2d(cin, cout, k, padding=pad, dilation=dilation, bias=False)
+
+
+def _bn(c):
+    return nn.BatchNorm2d(c, eps=BN_EPS, momentum=BN_MOMENTUM)
+
+
+def _nhwc_view(x):
+    """NCHW channels_last tensor -> contiguous NHWC view (no copy)."""
+    return x.permute(0, 2, 3, 1)
+
+
+def _to_nchw(x_nhwc):
+    """NHWC tensor -> NCHW view in channels_last memory format (no copy when x is contiguous)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+class _ConvBlock(nn.Module):
+    """conv_block / conv_block_no_lpg (bts_decoder.py:30-44): upsample x2, 3x3 conv + ELU, BN, concat, 3x3 conv + ELU."""
+
+    def __init__(self, cin, cskip, clpg, nf):
+        super().__init__()
+        self.upconv = _conv(cin, nf)
+        self.bn = _bn(nf)
+        self.iconv = _conv(nf + cskip + clpg, nf)
+
+    def forward(self, x, skip, lpg=None):
+        up = F.interpolate(x, scale_factor=2, mode="nearest")
+        up = self.bn(F.elu(self.upconv(up)))
+        parts = [up, skip] + ([lpg] if lpg is not None else [])        # order is load-bearing (bts_decoder.py:42)
+        return F.elu(self.iconv(torch.cat(parts, dim=1)))
+
+
+class _DenseAspp(nn.Module):
+    """dense_aspp_block (bts_decoder.py:46-54)."""
+
+    def __init__(self, cin, nf, rate, batch_norm_first=True):
+        super().__init__()
+        self.bn_first = _bn(cin) if batch_norm_first else None
+        self.conv1 = _conv(cin, nf, k=1)
+        self.bn2 = _bn(nf)
+        self.conv2 = _conv(nf, nf // 2, k=3, dilation=rate)
+
+    def forward(self, x):
+        if self.bn_first is not None:
+            x = self.bn_first(x)
+        x = self.conv1(F.relu(x))
+        return self.conv2(F.relu(self.bn2(x)))
+
+
+class BtsDecoder(nn.Module):
+    """The decoder graph of bts_decoder.py with the three LPG heads fused.  Sub-modules are created in
+    the reference's layer-creation order, so `conv_kernels()` lines up with a Keras weight list."""
+
+    def __init__(self, in_channels, max_depth, num_filters=256):
+        """in_channels: channel counts of [dense_features, skip_2, skip_4, skip_8, skip_16]."""
+        super().__init__()
+        c_dense, c2, c4, c8, c16 = in_channels
+        self.max_depth = float(max_depth)
+        nf = num_filters
+        self.block5 = _ConvBlock(c_dense, c16, 0, nf)             # iconv5, H/16
+        nf //= 2
+        self.block4 = _ConvBlock(nf * 2, c8, 0, nf)               # iconv4, H/8
+        self.bn4 = _bn(nf)
+        self.daspp_3 = _DenseAspp(nf, nf, 3, batch_norm_first=False)
+        self.daspp_6 = _DenseAspp(nf + nf // 2, nf, 6)
+        self.daspp_12 = _DenseAspp(nf + 2 * (nf // 2), nf, 12)
+        self.daspp_18 = _DenseAspp(nf + 3 * (nf // 2), nf, 18)
+        self.daspp_24 = _DenseAspp(nf + 4 * (nf // 2), nf, 24)
+        self.daspp_feat = _conv(nf + 5 * (nf // 2), nf // 2)
+        self.reduction_8x8 = ReductionLPG(nf // 2, 8, ds_stride=4, name="reduction_8x8")
+        c_daspp = nf // 2
+        nf //= 2
+        self.block3 = _ConvBlock(c_daspp, c4, 1, nf)              # iconv3, H/4
+        self.reduction_4x4 = ReductionLPG(nf, 4, ds_stride=2, name="reduction_4x4")
+        nf //= 2
+        self.block2 = _ConvBlock(nf * 2, c2, 1, nf)               # iconv2, H/2
+        self.reduction_2x2 = ReductionLPG(nf, 2, ds_stride=0, name="reduction_2x2")
+        c_iconv2 = nf
+        nf //= 2
+        self.upconv1 = _conv(c_iconv2, nf)
+        self.iconv1 = _conv(nf + 3, nf)
+        self.depth_conv = _conv(nf, 1)
+        self.to(memory_format=torch.channels_last)
+        self.intermediates = {}
+
+    # --- weights in Keras order / layout -----------------------------------------------------
+    def conv_modules(self):
+        """Convolution-like modules in the reference's creation order (25 for bts_decoder.py)."""
+        out = [self.block5.upconv, self.block5.iconv, self.block4.upconv, self.block4.iconv]
+        for d in (self.daspp_3, self.daspp_6, self.daspp_12, self.daspp_18, self.daspp_24):
+            out += [d.conv1, d.conv2]
+        out += [self.daspp_feat, self.reduction_8x8, self.block3.upconv, self.block3.iconv, self.reduction_4x4,
+                self.block2.upconv, self.block2.iconv, self.reduction_2x2, self.upconv1, self.iconv1, self.depth_conv]
+        return out
+
+    def load_keras_kernels(self, kernels):
+        """kernels: list of HWIO arrays/tensors in creation order (Keras `layer.kernel`)."""
+        mods = self.conv_modules()
+        assert len(kernels) == len(mods), (len(kernels), len(mods))
+        with torch.no_grad():
+            for m, k in zip(mods, kernels):
+                k = torch.as_tensor(k)
+                if isinstance(m, ReductionLPG):
+                    m.kernel.copy_(k.to(m.kernel))
+                else:
+                    m.weight.copy_(k.permute(3, 2, 0, 1).to(m.weight))      # HWIO -> OIHW
+
+    def keras_kernel_grads(self):
+        """Gradients of the conv kernels, HWIO, creation order."""
+        out = []
+        for m in self.conv_modules():
+            g = m.kernel.grad if isinstance(m, ReductionLPG) else m.weight.grad.permute(2, 3, 1, 0)
+            out.append(g)
+        return out
+
+    # --- forward -------------------------------------------------------------------------------
+    def forward(self, decoder_inputs):
+        """decoder_inputs: NHWC [dense_features, skip_2, skip_4, skip_8, skip_16] -> depth_est NHWC (B,H,W,1)."""
+        dense, s2, s4, s8, s16 = [_to_nchw(t) for t in decoder_inputs]
+        iconv5 = self.block5(dense, s16)
+        iconv4 = self.block4(iconv5, s8)
+        iconv4_bn = self.bn4(iconv4)
+        d3 = self.daspp_3(iconv4_bn)
+        c2 = torch.cat([iconv4, d3], 1)
+        d6 = self.daspp_6(c2)
+        c3 = torch.cat([c2, d6], 1)
+        d12 = self.daspp_12(c3)
+        c4 = torch.cat([c3, d12], 1)
+        d18 = self.daspp_18(c4)
+        c5 = torch.cat([c4, d18], 1)
+        d24 = self.daspp_24(c5)
+        daspp_feat = F.elu(self.daspp_feat(torch.cat([iconv4_bn, d3, d6, d12, d18, d24], 1)))
+
+        # bts_decoder.py:79-81: reduction_8x8 -> depth_8x8_scaled -> ds  (one kernel)
+        red8, d8, d8_ds = self.reduction_8x8(_nhwc_view(daspp_feat.contiguous(memory_format=torch.channels_last)))
+        iconv3 = self.block3(daspp_feat, s4, _to_nchw(d8_ds))
+        red4, d4, d4_ds = self.reduction_4x4(_nhwc_view(iconv3.contiguous(memory_format=torch.channels_last)))
+        iconv2 = self.block2(iconv3, s2, _to_nchw(d4_ds))
+        red2, d2 = self.reduction_2x2(_nhwc_view(iconv2.contiguous(memory_format=torch.channels_last)))
+
+        up1 = F.elu(self.upconv1(F.interpolate(iconv2, scale_factor=2, mode="nearest")))
+        concat1 = torch.cat([up1, _to_nchw(d2), _to_nchw(d4), _to_nchw(d8)], 1)        # bts_decoder.py:99
+        iconv1 = F.elu(self.iconv1(concat1))
+        depth = torch.sigmoid(self.depth_conv(iconv1)) * self.max_depth                # bts_decoder.py:102-103
+        self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
+                              "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
+        return _nhwc_view(depth)
+
+
+def decoder_model(decoder_inputs, max_depth, num_filters=256, is_training=False, decoder=None):
+    """Same call as the reference's decoder_model (bts_decoder.py:26).  A BtsDecoder is built from the
+    input channel counts on first use (pass `decoder=` to reuse weights); returns depth_est NHWC."""
+    if decoder is None:
+        decoder = BtsDecoder([t.shape[-1] for t in decoder_inputs], max_depth, num_filters).to(decoder_inputs[0].device)
+    decoder.train(bool(is_training))
+    return decoder(decoder_inputs)
+
+
+def si_log_loss(y_true, y_pred, dataset="nyu"):
+    """bts.py:27-41 (torch restatement for the training-step benches; not a hot-path kernel)."""
+    th = {"nyu": 0.1, "kitti": 1.0, "matterport": 0.1}[dataset]
+    mask = y_true > th
+    d = torch.log(y_true[mask] + 1e-7) - torch.log(y_pred[mask] + 1e-7)
+    return torch.sqrt((d * d).mean() - 0.85 * d.mean() ** 2) * 10.0

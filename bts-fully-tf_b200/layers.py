@@ -93,10 +93,18 @@ class ReductionLPG(torch.nn.Module):
         self.layer_name = name or "reduction_%dx%d" % (upratio, upratio)
         limit = math.sqrt(6.0 / (in_channels + 3))        # glorot_uniform, fan_in = C, fan_out = 3
         self.kernel = torch.nn.Parameter((torch.rand(1, 1, in_channels, 3) * 2 - 1) * limit)
+        self._grad_view = None
+
+    def bind_gradient_view(self, view):
+        """Let backward write d loss / d kernel straight into `view` (a float32 slice of a flat gradient
+        bucket, see parallel.GradientBucket) instead of handing it to autograd for accumulation."""
+        if view is not None and (view.dtype != torch.float32 or view.numel() != self.kernel.numel() or not view.is_contiguous()):
+            raise ValueError("gradient view must be a contiguous float32 tensor with %d elements" % self.kernel.numel())
+        self._grad_view = view
 
     @property
     def name(self):
         return self.layer_name
 
     def forward(self, feat):
-        return ops.reduce_lpg(feat, self.kernel, self.upratio, self.ds_stride)
+        return ops.reduce_lpg(feat, self.kernel, self.upratio, self.ds_stride, self._grad_view)

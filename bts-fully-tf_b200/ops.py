@@ -189,11 +189,14 @@ class ReduceLpgFunction(torch.autograd.Function):
     """Differentiable fused head: (feat, kernel) -> (reduction, depth, depth_ds)."""
 
     @staticmethod
-    def forward(ctx, feat, kernel, upratio, ds_stride):
+    def forward(ctx, feat, kernel, upratio, ds_stride, g_kernel_out=None):
         feat_c = feat.contiguous()
         coef, full, ds = reduce_lpg_forward(feat_c, kernel, upratio, ds_stride)
         ctx.save_for_backward(feat_c, kernel, coef)
         ctx.upratio, ctx.ds_stride = upratio, ds_stride
+        # optional [C][3] float32 view into a flat gradient bucket: backward writes g_kernel there
+        # directly (the bucket is what the all-reduce sends) instead of returning it to autograd
+        ctx.g_kernel_out = g_kernel_out
         ctx.set_materialize_grads(False)
         if ds is None:
             ds = full.new_empty(0)
@@ -211,17 +214,22 @@ class ReduceLpgFunction(torch.autograd.Function):
             g_ds = None
         need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if (g_full is None and g_ds is None) or not (need_f or need_k):
-            return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None
+            return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None, None
+        direct = ctx.g_kernel_out if need_k else None
         g_feat, g_kernel, _ = reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, ctx.upratio, ctx.ds_stride,
-                                                  need_g_feat=need_f, need_g_kernel=need_k)
-        if g_kernel is not None:
+                                                  need_g_feat=need_f, need_g_kernel=need_k,
+                                                  g_kernel_out=None if direct is None else direct.view(-1, 3))
+        if direct is not None:
+            g_kernel = None                      # already in the bucket; nothing for autograd to accumulate
+        elif g_kernel is not None:
             g_kernel = g_kernel.reshape(kernel.shape).to(kernel.dtype)
-        return g_feat, g_kernel, None, None
+        return g_feat, g_kernel, None, None, None
 
 
-def reduce_lpg(feat, kernel, upratio, ds_stride=0):
-    """Functional fused head with autograd.  Returns (reduction, depth[, depth_ds])."""
-    coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride))
+def reduce_lpg(feat, kernel, upratio, ds_stride=0, g_kernel_out=None):
+    """Functional fused head with autograd.  Returns (reduction, depth[, depth_ds]).
+    g_kernel_out: optional float32 view (same numel as kernel) that receives d loss / d kernel in backward."""
+    coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride), g_kernel_out)
     return (coef, full, ds) if ds_stride else (coef, full)
 
 

@@ -1,0 +1,71 @@
+"""GPU test of the decoder wiring (bts_decoder.py:26-105) around the fused LPG heads against the
+fixture recorded from the UNMODIFIED reference decoder_model (tests/golden/decoder_small.npz),
+forward and backward, inference-mode and training-mode BatchNorm."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bts_fully_tf_b200 import LocalPlanarGuidance, ops
+from bts_fully_tf_b200.decoder import BtsDecoder, decoder_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _load(golden_dir):
+    z = np.load(os.path.join(golden_dir, "decoder_small.npz"))
+    feats = [torch.from_numpy(z["feat_" + k]).float().to(DEV).requires_grad_(True) for k in ("dense", "s2", "s4", "s8", "s16")]
+    kernels = [z["kernel_%02d" % i] for i in range(int(z["n_convs"]))]
+    return z, feats, kernels
+
+
+@pytest.mark.parametrize("tag,training", [("infer", False), ("train", True)])
+def test_decoder_matches_reference_fixture(golden_dir, tag, training):
+    z, feats, kernels = _load(golden_dir)
+    dec = BtsDecoder([f.shape[-1] for f in feats], 10.0, num_filters=32).to(DEV)
+    dec.load_keras_kernels(kernels)
+    depth = decoder_model(feats, 10.0, num_filters=32, is_training=training, decoder=dec)
+    assert tuple(depth.shape) == z[tag + "_depth_est"].shape
+    for r in (8, 4, 2):
+        np.testing.assert_allclose(dec.intermediates["reduction_%dx%d" % (r, r)].detach().cpu().numpy(), z["%s_head%d_out" % (tag, r)],
+                                   rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(dec.intermediates["depth_%dx%d_scaled" % (r, r)].detach().cpu().numpy(),
+                                   z["%s_depth_%dx%d_scaled" % (tag, r, r)], rtol=5e-4, atol=1e-5)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), z[tag + "_depth_est"], rtol=5e-4, atol=1e-5)
+
+    depth.backward(torch.from_numpy(z["g_depth"]).float().to(DEV))
+    grads = dec.keras_kernel_grads()
+    for i, g in enumerate(grads):
+        ref = z["%s_gkernel_%02d" % (tag, i)]
+        assert np.abs(g.detach().cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, "kernel %d" % i
+    for k, f in zip(("dense", "s2", "s4", "s8", "s16"), feats):
+        ref = z["%s_gfeat_%s" % (tag, k)]
+        assert np.abs(f.grad.cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, k
+
+
+def test_fused_heads_equal_unfused_composition():
+    """ReductionLPG (one kernel) == torch 1x1 conv + sigmoid -> LocalPlanarGuidance layer -> slice, at
+    channel counts that take the fused fast path (F=256: C = 64, 64, 32)."""
+    torch.manual_seed(0)
+    B, H, W, F = 2, 64, 96, 256
+    chans = [48, 24, 24, 32, 40]
+    feats = [torch.randn(B, H // s, W // s, c, device=DEV) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    dec = BtsDecoder(chans, 10.0, num_filters=F).to(DEV).eval()
+    depth = dec(feats)
+    assert ops.launch_count() > 0
+    for r, d, head in ((8, 4, dec.reduction_8x8), (4, 2, dec.reduction_4x4), (2, 0, dec.reduction_2x2)):
+        red = dec.intermediates["reduction_%dx%d" % (r, r)]
+        layer = LocalPlanarGuidance(upratio=r, name="depth_%dx%d_scaled" % (r, r))
+        np.testing.assert_array_equal(layer(red).cpu().numpy(), dec.intermediates["depth_%dx%d_scaled" % (r, r)].detach().cpu().numpy())
+    assert torch.isfinite(depth).all() and float(depth.max()) <= 10.0 and float(depth.min()) >= 0.0
