@@ -108,7 +108,6 @@ class BtsDecoder(nn.Module):
         self.upconv1 = _conv(c_iconv2, nf)
         self.iconv1 = _conv(nf + 3, nf)
         self.depth_conv = _conv(nf, 1)
-        self.to(memory_format=torch.channels_last)
         self.intermediates = {}
 
     # --- weights in Keras order / layout -----------------------------------------------------

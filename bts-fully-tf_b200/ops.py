@@ -38,6 +38,14 @@ def lpg_forward(coef, upratio, ds_stride=0, out_full=None, out_ds=None):
     return out_full, (out_ds if ds_stride else None)
 
 
+def _unit_stride_map(g):
+    """Gradients that arrive as channel slices of an NHWC concat gradient (bts_decoder.py:42,99) have a
+    column stride of the concat's channel count; one packing copy puts them on the vectorised kernels."""
+    if g is not None and g.dim() >= 3 and g.shape[2] > 1 and g.stride(2) != 1:
+        return g.contiguous()
+    return g
+
+
 def lpg_backward(coef, g_full, g_ds, upratio, ds_stride=0, g_coef=None):
     """d loss / d coef from d loss / d depth (g_full) and d loss / d depth_ds (g_ds); either may be None."""
     lib = load()
@@ -106,7 +114,7 @@ class LpgFunction(torch.autograd.Function):
             g_ds = None
         if g_full is None and g_ds is None:
             return torch.zeros_like(coef), None, None
-        return lpg_backward(coef, g_full, g_ds, ctx.upratio, ctx.ds_stride), None, None
+        return lpg_backward(coef, _unit_stride_map(g_full), _unit_stride_map(g_ds), ctx.upratio, ctx.ds_stride), None, None
 
 
 def local_planar_guidance(coef, upratio, ds_stride=0):
@@ -172,7 +180,10 @@ def reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, upratio, ds_stride=0, 
     g_kernel = None
     if need_g_kernel:
         g_kernel = g_kernel_out if g_kernel_out is not None else torch.empty((C, 3), dtype=torch.float32, device=feat.device)
-    g_coef = torch.empty_like(coef) if need_g_coef else None
+    # channel counts / layouts outside the fused variants run the generic kernels, which need the LPG
+    # coefficient gradient as scratch (the library never allocates)
+    fused_ok = C in (32, 64, 128) and feat.is_contiguous() and coef.is_contiguous()
+    g_coef = torch.empty_like(coef, memory_format=torch.contiguous_format) if (need_g_coef or not fused_ok) else None
     npix = feat.numel() // C
     nbytes = lib.btslpg_reduce_backward_workspace_bytes(npix, C)
     ws = _workspace(feat.device, nbytes)
@@ -216,6 +227,7 @@ class ReduceLpgFunction(torch.autograd.Function):
         if (g_full is None and g_ds is None) or not (need_f or need_k):
             return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None, None
         direct = ctx.g_kernel_out if need_k else None
+        g_full, g_ds = _unit_stride_map(g_full), _unit_stride_map(g_ds)
         g_feat, g_kernel, _ = reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, ctx.upratio, ctx.ds_stride,
                                                   need_g_feat=need_f, need_g_kernel=need_k,
                                                   g_kernel_out=None if direct is None else direct.view(-1, 3))

@@ -68,4 +68,5 @@ def test_fused_heads_equal_unfused_composition():
         red = dec.intermediates["reduction_%dx%d" % (r, r)]
         layer = LocalPlanarGuidance(upratio=r, name="depth_%dx%d_scaled" % (r, r))
         np.testing.assert_array_equal(layer(red).cpu().numpy(), dec.intermediates["depth_%dx%d_scaled" % (r, r)].detach().cpu().numpy())
+    depth = depth.detach()
     assert torch.isfinite(depth).all() and float(depth.max()) <= 10.0 and float(depth.min()) >= 0.0

@@ -125,8 +125,13 @@ def test_generic_channel_counts(C):
     gf_o, gw_o = c_oracle.head_backward_f64(npf(feat), kern.numpy(), npf(coef), npf(g_coef))
     np.testing.assert_allclose(npf(g_feat), gf_o, rtol=1e-5, atol=1e-5 * np.abs(gf_o).max())
     assert np.abs(npf(g_kern) - gw_o).max() <= 2e-5 * np.abs(gw_o).max()
-    with pytest.raises(ValueError, match="g_coef_out"):
-        ops.reduce_lpg_backward(f, k, coef, gf, gd, r, d, need_g_coef=False)
+    # the Python wrapper supplies the scratch the generic path needs; the raw ABI refuses without it
+    from bts_fully_tf_b200 import _cabi
+    lib = _cabi.load()
+    refs = [_cabi.as_ref(t) for t in (f, k, coef, gf, gd, torch.empty_like(f))]
+    rc = lib.btslpg_reduce_backward(refs[0].ptr, refs[1].ptr, refs[2].ptr, refs[3].ptr, refs[4].ptr, r, d, refs[5].ptr, None, None,
+                                    None, 0, _cabi.current_stream_ptr(f.device))
+    assert rc == -5 and b"g_coef_out" in lib.btslpg_last_error()
 
 
 def test_keras_hwio_kernel_and_module_autograd():

@@ -114,7 +114,7 @@ def run(cfg_id, a, rank, local_rank, world):
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    result = float(out.float().mean())            # device->host read of the step's result
+    result = float(out.detach().float().mean())   # device->host read of the step's result
 
     # share of the step spent in the LPG heads (events around the three fused ops, forward only)
     lpg_ms = None
