@@ -246,7 +246,19 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the first communicator is created; keep stdout
+        # for the one JSON line by pointing fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from bts_fully_tf_b200 import _cabi
     _cabi.load()          # fail loudly now if libbtslpg.so is missing: there is no fallback path
 
