@@ -177,21 +177,22 @@ struct Variant {
     int px = 0, rows = 0;
     bool ok() const { return px > 0; }
 };
-std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0};
+std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0}, g_tune_r2_px{0}, g_tune_multi_u{0}, g_tune_multi_minb{-1};
 
-int candidates(int dtype, int r, Variant *out) {
+int candidates(int dtype, int r, bool fwd, Variant *out) {
     int n = 0;
     auto add = [&](int px, int rows) { out[n].px = px; out[n].rows = rows; ++n; };
     if (dtype == kF32) {
         if (r == 8) {
             const int t = g_tune_r8_rows.load();
-            if (t == 8 || t == 4 || t == 2) add(1, t);
-            add(1, 2); add(1, 4); add(1, 8);
+            if (t == 8 || t == 2) add(1, t);
+            if (fwd) { add(1, 8); add(1, 2); } else { add(1, 2); add(1, 8); }
         } else if (r == 4) {
             if (g_tune_r4_px.load() == 2) add(2, 4);
             add(1, 4); add(2, 4);
         } else if (r == 2) {
-            add(4, 2); add(2, 2); add(1, 2);
+            if (g_tune_r2_px.load() == 4) add(4, 2);
+            add(2, 2); add(4, 2); add(1, 2);
         }
     } else {
         if (r == 8) { add(2, 2); add(2, 4); }
@@ -218,7 +219,7 @@ bool variant_fits(const LayerGeom &g, const Variant &v) {
     return true;
 }
 
-Variant pick_variant(const LayerGeom &g, bool first_only = false) {
+Variant pick_variant(const LayerGeom &g, bool fwd) {
     const int r = g.r;
     Variant none;
     if (r != 2 && r != 4 && r != 8) return none;
@@ -227,8 +228,8 @@ Variant pick_variant(const LayerGeom &g, bool first_only = false) {
     if (g.has_full && g.full.sW != 1) return none;
     if (g.has_ds && g.ds.sW != 1) return none;
     Variant c[6];
-    const int n = candidates(g.coef.dtype, r, c);
-    for (int k = 0; k < (first_only ? 1 : n); ++k)
+    const int n = candidates(g.coef.dtype, r, fwd, c);
+    for (int k = 0; k < n; ++k)
         if (variant_fits(g, c[k])) return c[k];
     return none;
 }
@@ -289,18 +290,18 @@ template <typename T> LpgGenericParams<T> make_generic_params(const LayerGeom &g
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_fwd_variant(const LpgFwdParams<T> &p, int threads, cudaStream_t st) {
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
-    lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
+    lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads * kVecU - 1) / (threads * kVecU), threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_bwd_variant(const LpgBwdParams<T> &p, int threads, cudaStream_t st) {
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
-    lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
+    lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads * kVecU - 1) / (threads * kVecU), threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 
 // every instantiated (R, PX, ROWS) per dtype
-#define BTSLPG_VARIANTS_F32(X) X(8, 1, 2) X(8, 1, 4) X(8, 1, 8) X(4, 1, 4) X(4, 2, 4) X(2, 4, 2) X(2, 2, 2) X(2, 1, 2)
+#define BTSLPG_VARIANTS_F32(X) X(8, 1, 2) X(8, 1, 8) X(4, 1, 4) X(4, 2, 4) X(2, 4, 2) X(2, 2, 2) X(2, 1, 2)
 #define BTSLPG_VARIANTS_BF16(X) X(8, 2, 2) X(8, 2, 4) X(4, 2, 4) X(2, 4, 2) X(2, 2, 2)
 
 template <typename T, typename P, bool FWD> void dispatch_vec(const P &p, int r, Variant v, bool has_ds, int threads, cudaStream_t st) {
@@ -361,7 +362,7 @@ int parse_layer_bwd(const BtsTensor *coef, const BtsTensor *g_full, const BtsTen
 template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
     const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
     if (npix == 0) return 0;
-    const Variant v = pick_variant(g);
+    const Variant v = pick_variant(g, true);
     if (v.ok()) {
         auto p = make_fwd_params<T>(g, v.px);
         tl_kernel[0] = 0;
@@ -378,7 +379,7 @@ template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
 template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaStream_t st) {
     const int64_t npix = g.coef.B * g.coef.H * g.coef.W;
     if (npix == 0) return 0;
-    Variant v = pick_variant(g);
+    Variant v = pick_variant(g, false);
     if (v.ok() && !(is_contig_nhwc(gc) && gc.aligned(16))) v = Variant();
     if (v.ok()) {
         auto p = make_bwd_params<T>(g, gc, v.px);
@@ -393,17 +394,23 @@ template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaS
     return check_launch("btslpg_backward");
 }
 
+constexpr int kMultiUDefault = 1;
+int multi_u() {
+    const int u = g_tune_multi_u.load();
+    return (u == 1 || u == 2 || u == 4) ? u : kMultiUDefault;
+}
+
 // multi-launch eligibility: the default vector variant (VecCfg) with the reference's ds stride (or none)
-template <typename T> bool multi_eligible_t(const LayerGeom &g) {
+template <typename T> bool multi_eligible_t(const LayerGeom &g, bool fwd) {
     if (g.r != 2 && g.r != 4 && g.r != 8) return false;
     Variant want;
     want.px = px_max<T>(g.r);
-    want.rows = rows_default<T>(g.r);
-    if (!pick_variant(g).ok()) return false;      // layout / ds-stride preconditions
+    want.rows = rows_default<T>(g.r, fwd);
+    if (!pick_variant(g, fwd).ok()) return false;      // layout / ds-stride preconditions
     return variant_fits(g, want);
 }
-bool multi_eligible(const LayerGeom &g) {
-    return g.coef.dtype == kF32 ? multi_eligible_t<float>(g) : multi_eligible_t<__nv_bfloat16>(g);
+bool multi_eligible(const LayerGeom &g, bool fwd) {
+    return g.coef.dtype == kF32 ? multi_eligible_t<float>(g, fwd) : multi_eligible_t<__nv_bfloat16>(g, fwd);
 }
 
 }  // namespace
@@ -428,6 +435,9 @@ void btslpg_set_tuning(int key, int value) {
         case 1: g_bwd_threads.store(value); break;
         case 2: g_tune_r8_rows.store(value); break;   // float32 r=8: patch rows per lane (2, 4 or 8)
         case 3: g_tune_r4_px.store(value); break;     // float32 r=4: coarse pixels per thread (1 or 2)
+        case 6: g_tune_r2_px.store(value); break;     // float32 r=2: coarse pixels per thread (2 or 4)
+        case 4: g_tune_multi_u.store(value); break;   // multi-layer kernels: slots per thread (1, 2 or 4)
+        case 5: g_tune_multi_minb.store(value); break; // multi-layer kernels: register cap for 12 (fwd) / 8 (bwd) blocks of 128 per SM
         default: break;
     }
 }
@@ -473,7 +483,7 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
     bool fused = true;
     for (int k = 0; k < n; ++k) {
         if (int e = parse_layer_fwd(layers[k].coef, layers[k].upratio, layers[k].out_full, layers[k].out_ds, layers[k].ds_stride, g[k])) return e;
-        fused = fused && multi_eligible(g[k]) && g[k].coef.dtype == g[0].coef.dtype && g[k].coef.dev == g[0].coef.dev &&
+        fused = fused && multi_eligible(g[k], true) && g[k].coef.dtype == g[0].coef.dtype && g[k].coef.dev == g[0].coef.dev &&
                 g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -484,7 +494,9 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
     }
     DeviceGuard guard(g[0].coef.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
-    const int threads = block_threads(true, 4);
+    const int U = multi_u(), minb = g_tune_multi_minb.load() != 0 ? 1 : 0;
+    int threads = block_threads(true, 4);
+    if (minb && threads > 128) threads = 128;
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
         LpgFwdMulti<T> m;
@@ -493,11 +505,14 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
         for (int k = 0; k < n; ++k) {
             m.layer[k] = make_fwd_params<T>(g[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r)) + threads - 1) / threads;
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, true)) + threads * U - 1) / (threads * U);
             m.block_end[k] = blocks;
         }
         m.n = n;
-        lpg_fwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
+#define BTSLPG_FWD_MULTI(UU, MB) lpg_fwd_multi_kernel<T, UU, MB><<<blocks, threads, 0, st>>>(m)
+        if (minb) { if (U == 4) BTSLPG_FWD_MULTI(4, 16); else if (U == 2) BTSLPG_FWD_MULTI(2, 16); else BTSLPG_FWD_MULTI(1, 16); }
+        else { if (U == 4) BTSLPG_FWD_MULTI(4, 0); else if (U == 2) BTSLPG_FWD_MULTI(2, 0); else BTSLPG_FWD_MULTI(1, 0); }
+#undef BTSLPG_FWD_MULTI
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_forward_multi");
     };
@@ -512,7 +527,7 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
     for (int k = 0; k < n; ++k) {
         if (!layers[k].g_coef) return fail(BTSLPG_EINVAL, "g_coef: tensor is NULL");
         if (int e = parse_layer_bwd(layers[k].coef, layers[k].g_full, layers[k].g_ds, layers[k].upratio, layers[k].ds_stride, layers[k].g_coef, g[k], gc[k])) return e;
-        fused = fused && multi_eligible(g[k]) && is_contig_nhwc(gc[k]) && gc[k].aligned(16) && g[k].coef.dtype == g[0].coef.dtype &&
+        fused = fused && multi_eligible(g[k], false) && is_contig_nhwc(gc[k]) && gc[k].aligned(16) && g[k].coef.dtype == g[0].coef.dtype &&
                 g[k].coef.dev == g[0].coef.dev && g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -523,7 +538,9 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
     }
     DeviceGuard guard(g[0].coef.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
-    const int threads = block_threads(false, 4);
+    const int U = multi_u(), minb = g_tune_multi_minb.load() != 0 ? 1 : 0;
+    int threads = block_threads(false, 4);
+    if (minb && threads > 128) threads = 128;
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
         LpgBwdMulti<T> m;
@@ -532,11 +549,14 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
         for (int k = 0; k < n; ++k) {
             m.layer[k] = make_bwd_params<T>(g[k], gc[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r)) + threads - 1) / threads;
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, false)) + threads * U - 1) / (threads * U);
             m.block_end[k] = blocks;
         }
         m.n = n;
-        lpg_bwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
+#define BTSLPG_BWD_MULTI(UU, MB) lpg_bwd_multi_kernel<T, UU, MB><<<blocks, threads, 0, st>>>(m)
+        if (minb) { if (U == 4) BTSLPG_BWD_MULTI(4, 12); else if (U == 2) BTSLPG_BWD_MULTI(2, 12); else BTSLPG_BWD_MULTI(1, 12); }
+        else { if (U == 4) BTSLPG_BWD_MULTI(4, 0); else if (U == 2) BTSLPG_BWD_MULTI(2, 0); else BTSLPG_BWD_MULTI(1, 0); }
+#undef BTSLPG_BWD_MULTI
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_backward_multi");
     };

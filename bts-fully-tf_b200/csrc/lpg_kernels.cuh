@@ -105,25 +105,28 @@ __device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
 
 // ------------------------------------------------------------------------------------------------
 // Direction weights of the ROWS patch rows a lane owns.
-//   LPP == 1 (ROWS == R): compile-time indices -> constant-bank operands, no registers.
-//   LPP  > 1: rows [sub*ROWS, sub*ROWS+ROWS) -> ROWS*R weights in registers (vector loads from the
-//             global copy of the table, L1-resident) and a per-lane row offset.
+//   LPP == 1 (ROWS == R): compile-time indices -> constant-bank operands of the FFMAs, no registers.
+//   LPP  > 1: rows [sub*ROWS, sub*ROWS+ROWS) with a per-lane `sub`: the r*r table is staged once per
+//             CTA in shared memory and read on demand (a divergent __constant__ index would serialise,
+//             and keeping ROWS*R weights in registers costs occupancy, which these latency-bound
+//             kernels cannot afford).
 // ------------------------------------------------------------------------------------------------
+template <int R> __device__ __forceinline__ const float *stage_dir_table() {
+    __shared__ float tab[R * R];
+    for (int t = threadIdx.x; t < R * R; t += blockDim.x) tab[t] = DirTable<R>::gw()[t];
+    __syncthreads();
+    return tab;
+}
+
 template <int R, int ROWS> struct LaneDirs {
-    float wl[ROWS][R];
-    float a0;   // row offset of the lane's first row minus off(0)
-    __device__ __forceinline__ void init(int sub) {
+    const float *sw;   // shared-memory weights of this lane's first row
+    float a0;          // row offset of the lane's first row minus off(0)
+    __device__ __forceinline__ void init(int sub) {   // must be reached by every thread of the CTA
         a0 = (float)(sub * ROWS) * (1.0f / R);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(DirTable<R>::gw() + sub * ROWS * R);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&wl[0][0]);
-#pragma unroll
-        for (int i = 0; i < ROWS * R; i += 4) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + i));
-            dst[i] = v.x; dst[i + 1] = v.y; dst[i + 2] = v.z; dst[i + 3] = v.w;
-        }
+        sw = stage_dir_table<R>() + sub * ROWS * R;
     }
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
-    __device__ __forceinline__ float w(int k, int q) const { return wl[k][q]; }
+    __device__ __forceinline__ float w(int k, int q) const { return sw[k * R + q]; }
 };
 template <int R> struct LaneDirs<R, R> {
     __device__ __forceinline__ void init(int) {}
@@ -279,33 +282,46 @@ template <int R, int ROWS> struct Split {
     static_assert(R % ROWS == 0 && (LPP == 1 || LPP == 2 || LPP == 4), "bad row split");
 };
 
-// `slot` = index of this thread among the threads of its layer (block-uniform base + threadIdx)
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
+// ------------------------------------------------------------------------------------------------
+// A thread works on U "slots" (slot = one lane's share of a group), `stride` slots apart, with the
+// inputs of slot u+1 requested before slot u is computed (one-ahead software prefetch): the load
+// latency is exposed once per thread instead of once per slot, and the per-thread set-up (direction
+// weights, parameters) is amortised.  stride is a multiple of 32, so lane and row-group are fixed.
+// ------------------------------------------------------------------------------------------------
+template <int R, int ROWS> __device__ __forceinline__ uint32_t slot_group(uint32_t slot) {
     using S = Split<R, ROWS>;
-    constexpr int NDS = D ? R / D : 0;
-    const int lane = slot & 31;
-    const int sub = S::LPP == 1 ? 0 : lane / S::GPW;
-    const uint32_t group = S::LPP == 1 ? slot : (slot >> 5) * S::GPW + (lane % S::GPW);
-    if (group >= prm.groups) return;
-    uint32_t row, jg, b, i;
-    prm.wg.divmod(group, row, jg);
-    prm.h.divmod(row, b, i);
+    return S::LPP == 1 ? slot : (slot >> 5) * S::GPW + ((slot & 31) % S::GPW);
+}
 
+template <int PX> struct FwdItem {
     float c[PX * 3];
-    load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);
+    uint32_t group;
+    bool active;
+};
 
+template <typename T, int R, int PX, int ROWS>
+__device__ __forceinline__ void lpg_fwd_fetch(const LpgFwdParams<T> &prm, uint32_t slot, FwdItem<PX> &it) {
+    it.group = slot_group<R, ROWS>(slot);
+    it.active = it.group < prm.groups;
+    if (it.active) load_elems<T, PX * 3, 4>(prm.coef + (size_t)it.group * (PX * 3), it.c);
+}
+
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_fwd_emit(const LpgFwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, const FwdItem<PX> &it) {
+    constexpr int NDS = D ? R / D : 0;
+    if (!it.active) return;
+    uint32_t row, jg, b, i;
+    prm.wg.divmod(it.group, row, jg);
+    prm.h.divmod(row, b, i);
     float n1[PX], n2[PX], n3[PX], n4[PX];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
         Angles a;
-        decode_angles(c[3 * px], c[3 * px + 1], a);
+        decode_angles(it.c[3 * px], it.c[3 * px + 1], a);
         n1[px] = a.st * a.cp;   // custom_layers.py:50
         n2[px] = a.st * a.sp;
         n3[px] = a.ct;
-        n4[px] = c[3 * px + 2];
+        n4[px] = it.c[3 * px + 2];
     }
     T *orow = prm.out + (int64_t)b * prm.out_sB + (int64_t)(i * R) * prm.out_sH + (size_t)jg * (PX * R);
     T *drow = nullptr;
@@ -315,48 +331,67 @@ __device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint3
     lpg_expand_store<T, R, PX, ROWS, D>(dir, sub, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
 }
 
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot) {
+template <typename T, int R, int PX, int ROWS, int D, int U>
+__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot0, uint32_t stride) {
     using S = Split<R, ROWS>;
-    constexpr int NDS = D ? R / D : 0;
-    const int lane = slot & 31;
-    const int sub = S::LPP == 1 ? 0 : lane / S::GPW;
-    const uint32_t group = S::LPP == 1 ? slot : (slot >> 5) * S::GPW + (lane % S::GPW);
-    const bool active = group < prm.groups;
-    if (S::LPP == 1 && !active) return;            // with LPP > 1 every lane takes part in the shuffles
-
-    float G[ROWS][PX * R];
-    float c[PX * 3];
+    const int sub = S::LPP == 1 ? 0 : (int)(slot0 & 31) / S::GPW;
     LaneDirs<R, ROWS> dir;
     dir.init(sub);
-    if (active) {
+    FwdItem<PX> cur;
+    lpg_fwd_fetch<T, R, PX, ROWS>(prm, slot0, cur);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        FwdItem<PX> nxt;
+        if (u + 1 < U) lpg_fwd_fetch<T, R, PX, ROWS>(prm, slot0 + (u + 1) * stride, nxt);
+        lpg_fwd_emit<T, R, PX, ROWS, D>(prm, dir, sub, cur);
+        if (u + 1 < U) cur = nxt;
+    }
+}
+
+template <int R, int PX, int ROWS> struct BwdItem {
+    float G[ROWS][PX * R];
+    float c[PX * 3];
+    uint32_t group;
+    bool active;
+};
+
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_bwd_fetch(const LpgBwdParams<T> &prm, int sub, uint32_t slot, BwdItem<R, PX, ROWS> &it) {
+    constexpr int NDS = D ? R / D : 0;
+    it.group = slot_group<R, ROWS>(slot);
+    it.active = it.group < prm.groups;
+    if (it.active) {
         uint32_t row, jg, b, i;
-        prm.wg.divmod(group, row, jg);
+        prm.wg.divmod(it.group, row, jg);
         prm.h.divmod(row, b, i);
-        // issue every load of the lane first (memory-level parallelism), then compute
         const T *grow = prm.g_full ? prm.g_full + (int64_t)b * prm.gf_sB + (int64_t)(i * R) * prm.gf_sH + (size_t)jg * (PX * R) : nullptr;
         const T *drow = nullptr;
         if constexpr (D > 0) {
             if (prm.g_ds) drow = prm.g_ds + (int64_t)b * prm.gd_sB + (int64_t)(i * NDS) * prm.gd_sH + (size_t)jg * (PX * NDS);
         }
-        load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
-        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, G);
-    } else {
+        load_elems<T, PX * 3, 4>(prm.coef + (size_t)it.group * (PX * 3), it.c);
+        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, it.G);
+    } else {            // lanes past the end still take part in the shuffles of their group
 #pragma unroll
-        for (int e = 0; e < PX * 3; ++e) c[e] = 0.0f;
+        for (int e = 0; e < PX * 3; ++e) it.c[e] = 0.0f;
 #pragma unroll
         for (int k = 0; k < ROWS; ++k)
 #pragma unroll
-            for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
+            for (int e = 0; e < PX * R; ++e) it.G[k][e] = 0.0f;
     }
+}
 
+template <typename T, int R, int PX, int ROWS>
+__device__ __forceinline__ void lpg_bwd_reduce(const LpgBwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, const BwdItem<R, PX, ROWS> &it) {
+    using S = Split<R, ROWS>;
+    if (S::LPP == 1 && !it.active) return;
     float gout[PX * 3];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
         Angles a;
-        decode_angles(c[3 * px], c[3 * px + 1], a);
+        decode_angles(it.c[3 * px], it.c[3 * px + 1], a);
         float acc[4];
-        lpg_patch_partial<R, PX, ROWS>(dir, G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
+        lpg_patch_partial<R, PX, ROWS>(dir, it.G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
         if constexpr (S::LPP > 1) {                 // fixed xor tree over the lanes that share the group
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -364,30 +399,53 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
                 for (int m = S::GPW; m < 32; m <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
             }
         }
-        lpg_finish_grad(a, c[3 * px + 2], acc, &gout[3 * px]);
+        lpg_finish_grad(a, it.c[3 * px + 2], acc, &gout[3 * px]);
     }
-    if (active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
+    if (it.active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)it.group * (PX * 3), gout);
 }
+
+template <typename T, int R, int PX, int ROWS, int D, int U>
+__device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot0, uint32_t stride) {
+    using S = Split<R, ROWS>;
+    const int sub = S::LPP == 1 ? 0 : (int)(slot0 & 31) / S::GPW;
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);
+    BwdItem<R, PX, ROWS> cur;
+    lpg_bwd_fetch<T, R, PX, ROWS, D>(prm, sub, slot0, cur);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        BwdItem<R, PX, ROWS> nxt;
+        if (u + 1 < U) lpg_bwd_fetch<T, R, PX, ROWS, D>(prm, sub, slot0 + (u + 1) * stride, nxt);
+        lpg_bwd_reduce<T, R, PX, ROWS>(prm, dir, sub, cur);
+        if (u + 1 < U) cur = nxt;
+    }
+}
+
+constexpr int kVecU = 1;   // slots per thread of the single-layer kernels
 
 template <typename T, int R, int PX, int ROWS, int D>
 __global__ void __launch_bounds__(256) lpg_fwd_vec_kernel(const __grid_constant__ LpgFwdParams<T> prm) {
-    lpg_fwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
+    lpg_fwd_thread<T, R, PX, ROWS, D, kVecU>(prm, blockIdx.x * (blockDim.x * kVecU) + threadIdx.x, blockDim.x);
 }
 template <typename T, int R, int PX, int ROWS, int D>
 __global__ void __launch_bounds__(256) lpg_bwd_vec_kernel(const __grid_constant__ LpgBwdParams<T> prm) {
-    lpg_bwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
+    lpg_bwd_thread<T, R, PX, ROWS, D, kVecU>(prm, blockIdx.x * (blockDim.x * kVecU) + threadIdx.x, blockDim.x);
 }
 
-// default (PX, ROWS) of the vectorised variants: every thread produces 16-32 output pixels
+// Default (PX, ROWS) of the vectorised variants, chosen for the smallest register footprint (occupancy
+// is what hides the load latency here; measured in profiles/r01_sweep_*.json):
+//   forward   r8: one thread per coarse pixel, all 8 rows (constant-bank weights, 32 registers)
+//   backward  r8: 4 lanes x 2 rows + shuffle tree (holding 8 rows of gradients would need 64 registers)
+//   r4: one coarse pixel per thread;  r2: two (float32) / four (bfloat16) coarse pixels per thread
 template <typename T> __host__ __device__ constexpr int px_max(int r) {
-    return sizeof(T) == 4 ? (r == 2 ? 4 : 1) : (r == 2 ? 4 : 2);
+    return sizeof(T) == 4 ? (r == 2 ? 2 : 1) : (r == 2 ? 4 : 2);
 }
-template <typename T> __host__ __device__ constexpr int rows_default(int r) {
-    return r == 8 ? 2 : r;
+template <typename T> __host__ __device__ constexpr int rows_default(int r, bool fwd) {
+    return r == 8 ? ((fwd && sizeof(T) == 4) ? 8 : 2) : r;
 }
-template <typename T, int R> struct VecCfg {
+template <typename T, int R, bool FWD> struct VecCfg {
     static constexpr int PX = px_max<T>(R);
-    static constexpr int ROWS = rows_default<T>(R);
+    static constexpr int ROWS = rows_default<T>(R, FWD);
     static constexpr int LPP = R / ROWS;
 };
 // threads needed for `groups` groups
@@ -415,35 +473,37 @@ template <typename T> struct LpgBwdMulti {
     int32_t n;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
+// U = slots per thread; MINB = minimum resident blocks per SM asked of the compiler (0 = unconstrained);
+// block size <= 128 whenever MINB > 0.
+template <typename T, int U, int MINB>
+__global__ void __launch_bounds__(MINB ? 128 : 256, MINB ? MINB : 1) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
     int l = 0;
     uint32_t first = 0;
 #pragma unroll
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgFwdParams<T> &prm = m.layer[l];
-    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
+    const uint32_t slot0 = (blockIdx.x - first) * (blockDim.x * U) + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8>::PX, VecCfg<T, 8>::ROWS, 4>(prm, slot); break;
-        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4>::PX, VecCfg<T, 4>::ROWS, 2>(prm, slot); break;
-        default: lpg_fwd_thread<T, 2, VecCfg<T, 2>::PX, VecCfg<T, 2>::ROWS, 0>(prm, slot); break;
+        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8, true>::PX, VecCfg<T, 8, true>::ROWS, 4, U>(prm, slot0, blockDim.x); break;
+        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4, true>::PX, VecCfg<T, 4, true>::ROWS, 2, U>(prm, slot0, blockDim.x); break;
+        default: lpg_fwd_thread<T, 2, VecCfg<T, 2, true>::PX, VecCfg<T, 2, true>::ROWS, 0, U>(prm, slot0, blockDim.x); break;
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) lpg_bwd_multi_kernel(const __grid_constant__ LpgBwdMulti<T> m) {
+template <typename T, int U, int MINB>
+__global__ void __launch_bounds__(MINB ? 128 : 256, MINB ? MINB : 1) lpg_bwd_multi_kernel(const __grid_constant__ LpgBwdMulti<T> m) {
     int l = 0;
     uint32_t first = 0;
 #pragma unroll
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgBwdParams<T> &prm = m.layer[l];
-    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
+    const uint32_t slot0 = (blockIdx.x - first) * (blockDim.x * U) + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8>::PX, VecCfg<T, 8>::ROWS, 4>(prm, slot); break;
-        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4>::PX, VecCfg<T, 4>::ROWS, 2>(prm, slot); break;
-        default: lpg_bwd_thread<T, 2, VecCfg<T, 2>::PX, VecCfg<T, 2>::ROWS, 0>(prm, slot); break;
+        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8, false>::PX, VecCfg<T, 8, false>::ROWS, 4, U>(prm, slot0, blockDim.x); break;
+        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4, false>::PX, VecCfg<T, 4, false>::ROWS, 2, U>(prm, slot0, blockDim.x); break;
+        default: lpg_bwd_thread<T, 2, VecCfg<T, 2, false>::PX, VecCfg<T, 2, false>::ROWS, 0, U>(prm, slot0, blockDim.x); break;
     }
 }
 
