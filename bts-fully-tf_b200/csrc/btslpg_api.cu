@@ -177,7 +177,7 @@ struct Variant {
     int px = 0, rows = 0;
     bool ok() const { return px > 0; }
 };
-std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0}, g_tune_r2_px{0}, g_tune_multi_u{0}, g_tune_multi_minb{-1};
+std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0}, g_tune_r2_px{0};
 
 int candidates(int dtype, int r, bool fwd, Variant *out) {
     int n = 0;
@@ -227,6 +227,9 @@ Variant pick_variant(const LayerGeom &g, bool fwd) {
     if (!is_contig_nhwc(g.coef) || !g.coef.aligned(16)) return none;
     if (g.has_full && g.full.sW != 1) return none;
     if (g.has_ds && g.ds.sW != 1) return none;
+    auto fits32 = [](int64_t v) { return v >= 0 && v < ((int64_t)1 << 31); };   // kernels keep strides in 32 bits
+    if (g.has_full && !(fits32(g.full.sB) && fits32(g.full.sH))) return none;
+    if (g.has_ds && !(fits32(g.ds.sB) && fits32(g.ds.sH))) return none;
     Variant c[6];
     const int n = candidates(g.coef.dtype, r, fwd, c);
     for (int k = 0; k < n; ++k)
@@ -239,8 +242,8 @@ template <typename T> LpgFwdParams<T> make_fwd_params(const LayerGeom &g, int px
     p.coef = reinterpret_cast<const T *>(g.coef.ptr);
     p.out = reinterpret_cast<T *>(g.full.ptr);
     p.ds = g.has_ds ? reinterpret_cast<T *>(g.ds.ptr) : nullptr;
-    p.out_sB = g.full.sB; p.out_sH = g.full.sH;
-    p.ds_sB = g.has_ds ? g.ds.sB : 0; p.ds_sH = g.has_ds ? g.ds.sH : 0;
+    p.out_sB = (uint32_t)g.full.sB; p.out_sH = (uint32_t)g.full.sH;
+    p.ds_sB = g.has_ds ? (uint32_t)g.ds.sB : 0; p.ds_sH = g.has_ds ? (uint32_t)g.ds.sH : 0;
     const uint32_t wg = (uint32_t)(g.coef.W / px);
     p.groups = (uint32_t)(g.coef.B * g.coef.H * wg);
     p.wg = FastDiv(wg);
@@ -254,8 +257,8 @@ template <typename T> LpgBwdParams<T> make_bwd_params(const LayerGeom &g, const 
     p.g_full = g.has_full ? reinterpret_cast<const T *>(g.full.ptr) : nullptr;
     p.g_ds = g.has_ds ? reinterpret_cast<const T *>(g.ds.ptr) : nullptr;
     p.g_coef = reinterpret_cast<T *>(gcoef.ptr);
-    p.gf_sB = g.has_full ? g.full.sB : 0; p.gf_sH = g.has_full ? g.full.sH : 0;
-    p.gd_sB = g.has_ds ? g.ds.sB : 0; p.gd_sH = g.has_ds ? g.ds.sH : 0;
+    p.gf_sB = g.has_full ? (uint32_t)g.full.sB : 0; p.gf_sH = g.has_full ? (uint32_t)g.full.sH : 0;
+    p.gd_sB = g.has_ds ? (uint32_t)g.ds.sB : 0; p.gd_sH = g.has_ds ? (uint32_t)g.ds.sH : 0;
     const uint32_t wg = (uint32_t)(g.coef.W / px);
     p.groups = (uint32_t)(g.coef.B * g.coef.H * wg);
     p.wg = FastDiv(wg);
@@ -290,13 +293,13 @@ template <typename T> LpgGenericParams<T> make_generic_params(const LayerGeom &g
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_fwd_variant(const LpgFwdParams<T> &p, int threads, cudaStream_t st) {
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
-    lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads * kVecU - 1) / (threads * kVecU), threads, 0, st>>>(p);
+    lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_bwd_variant(const LpgBwdParams<T> &p, int threads, cudaStream_t st) {
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
-    lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads * kVecU - 1) / (threads * kVecU), threads, 0, st>>>(p);
+    lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 
@@ -394,12 +397,6 @@ template <typename T> int run_backward(const LayerGeom &g, const View &gc, cudaS
     return check_launch("btslpg_backward");
 }
 
-constexpr int kMultiUDefault = 1;
-int multi_u() {
-    const int u = g_tune_multi_u.load();
-    return (u == 1 || u == 2 || u == 4) ? u : kMultiUDefault;
-}
-
 // multi-launch eligibility: the default vector variant (VecCfg) with the reference's ds stride (or none)
 template <typename T> bool multi_eligible_t(const LayerGeom &g, bool fwd) {
     if (g.r != 2 && g.r != 4 && g.r != 8) return false;
@@ -436,8 +433,6 @@ void btslpg_set_tuning(int key, int value) {
         case 2: g_tune_r8_rows.store(value); break;   // float32 r=8: patch rows per lane (2, 4 or 8)
         case 3: g_tune_r4_px.store(value); break;     // float32 r=4: coarse pixels per thread (1 or 2)
         case 6: g_tune_r2_px.store(value); break;     // float32 r=2: coarse pixels per thread (2 or 4)
-        case 4: g_tune_multi_u.store(value); break;   // multi-layer kernels: slots per thread (1, 2 or 4)
-        case 5: g_tune_multi_minb.store(value); break; // multi-layer kernels: register cap for 12 (fwd) / 8 (bwd) blocks of 128 per SM
         default: break;
     }
 }
@@ -494,9 +489,7 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
     }
     DeviceGuard guard(g[0].coef.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
-    const int U = multi_u(), minb = g_tune_multi_minb.load() != 0 ? 1 : 0;
-    int threads = block_threads(true, 4);
-    if (minb && threads > 128) threads = 128;
+    const int threads = kMultiThreads;
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
         LpgFwdMulti<T> m;
@@ -505,14 +498,11 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
         for (int k = 0; k < n; ++k) {
             m.layer[k] = make_fwd_params<T>(g[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, true)) + threads * U - 1) / (threads * U);
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, true)) + threads - 1) / threads;
             m.block_end[k] = blocks;
         }
         m.n = n;
-#define BTSLPG_FWD_MULTI(UU, MB) lpg_fwd_multi_kernel<T, UU, MB><<<blocks, threads, 0, st>>>(m)
-        if (minb) { if (U == 4) BTSLPG_FWD_MULTI(4, 16); else if (U == 2) BTSLPG_FWD_MULTI(2, 16); else BTSLPG_FWD_MULTI(1, 16); }
-        else { if (U == 4) BTSLPG_FWD_MULTI(4, 0); else if (U == 2) BTSLPG_FWD_MULTI(2, 0); else BTSLPG_FWD_MULTI(1, 0); }
-#undef BTSLPG_FWD_MULTI
+        lpg_fwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_forward_multi");
     };
@@ -538,9 +528,7 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
     }
     DeviceGuard guard(g[0].coef.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g[0].coef.dev, cudaGetErrorString(guard.err));
-    const int U = multi_u(), minb = g_tune_multi_minb.load() != 0 ? 1 : 0;
-    int threads = block_threads(false, 4);
-    if (minb && threads > 128) threads = 128;
+    const int threads = kMultiThreads;
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
         LpgBwdMulti<T> m;
@@ -549,14 +537,11 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
         for (int k = 0; k < n; ++k) {
             m.layer[k] = make_bwd_params<T>(g[k], gc[k], px_max<T>(g[k].r));
             m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, false)) + threads * U - 1) / (threads * U);
+            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, false)) + threads - 1) / threads;
             m.block_end[k] = blocks;
         }
         m.n = n;
-#define BTSLPG_BWD_MULTI(UU, MB) lpg_bwd_multi_kernel<T, UU, MB><<<blocks, threads, 0, st>>>(m)
-        if (minb) { if (U == 4) BTSLPG_BWD_MULTI(4, 12); else if (U == 2) BTSLPG_BWD_MULTI(2, 12); else BTSLPG_BWD_MULTI(1, 12); }
-        else { if (U == 4) BTSLPG_BWD_MULTI(4, 0); else if (U == 2) BTSLPG_BWD_MULTI(2, 0); else BTSLPG_BWD_MULTI(1, 0); }
-#undef BTSLPG_BWD_MULTI
+        lpg_bwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_backward_multi");
     };

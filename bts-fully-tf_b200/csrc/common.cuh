@@ -12,22 +12,28 @@ namespace btslpg {
 #define BTSLPG_EPS_F 1e-7f
 
 // ------------------------------------------------------------------------------------------------
-// Division of a 31-bit unsigned by a run-time constant without the integer-divide sequence.
+// Division of a 31-bit unsigned by a run-time constant in three instructions, no special cases
+// (Granlund-Montgomery "add" form): l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1,
+// q = (umulhi(n, m) + n) >> l.  umulhi(n, m) < n < 2^31, so the sum cannot overflow.  d = 1 gives
+// m = 1, l = 0 -> q = n.
 // ------------------------------------------------------------------------------------------------
 struct FastDiv {
     uint32_t d, mul, shr;
-    FastDiv() : d(1), mul(0), shr(0) {}
-    explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
-        if (div > 1) {
-            uint32_t lg = 0;
-            while ((1ull << lg) < div) ++lg;                 // ceil(log2(div))
-            uint32_t p = 31 + lg;
-            mul = (uint32_t)(((1ull << p) + div - 1) / div);
-            shr = p - 32;
-        }
+    FastDiv() : d(1), mul(1), shr(0) {}
+    explicit FastDiv(uint32_t div) : d(div ? div : 1), mul(1), shr(0) {
+        uint32_t l = 0;
+        while ((1ull << l) < d) ++l;                     // ceil(log2(d))
+        mul = (uint32_t)((((1ull << l) - d) << 32) / d) + 1;
+        shr = l;
     }
-    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
-    __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &rem) const {
+    __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+        return (__umulhi(n, mul) + n) >> shr;
+#else
+        return (uint32_t)(((((uint64_t)n * mul) >> 32) + n) >> shr);
+#endif
+    }
+    __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &rem) const {
         q = div(n);
         rem = n - q * d;
     }

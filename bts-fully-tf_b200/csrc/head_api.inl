@@ -35,6 +35,9 @@ bool head_maps_ok(const LayerGeom &g) {
     const int es = g.coef.esize();
     if (g.r != 2 && g.r != 4 && g.r != 8) return false;
     if (g.has_ds && (g.d != g.r / 2 || g.r == 2)) return false;
+    auto fits32 = [](int64_t s) { return s >= 0 && s < ((int64_t)1 << 31); };
+    if (g.has_full && !(fits32(g.full.sB) && fits32(g.full.sH))) return false;
+    if (g.has_ds && !(fits32(g.ds.sB) && fits32(g.ds.sH))) return false;
     const int row_bytes = g.r * es;
     if (row_bytes % 4) return false;
     if (g.has_full) {
@@ -105,8 +108,8 @@ template <typename T> int run_head_fwd_fast(const HeadGeom &hg, cudaStream_t st)
     p.coef_out = reinterpret_cast<T *>(g.coef.ptr);
     p.out = reinterpret_cast<T *>(g.full.ptr);
     p.ds = g.has_ds ? reinterpret_cast<T *>(g.ds.ptr) : nullptr;
-    p.out_sB = g.full.sB; p.out_sH = g.full.sH;
-    p.ds_sB = g.has_ds ? g.ds.sB : 0; p.ds_sH = g.has_ds ? g.ds.sH : 0;
+    p.out_sB = (uint32_t)g.full.sB; p.out_sH = (uint32_t)g.full.sH;
+    p.ds_sB = g.has_ds ? (uint32_t)g.ds.sB : 0; p.ds_sH = g.has_ds ? (uint32_t)g.ds.sH : 0;
     p.npix = (uint32_t)(g.coef.B * g.coef.H * g.coef.W);
     p.iters = (p.npix + 31) / 32;
     p.w = FastDiv((uint32_t)g.coef.W);
@@ -124,8 +127,8 @@ template <typename T> int run_head_bwd_fast(const HeadGeom &hg, const View *gfea
     p.coef = reinterpret_cast<const T *>(g.coef.ptr);
     p.g_full = g.has_full ? reinterpret_cast<const T *>(g.full.ptr) : nullptr;
     p.g_ds = g.has_ds ? reinterpret_cast<const T *>(g.ds.ptr) : nullptr;
-    p.gf_sB = g.has_full ? g.full.sB : 0; p.gf_sH = g.has_full ? g.full.sH : 0;
-    p.gd_sB = g.has_ds ? g.ds.sB : 0; p.gd_sH = g.has_ds ? g.ds.sH : 0;
+    p.gf_sB = g.has_full ? (uint32_t)g.full.sB : 0; p.gf_sH = g.has_full ? (uint32_t)g.full.sH : 0;
+    p.gd_sB = g.has_ds ? (uint32_t)g.ds.sB : 0; p.gd_sH = g.has_ds ? (uint32_t)g.ds.sH : 0;
     p.g_feat = gfeat ? reinterpret_cast<T *>(gfeat->ptr) : nullptr;
     p.g_kernel = gkern ? reinterpret_cast<float *>(gkern->ptr) : nullptr;
     p.g_coef_out = gcoef ? reinterpret_cast<T *>(gcoef->ptr) : nullptr;

@@ -36,7 +36,7 @@ template <typename T> struct HeadFwdParams {
     T *coef_out;          // (npix, 3) contiguous
     T *out;
     T *ds;                // nullable
-    int64_t out_sB, out_sH, ds_sB, ds_sH;
+    uint32_t out_sB, out_sH, ds_sB, ds_sH;   // < 2^31, checked on the host
     uint32_t npix, iters;
     FastDiv w, h;
 };
@@ -47,7 +47,7 @@ template <typename T> struct HeadBwdParams {
     const T *coef;        // saved sigmoid output (npix, 3)
     const T *g_full;      // nullable
     const T *g_ds;        // nullable
-    int64_t gf_sB, gf_sH, gd_sB, gd_sH;
+    uint32_t gf_sB, gf_sH, gd_sB, gd_sH;
     T *g_feat;            // nullable
     float *g_kernel;      // nullable, [C][3]
     T *g_coef_out;        // nullable
@@ -144,10 +144,10 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
             Angles a;
             decode_angles(x[0], x[1], a);
             float n1[1] = {a.st * a.cp}, n2[1] = {a.st * a.sp}, n3[1] = {a.ct}, n4[1] = {x[2]};
-            T *orow = prm.out + (int64_t)b * prm.out_sB + (int64_t)(i * R) * prm.out_sH + (size_t)j * R;
+            T *orow = prm.out + ((size_t)b * prm.out_sB + (size_t)(i * R) * prm.out_sH + j * R);
             T *drow = nullptr;
             if constexpr (D > 0) {
-                if (prm.ds) drow = prm.ds + (int64_t)b * prm.ds_sB + (int64_t)(i * NDS) * prm.ds_sH + (size_t)j * NDS;
+                if (prm.ds) drow = prm.ds + ((size_t)b * prm.ds_sB + (size_t)(i * NDS) * prm.ds_sH + j * NDS);
             }
             LaneDirs<R, R> dir;
             lpg_expand_store<T, R, 1, R, D>(dir, 0, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
@@ -188,10 +188,10 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_kernel(const __grid_constant
             prm.w.divmod(pix, row, j);
             prm.h.divmod(row, b, i);
             float G[R][R];
-            const T *grow = prm.g_full ? prm.g_full + (int64_t)b * prm.gf_sB + (int64_t)(i * R) * prm.gf_sH + (size_t)j * R : nullptr;
+            const T *grow = prm.g_full ? prm.g_full + ((size_t)b * prm.gf_sB + (size_t)(i * R) * prm.gf_sH + j * R) : nullptr;
             const T *drow = nullptr;
             if constexpr (D > 0) {
-                if (prm.g_ds) drow = prm.g_ds + (int64_t)b * prm.gd_sB + (int64_t)(i * NDS) * prm.gd_sH + (size_t)j * NDS;
+                if (prm.g_ds) drow = prm.g_ds + ((size_t)b * prm.gd_sB + (size_t)(i * NDS) * prm.gd_sH + j * NDS);
             }
             float x[3];
 #pragma unroll

@@ -34,17 +34,23 @@ template <int R> struct DirTable;
 template <> struct DirTable<2> {
     static __device__ __forceinline__ float off(int p) { return c_off2[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w2[k]; }
+    static __device__ __forceinline__ float v(int k) { return c_v2[k]; }
     static __device__ __forceinline__ const float *gw() { return g_w2; }
+    static __device__ __forceinline__ const float *gv() { return g_v2; }
 };
 template <> struct DirTable<4> {
     static __device__ __forceinline__ float off(int p) { return c_off4[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w4[k]; }
+    static __device__ __forceinline__ float v(int k) { return c_v4[k]; }
     static __device__ __forceinline__ const float *gw() { return g_w4; }
+    static __device__ __forceinline__ const float *gv() { return g_v4; }
 };
 template <> struct DirTable<8> {
     static __device__ __forceinline__ float off(int p) { return c_off8[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w8[k]; }
+    static __device__ __forceinline__ float v(int k) { return c_v8[k]; }
     static __device__ __forceinline__ const float *gw() { return g_w8; }
+    static __device__ __forceinline__ const float *gv() { return g_v8; }
 };
 
 struct Angles {
@@ -112,8 +118,11 @@ __device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
 //             kernels cannot afford).
 // ------------------------------------------------------------------------------------------------
 template <int R> __device__ __forceinline__ const float *stage_dir_table() {
-    __shared__ float tab[R * R];
-    for (int t = threadIdx.x; t < R * R; t += blockDim.x) tab[t] = DirTable<R>::gw()[t];
+    __shared__ float tab[2 * R * R];   // [0, R*R): w_pq ; [R*R, 2*R*R): v_pq = b_q * w_pq
+    for (int t = threadIdx.x; t < R * R; t += blockDim.x) {
+        tab[t] = DirTable<R>::gw()[t];
+        tab[R * R + t] = DirTable<R>::gv()[t];
+    }
     __syncthreads();
     return tab;
 }
@@ -127,11 +136,13 @@ template <int R, int ROWS> struct LaneDirs {
     }
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
     __device__ __forceinline__ float w(int k, int q) const { return sw[k * R + q]; }
+    __device__ __forceinline__ float v(int k, int q) const { return sw[R * R + k * R + q]; }
 };
 template <int R> struct LaneDirs<R, R> {
     __device__ __forceinline__ void init(int) {}
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k); }
     __device__ __forceinline__ float w(int k, int q) const { return DirTable<R>::w(k * R + q); }
+    __device__ __forceinline__ float v(int k, int q) const { return DirTable<R>::v(k * R + q); }
 };
 
 // does patch row (sub*ROWS + k) carry a down-sampled sample (row % D == 0)?
@@ -148,8 +159,8 @@ template <int ROWS, int D> __device__ __forceinline__ bool ds_row(int sub, int k
 // ------------------------------------------------------------------------------------------------
 template <typename T, int R, int PX, int ROWS, int D>
 __device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, int sub, const float (&n1)[PX], const float (&n2)[PX],
-                                                 const float (&n3)[PX], const float (&n4)[PX], T *orow, int64_t out_sH, T *drow,
-                                                 int64_t ds_sH) {
+                                                 const float (&n3)[PX], const float (&n4)[PX], T *orow, uint32_t out_sH, T *drow,
+                                                 uint32_t ds_sH) {
     using Tab = DirTable<R>;
     constexpr int NDS = D ? R / D : 0;
 #pragma unroll
@@ -166,7 +177,7 @@ __device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, i
             }
         }
         const int p = sub * ROWS + k;
-        store_elems<T, PX * R>(orow + (int64_t)p * out_sH, o);
+        store_elems<T, PX * R>(orow + (size_t)p * out_sH, o);
         if constexpr (D > 0) {
             if (drow && ds_row<ROWS, D>(sub, k)) {
                 float dsv[PX * NDS];
@@ -174,7 +185,7 @@ __device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, i
                 for (int px = 0; px < PX; ++px)
 #pragma unroll
                     for (int qq = 0; qq < NDS; ++qq) dsv[px * NDS + qq] = o[px * R + qq * D];
-                store_elems<T, PX * NDS>(drow + (int64_t)(p / D) * ds_sH, dsv);
+                store_elems<T, PX * NDS>(drow + (size_t)(p / D) * ds_sH, dsv);
             }
         }
     }
@@ -182,11 +193,11 @@ __device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, i
 
 // Gather G = g_full + scatter(g_ds) for rows [sub*ROWS, sub*ROWS+ROWS) of the patches of PX coarse pixels.
 template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, int64_t gf_sH, const T *drow, int64_t gd_sH, float (&G)[ROWS][PX * R]) {
+__device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, uint32_t gf_sH, const T *drow, uint32_t gd_sH, float (&G)[ROWS][PX * R]) {
     constexpr int NDS = D ? R / D : 0;
     if (grow) {
 #pragma unroll
-        for (int k = 0; k < ROWS; ++k) load_elems<T, PX * R>(grow + (int64_t)(sub * ROWS + k) * gf_sH, G[k]);
+        for (int k = 0; k < ROWS; ++k) load_elems<T, PX * R>(grow + (size_t)(sub * ROWS + k) * gf_sH, G[k]);
     } else {
 #pragma unroll
         for (int k = 0; k < ROWS; ++k)
@@ -199,7 +210,7 @@ __device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, int64_t g
             for (int k = 0; k < ROWS; ++k) {
                 if (ds_row<ROWS, D>(sub, k)) {
                     float t[PX * NDS];
-                    load_elems<T, PX * NDS>(drow + (int64_t)((sub * ROWS + k) / D) * gd_sH, t);
+                    load_elems<T, PX * NDS>(drow + (size_t)((sub * ROWS + k) / D) * gd_sH, t);
 #pragma unroll
                     for (int px = 0; px < PX; ++px)
 #pragma unroll
@@ -211,8 +222,9 @@ __device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, int64_t g
 }
 
 // Partial sums of one lane over its ROWS rows of the patch of coarse pixel `px`:
-//   u = G/den ; acc[3] += u ; z = u/den * w ; acc[2] += z ; acc[1] += b_q z ; acc[0] += a_p * (row sum of z)
-// so that, after the lanes of a group are added, g1..g3 = -n4 * acc[0..2] and g4 = acc[3].
+//   inv = 1/den ; u = G*inv ; y = u*inv ; acc[3] += u ; acc[2] += y*w ; acc[1] += y*v ; acc[0] += a_p * (row sum of y*w)
+// (w, v = b_q*w from the direction table) so that, after the lanes of a group are added,
+// g1..g3 = -n4 * acc[0..2] and g4 = acc[3].  8 instructions per pixel: 2 FFMA (den), MUFU.RCP, 2 FMUL, FADD, 2 FFMA.
 template <int R, int PX, int ROWS>
 __device__ __forceinline__ void lpg_patch_partial(const LaneDirs<R, ROWS> &dir, const float (&G)[ROWS][PX * R], int px, float n1,
                                                   float n2, float n3, float (&acc)[4]) {
@@ -226,13 +238,12 @@ __device__ __forceinline__ void lpg_patch_partial(const LaneDirs<R, ROWS> &dir, 
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const float s = fmaf(Tab::off(q), n2, A);
-            const float w = dir.w(k, q);
-            const float inv = rcp_approx(fmaf(w, s, BTSLPG_EPS_F));
+            const float inv = rcp_approx(fmaf(dir.w(k, q), s, BTSLPG_EPS_F));
             const float u = G[k][px * R + q] * inv;
-            const float z = (u * inv) * w;
+            const float y = u * inv;
             r4 += u;
-            r3 += z;
-            r2 = fmaf(z, Tab::off(q), r2);
+            r3 = fmaf(y, dir.w(k, q), r3);
+            r2 = fmaf(y, dir.v(k, q), r2);
         }
         acc[0] = fmaf(ap, r3, acc[0]);
         acc[1] += r2;
@@ -259,8 +270,8 @@ template <typename T> struct LpgFwdParams {
     const T *coef;
     T *out;
     T *ds;                 // nullable
-    int64_t out_sB, out_sH; // element strides of out (column stride 1)
-    int64_t ds_sB, ds_sH;
+    uint32_t out_sB, out_sH; // element strides of out (column stride 1); < 2^31, checked on the host
+    uint32_t ds_sB, ds_sH;
     uint32_t groups;
     FastDiv wg, h;          // groups per coarse row, coarse rows per image
 };
@@ -270,8 +281,8 @@ template <typename T> struct LpgBwdParams {
     const T *g_full;  // nullable
     const T *g_ds;    // nullable
     T *g_coef;
-    int64_t gf_sB, gf_sH;
-    int64_t gd_sB, gd_sH;
+    uint32_t gf_sB, gf_sH;
+    uint32_t gd_sB, gd_sH;
     uint32_t groups;
     FastDiv wg, h;
 };
@@ -282,116 +293,86 @@ template <int R, int ROWS> struct Split {
     static_assert(R % ROWS == 0 && (LPP == 1 || LPP == 2 || LPP == 4), "bad row split");
 };
 
-// ------------------------------------------------------------------------------------------------
-// A thread works on U "slots" (slot = one lane's share of a group), `stride` slots apart, with the
-// inputs of slot u+1 requested before slot u is computed (one-ahead software prefetch): the load
-// latency is exposed once per thread instead of once per slot, and the per-thread set-up (direction
-// weights, parameters) is amortised.  stride is a multiple of 32, so lane and row-group are fixed.
-// ------------------------------------------------------------------------------------------------
+// `slot` = index of this thread among the threads of its layer: one lane's share of one group.
 template <int R, int ROWS> __device__ __forceinline__ uint32_t slot_group(uint32_t slot) {
     using S = Split<R, ROWS>;
     return S::LPP == 1 ? slot : (slot >> 5) * S::GPW + ((slot & 31) % S::GPW);
 }
 
-template <int PX> struct FwdItem {
-    float c[PX * 3];
-    uint32_t group;
-    bool active;
-};
-
-template <typename T, int R, int PX, int ROWS>
-__device__ __forceinline__ void lpg_fwd_fetch(const LpgFwdParams<T> &prm, uint32_t slot, FwdItem<PX> &it) {
-    it.group = slot_group<R, ROWS>(slot);
-    it.active = it.group < prm.groups;
-    if (it.active) load_elems<T, PX * 3, 4>(prm.coef + (size_t)it.group * (PX * 3), it.c);
-}
-
 template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_fwd_emit(const LpgFwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, const FwdItem<PX> &it) {
+__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
+    using S = Split<R, ROWS>;
     constexpr int NDS = D ? R / D : 0;
-    if (!it.active) return;
+    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);                                  // (CTA-wide barrier inside when the patch is split)
+    const uint32_t group = slot_group<R, ROWS>(slot);
+    if (group >= prm.groups) return;
+
+    float c[PX * 3];
+    load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
     uint32_t row, jg, b, i;
-    prm.wg.divmod(it.group, row, jg);
+    prm.wg.divmod(group, row, jg);
     prm.h.divmod(row, b, i);
+    T *orow = prm.out + ((size_t)b * prm.out_sB + (size_t)(i * R) * prm.out_sH + jg * (PX * R));
+    T *drow = nullptr;
+    if constexpr (D > 0) {
+        if (prm.ds) drow = prm.ds + ((size_t)b * prm.ds_sB + (size_t)(i * NDS) * prm.ds_sH + jg * (PX * NDS));
+    }
     float n1[PX], n2[PX], n3[PX], n4[PX];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
         Angles a;
-        decode_angles(it.c[3 * px], it.c[3 * px + 1], a);
+        decode_angles(c[3 * px], c[3 * px + 1], a);
         n1[px] = a.st * a.cp;   // custom_layers.py:50
         n2[px] = a.st * a.sp;
         n3[px] = a.ct;
-        n4[px] = it.c[3 * px + 2];
-    }
-    T *orow = prm.out + (int64_t)b * prm.out_sB + (int64_t)(i * R) * prm.out_sH + (size_t)jg * (PX * R);
-    T *drow = nullptr;
-    if constexpr (D > 0) {
-        if (prm.ds) drow = prm.ds + (int64_t)b * prm.ds_sB + (int64_t)(i * NDS) * prm.ds_sH + (size_t)jg * (PX * NDS);
+        n4[px] = c[3 * px + 2];
     }
     lpg_expand_store<T, R, PX, ROWS, D>(dir, sub, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
 }
 
-template <typename T, int R, int PX, int ROWS, int D, int U>
-__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot0, uint32_t stride) {
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot) {
     using S = Split<R, ROWS>;
-    const int sub = S::LPP == 1 ? 0 : (int)(slot0 & 31) / S::GPW;
+    constexpr int NDS = D ? R / D : 0;
+    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
     LaneDirs<R, ROWS> dir;
     dir.init(sub);
-    FwdItem<PX> cur;
-    lpg_fwd_fetch<T, R, PX, ROWS>(prm, slot0, cur);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        FwdItem<PX> nxt;
-        if (u + 1 < U) lpg_fwd_fetch<T, R, PX, ROWS>(prm, slot0 + (u + 1) * stride, nxt);
-        lpg_fwd_emit<T, R, PX, ROWS, D>(prm, dir, sub, cur);
-        if (u + 1 < U) cur = nxt;
-    }
-}
+    const uint32_t group = slot_group<R, ROWS>(slot);
+    const bool active = group < prm.groups;
+    if (S::LPP == 1 && !active) return;            // with LPP > 1 every lane takes part in the shuffles
 
-template <int R, int PX, int ROWS> struct BwdItem {
     float G[ROWS][PX * R];
     float c[PX * 3];
-    uint32_t group;
-    bool active;
-};
-
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_bwd_fetch(const LpgBwdParams<T> &prm, int sub, uint32_t slot, BwdItem<R, PX, ROWS> &it) {
-    constexpr int NDS = D ? R / D : 0;
-    it.group = slot_group<R, ROWS>(slot);
-    it.active = it.group < prm.groups;
-    if (it.active) {
+    if (S::LPP == 1 || active) {
+        // issue every load of the lane first (memory-level parallelism), then compute
         uint32_t row, jg, b, i;
-        prm.wg.divmod(it.group, row, jg);
+        prm.wg.divmod(group, row, jg);
         prm.h.divmod(row, b, i);
-        const T *grow = prm.g_full ? prm.g_full + (int64_t)b * prm.gf_sB + (int64_t)(i * R) * prm.gf_sH + (size_t)jg * (PX * R) : nullptr;
+        const T *grow = prm.g_full ? prm.g_full + ((size_t)b * prm.gf_sB + (size_t)(i * R) * prm.gf_sH + jg * (PX * R)) : nullptr;
         const T *drow = nullptr;
         if constexpr (D > 0) {
-            if (prm.g_ds) drow = prm.g_ds + (int64_t)b * prm.gd_sB + (int64_t)(i * NDS) * prm.gd_sH + (size_t)jg * (PX * NDS);
+            if (prm.g_ds) drow = prm.g_ds + ((size_t)b * prm.gd_sB + (size_t)(i * NDS) * prm.gd_sH + jg * (PX * NDS));
         }
-        load_elems<T, PX * 3, 4>(prm.coef + (size_t)it.group * (PX * 3), it.c);
-        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, it.G);
-    } else {            // lanes past the end still take part in the shuffles of their group
+        load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
+        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, G);
+    } else {
 #pragma unroll
-        for (int e = 0; e < PX * 3; ++e) it.c[e] = 0.0f;
+        for (int e = 0; e < PX * 3; ++e) c[e] = 0.0f;
 #pragma unroll
         for (int k = 0; k < ROWS; ++k)
 #pragma unroll
-            for (int e = 0; e < PX * R; ++e) it.G[k][e] = 0.0f;
+            for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
     }
-}
 
-template <typename T, int R, int PX, int ROWS>
-__device__ __forceinline__ void lpg_bwd_reduce(const LpgBwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, const BwdItem<R, PX, ROWS> &it) {
-    using S = Split<R, ROWS>;
-    if (S::LPP == 1 && !it.active) return;
     float gout[PX * 3];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
         Angles a;
-        decode_angles(it.c[3 * px], it.c[3 * px + 1], a);
+        decode_angles(c[3 * px], c[3 * px + 1], a);
         float acc[4];
-        lpg_patch_partial<R, PX, ROWS>(dir, it.G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
+        lpg_patch_partial<R, PX, ROWS>(dir, G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
         if constexpr (S::LPP > 1) {                 // fixed xor tree over the lanes that share the group
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -399,37 +380,18 @@ __device__ __forceinline__ void lpg_bwd_reduce(const LpgBwdParams<T> &prm, const
                 for (int m = S::GPW; m < 32; m <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
             }
         }
-        lpg_finish_grad(a, it.c[3 * px + 2], acc, &gout[3 * px]);
+        lpg_finish_grad(a, c[3 * px + 2], acc, &gout[3 * px]);
     }
-    if (it.active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)it.group * (PX * 3), gout);
+    if (active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
 }
-
-template <typename T, int R, int PX, int ROWS, int D, int U>
-__device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot0, uint32_t stride) {
-    using S = Split<R, ROWS>;
-    const int sub = S::LPP == 1 ? 0 : (int)(slot0 & 31) / S::GPW;
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);
-    BwdItem<R, PX, ROWS> cur;
-    lpg_bwd_fetch<T, R, PX, ROWS, D>(prm, sub, slot0, cur);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        BwdItem<R, PX, ROWS> nxt;
-        if (u + 1 < U) lpg_bwd_fetch<T, R, PX, ROWS, D>(prm, sub, slot0 + (u + 1) * stride, nxt);
-        lpg_bwd_reduce<T, R, PX, ROWS>(prm, dir, sub, cur);
-        if (u + 1 < U) cur = nxt;
-    }
-}
-
-constexpr int kVecU = 1;   // slots per thread of the single-layer kernels
 
 template <typename T, int R, int PX, int ROWS, int D>
 __global__ void __launch_bounds__(256) lpg_fwd_vec_kernel(const __grid_constant__ LpgFwdParams<T> prm) {
-    lpg_fwd_thread<T, R, PX, ROWS, D, kVecU>(prm, blockIdx.x * (blockDim.x * kVecU) + threadIdx.x, blockDim.x);
+    lpg_fwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
 }
 template <typename T, int R, int PX, int ROWS, int D>
 __global__ void __launch_bounds__(256) lpg_bwd_vec_kernel(const __grid_constant__ LpgBwdParams<T> prm) {
-    lpg_bwd_thread<T, R, PX, ROWS, D, kVecU>(prm, blockIdx.x * (blockDim.x * kVecU) + threadIdx.x, blockDim.x);
+    lpg_bwd_thread<T, R, PX, ROWS, D>(prm, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Default (PX, ROWS) of the vectorised variants, chosen for the smallest register footprint (occupancy
@@ -473,37 +435,42 @@ template <typename T> struct LpgBwdMulti {
     int32_t n;
 };
 
-// U = slots per thread; MINB = minimum resident blocks per SM asked of the compiler (0 = unconstrained);
-// block size <= 128 whenever MINB > 0.
-template <typename T, int U, int MINB>
-__global__ void __launch_bounds__(MINB ? 128 : 256, MINB ? MINB : 1) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
+// MINB = minimum resident CTAs per SM asked of the compiler (caps registers: occupancy is what hides the
+// one-shot load latency of these kernels); block size is 128.
+constexpr int kMultiThreads = 128;
+// float32: 16 / 12 CTAs per SM (<= 32 / 40 registers); bfloat16 threads hold twice the pixels: 12 / 8
+template <typename T> constexpr int fwd_min_blocks() { return sizeof(T) == 4 ? 16 : 12; }
+template <typename T> constexpr int bwd_min_blocks() { return sizeof(T) == 4 ? 12 : 8; }
+
+template <typename T>
+__global__ void __launch_bounds__(kMultiThreads, fwd_min_blocks<T>()) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
     int l = 0;
     uint32_t first = 0;
 #pragma unroll
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgFwdParams<T> &prm = m.layer[l];
-    const uint32_t slot0 = (blockIdx.x - first) * (blockDim.x * U) + threadIdx.x;
+    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8, true>::PX, VecCfg<T, 8, true>::ROWS, 4, U>(prm, slot0, blockDim.x); break;
-        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4, true>::PX, VecCfg<T, 4, true>::ROWS, 2, U>(prm, slot0, blockDim.x); break;
-        default: lpg_fwd_thread<T, 2, VecCfg<T, 2, true>::PX, VecCfg<T, 2, true>::ROWS, 0, U>(prm, slot0, blockDim.x); break;
+        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8, true>::PX, VecCfg<T, 8, true>::ROWS, 4>(prm, slot); break;
+        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4, true>::PX, VecCfg<T, 4, true>::ROWS, 2>(prm, slot); break;
+        default: lpg_fwd_thread<T, 2, VecCfg<T, 2, true>::PX, VecCfg<T, 2, true>::ROWS, 0>(prm, slot); break;
     }
 }
 
-template <typename T, int U, int MINB>
-__global__ void __launch_bounds__(MINB ? 128 : 256, MINB ? MINB : 1) lpg_bwd_multi_kernel(const __grid_constant__ LpgBwdMulti<T> m) {
+template <typename T>
+__global__ void __launch_bounds__(kMultiThreads, bwd_min_blocks<T>()) lpg_bwd_multi_kernel(const __grid_constant__ LpgBwdMulti<T> m) {
     int l = 0;
     uint32_t first = 0;
 #pragma unroll
     for (int k = 0; k < kMaxMulti - 1; ++k)
         if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
     const LpgBwdParams<T> &prm = m.layer[l];
-    const uint32_t slot0 = (blockIdx.x - first) * (blockDim.x * U) + threadIdx.x;
+    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
     switch (m.upratio[l]) {
-        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8, false>::PX, VecCfg<T, 8, false>::ROWS, 4, U>(prm, slot0, blockDim.x); break;
-        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4, false>::PX, VecCfg<T, 4, false>::ROWS, 2, U>(prm, slot0, blockDim.x); break;
-        default: lpg_bwd_thread<T, 2, VecCfg<T, 2, false>::PX, VecCfg<T, 2, false>::ROWS, 0, U>(prm, slot0, blockDim.x); break;
+        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8, false>::PX, VecCfg<T, 8, false>::ROWS, 4>(prm, slot); break;
+        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4, false>::PX, VecCfg<T, 4, false>::ROWS, 2>(prm, slot); break;
+        default: lpg_bwd_thread<T, 2, VecCfg<T, 2, false>::PX, VecCfg<T, 2, false>::ROWS, 0>(prm, slot); break;
     }
 }
 
@@ -586,10 +553,10 @@ template <typename T> __global__ void __launch_bounds__(128) lpg_bwd_generic_ker
             const float s = fmaf(bq, n2, A);
             const float inv = rcp_approx(fmaf(w, s, BTSLPG_EPS_F));
             const float u = G * inv;
-            const float z = (u * inv) * w;
+            const float y = u * inv;
             r4 += u;
-            r3 += z;
-            r2 = fmaf(z, bq, r2);
+            r3 = fmaf(y, w, r3);
+            r2 = fmaf(y, bq * w, r2);
         }
         acc[0] = fmaf(ap, r3, acc[0]);
         acc[1] += r2;
