@@ -85,6 +85,20 @@ template <> __device__ __forceinline__ void ldg_nc<8>(const void *p, uint32_t *w
                  : "l"(p));
 }
 
+// Same, but allocating in L1: for the 12-byte coefficient pixels, whose three words are fetched by
+// separate instructions (and, when a patch is split over lanes, by several lanes) -- the first touch
+// brings the sector, the others hit.
+template <int VW> __device__ __forceinline__ void ldg_nc_l1(const void *p, uint32_t *w);
+template <> __device__ __forceinline__ void ldg_nc_l1<1>(const void *p, uint32_t *w) {
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ldg_nc_l1<2>(const void *p, uint32_t *w) {
+    asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ldg_nc_l1<4>(const void *p, uint32_t *w) {
+    asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+}
+
 template <int VW> __device__ __forceinline__ void stg(void *p, const uint32_t *w);
 template <> __device__ __forceinline__ void stg<1>(void *p, const uint32_t *w) {
     asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
@@ -112,14 +126,17 @@ __host__ __device__ constexpr int vec_words(int nwords, int cap) {
 
 // Load N contiguous elements of T (N*sizeof(T) a multiple of 4 bytes; address aligned to the chosen
 // vector width, which the host guarantees) and widen to float.
-template <typename T, int N, int CAPW = 8> __device__ __forceinline__ void load_elems(const T *p, float (&v)[N]) {
+template <typename T, int N, int CAPW = 8, bool L1 = false> __device__ __forceinline__ void load_elems(const T *p, float (&v)[N]) {
     constexpr int NB = N * (int)sizeof(T);
     static_assert(NB % 4 == 0, "load_elems needs whole 32-bit words");
     constexpr int NW = NB / 4;
-    constexpr int VW = vec_words(NW, CAPW);
+    constexpr int VW = vec_words(NW, L1 ? cmin(CAPW, 4) : CAPW);
     uint32_t w[NW];
 #pragma unroll
-    for (int i = 0; i < NW; i += VW) ldg_nc<VW>(reinterpret_cast<const uint32_t *>(p) + i, w + i);
+    for (int i = 0; i < NW; i += VW) {
+        if constexpr (L1) ldg_nc_l1<VW>(reinterpret_cast<const uint32_t *>(p) + i, w + i);
+        else ldg_nc<VW>(reinterpret_cast<const uint32_t *>(p) + i, w + i);
+    }
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = __uint_as_float(w[i]);

@@ -304,13 +304,14 @@ __device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint3
     using S = Split<R, ROWS>;
     constexpr int NDS = D ? R / D : 0;
     const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);                                  // (CTA-wide barrier inside when the patch is split)
     const uint32_t group = slot_group<R, ROWS>(slot);
-    if (group >= prm.groups) return;
-
+    const bool active = group < prm.groups;
+    if (S::LPP == 1 && !active) return;
     float c[PX * 3];
-    load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
+    if (active) load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);                                  // CTA-wide barrier inside when the patch is split: every thread reaches it
+    if (!active) return;
     uint32_t row, jg, b, i;
     prm.wg.divmod(group, row, jg);
     prm.h.divmod(row, b, i);
@@ -337,8 +338,6 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
     using S = Split<R, ROWS>;
     constexpr int NDS = D ? R / D : 0;
     const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);
     const uint32_t group = slot_group<R, ROWS>(slot);
     const bool active = group < prm.groups;
     if (S::LPP == 1 && !active) return;            // with LPP > 1 every lane takes part in the shuffles
@@ -355,7 +354,7 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
         if constexpr (D > 0) {
             if (prm.g_ds) drow = prm.g_ds + ((size_t)b * prm.gd_sB + (size_t)(i * NDS) * prm.gd_sH + jg * (PX * NDS));
         }
-        load_elems<T, PX * 3, 4>(prm.coef + (size_t)group * (PX * 3), c);
+        load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
         lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, G);
     } else {
 #pragma unroll
@@ -365,7 +364,9 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
 #pragma unroll
             for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
     }
-
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);                                  // after the loads are in flight: staging the table (and its
+                                                    // CTA barrier, when the patch is split) overlaps their latency
     float gout[PX * 3];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
