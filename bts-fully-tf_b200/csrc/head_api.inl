@@ -62,13 +62,35 @@ template <typename KernelT> int occupancy_blocks(KernelT kernel, int threads) {
     return per_sm * sms;
 }
 
+std::atomic<int> g_tune_head_impl{0};   // 0 = TMA-staged (default), 1 = register-staged loads
+
+template <typename KernelT> int occupancy_blocks_smem(KernelT kernel, int threads, int smem) {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    if (sms < 1) sms = 148;
+    return per_sm * sms;
+}
+
 template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdParams<T> &p, cudaStream_t st) {
     const int threads = 256;
-    static const int resident = occupancy_blocks(head_lpg_fwd_kernel<T, R, D, M>, threads);
+    if (g_tune_head_impl.load() == 1) {
+        static const int resident = occupancy_blocks(head_lpg_fwd_kernel<T, R, D, M>, threads);
+        uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
+        if (blocks > (uint32_t)resident) blocks = resident;
+        head_lpg_fwd_kernel<T, R, D, M><<<blocks, threads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_fwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
+        return check_launch("btslpg_reduce_forward");
+    }
+    constexpr int smem = head_tma_smem_bytes<T, M>(256 / 32);
+    static const int resident = occupancy_blocks_smem(head_lpg_fwd_tma_kernel<T, R, D, M>, threads, smem);
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;
-    head_lpg_fwd_kernel<T, R, D, M><<<blocks, threads, 0, st>>>(p);
-    snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_fwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
+    head_lpg_fwd_tma_kernel<T, R, D, M><<<blocks, threads, smem, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_fwd_tma<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
     return check_launch("btslpg_reduce_forward");
 }
 

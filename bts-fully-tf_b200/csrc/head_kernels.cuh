@@ -24,6 +24,7 @@
 #pragma once
 
 #include "lpg_kernels.cuh"
+#include "tma_pipe.cuh"
 
 namespace btslpg {
 
@@ -129,6 +130,136 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
         }
         float z[3];
         butterfly8x3(acc, s, z);
+
+        const uint32_t pix = p0 + lane;
+        if (pix < prm.npix) {
+            float x[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                x[k] = round_to<T>(sigmoidf_acc(z[k]));                  // bts_decoder.py:79 activation='sigmoid'
+                store1(prm.coef_out + (size_t)pix * 3 + k, x[k]);
+            }
+            uint32_t row, j, b, i;
+            prm.w.divmod(pix, row, j);
+            prm.h.divmod(row, b, i);
+            Angles a;
+            decode_angles(x[0], x[1], a);
+            float n1[1] = {a.st * a.cp}, n2[1] = {a.st * a.sp}, n3[1] = {a.ct}, n4[1] = {x[2]};
+            T *orow = prm.out + ((size_t)b * prm.out_sB + (size_t)(i * R) * prm.out_sH + j * R);
+            T *drow = nullptr;
+            if constexpr (D > 0) {
+                if (prm.ds) drow = prm.ds + ((size_t)b * prm.ds_sB + (size_t)(i * NDS) * prm.ds_sH + j * NDS);
+            }
+            LaneDirs<R, R> dir;
+            lpg_expand_store<T, R, 1, R, D>(dir, 0, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged forward.  The feature map is the only large input and 32 coarse pixels x C channels are
+// ONE contiguous block of memory, so each warp streams its tiles through a private ring of NS
+// shared-memory stages filled by 1-D bulk copies (cp.async.bulk, mbarrier completion): a chunk is
+// 4 pixels x C channels (0.5-2 KB); lane 0 keeps NS-1 chunks in flight while the warp consumes the
+// current one, so the HBM latency is hidden by the ring instead of by registers or occupancy.
+// Lane (g, s) of a chunk reads pixel g, channels [32m+4s, 32m+4s+4): a quarter warp reads 128
+// contiguous bytes per LDS (conflict-free).  After 8 chunks the 3-level butterfly leaves lane (g, s)
+// with pixel 4s+g; one index shuffle puts pixel L on lane L for coalesced coefficient / depth stores.
+// ------------------------------------------------------------------------------------------------
+template <int M> struct HeadTmaCfg {
+    static constexpr int kStages = 4;
+    static constexpr int kChunkPx = 4;
+};
+
+template <typename T, int M> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
+    return warps * HeadTmaCfg<M>::kStages * (HeadTmaCfg<M>::kChunkPx * 32 * M * (int)sizeof(T) + 8);
+}
+
+template <typename T, int R, int D, int M>
+__global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_constant__ HeadFwdParams<T> prm) {
+    constexpr int C = 32 * M;
+    constexpr int NDS = D ? R / D : 0;
+    constexpr int NS = HeadTmaCfg<M>::kStages;
+    constexpr int CPX = HeadTmaCfg<M>::kChunkPx;
+    constexpr uint32_t PX_BYTES = C * sizeof(T);
+    constexpr uint32_t CHUNK_BYTES = CPX * PX_BYTES;
+    extern __shared__ __align__(128) unsigned char head_smem[];
+
+    const int lane = threadIdx.x & 31, s = lane & 7, g = lane >> 3, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned char *ring = head_smem + (size_t)wid * NS * CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(head_smem + (size_t)nw * NS * CHUNK_BYTES) + wid * NS;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) mbar_init(&bars[k], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    float wk[M][4][3];
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) wk[m][e][k] = __ldg(prm.kernel + (32 * m + 4 * s + e) * 3 + k);
+
+    // chunk q of this warp: tile (q >> 3), pixels [px0, px0 + 4)
+    const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
+    const uint32_t nchunks = ntiles * 8;
+    auto chunk_px0 = [&](uint32_t q) { return (warp + (q >> 3) * nwarps) * 32 + (q & 7) * CPX; };
+    auto issue = [&](uint32_t q) {          // lane 0 only
+        if (q < nchunks) {
+            const uint32_t px0 = chunk_px0(q);
+            if (px0 < prm.npix) {
+                const uint32_t npx = min((uint32_t)CPX, prm.npix - px0);
+                uint64_t *bar = &bars[q % NS];
+                mbar_arrive_expect_tx(bar, npx * PX_BYTES);
+                bulk_g2s(ring + (q % NS) * CHUNK_BYTES, prm.feat + (size_t)px0 * C, npx * PX_BYTES, bar);
+            }
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) issue(k);
+    }
+
+    uint32_t q = 0;
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t p0 = (warp + t * nwarps) * 32;
+        float acc[8][3];
+#pragma unroll
+        for (int it = 0; it < 8; ++it, ++q) {
+            acc[it][0] = acc[it][1] = acc[it][2] = 0.0f;
+            const uint32_t px0 = p0 + it * CPX;
+            if (px0 < prm.npix) {                                   // warp-uniform
+                mbar_wait(&bars[q % NS], (q / NS) & 1);
+                if (px0 + g < prm.npix) {
+                    const unsigned char *src = ring + (q % NS) * CHUNK_BYTES + g * PX_BYTES + 4 * s * sizeof(T);
+                    float f[M][4];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) lds_elems<T, 4>(src + 32 * m * sizeof(T), f[m]);
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) acc[it][k] = fmaf(f[m][e], wk[m][e][k], acc[it][k]);
+                }
+                __syncwarp();                                       // every lane has read the stage
+                if (lane == 0) {
+                    fence_proxy_async();
+                    issue(q + NS);
+                }
+            }
+        }
+        float z[3];
+        butterfly8x3(acc, s, z);                                    // lane (g, s) holds pixel p0 + 4 s + g
+        const int src_lane = 8 * (lane & 3) + (lane >> 2);          // lane L takes pixel p0 + L
+#pragma unroll
+        for (int k = 0; k < 3; ++k) z[k] = __shfl_sync(0xffffffffu, z[k], src_lane);
 
         const uint32_t pix = p0 + lane;
         if (pix < prm.npix) {
