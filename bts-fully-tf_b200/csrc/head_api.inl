@@ -96,12 +96,22 @@ template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdPara
 
 template <typename T, int R, int D, int M> int launch_head_bwd(HeadBwdParams<T> &p, uint32_t max_blocks, cudaStream_t st) {
     const int threads = 256;
-    static const int resident = occupancy_blocks(head_lpg_bwd_kernel<T, R, D, M>, threads);
+    if (g_tune_head_impl.load() == 1) {
+        static const int resident = occupancy_blocks(head_lpg_bwd_kernel<T, R, D, M>, threads);
+        uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
+        if (blocks > (uint32_t)resident) blocks = resident;
+        if (blocks > max_blocks) blocks = max_blocks;
+        head_lpg_bwd_kernel<T, R, D, M><<<blocks, threads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
+        return check_launch("btslpg_reduce_backward");
+    }
+    constexpr int smem = head_tma_smem_bytes<T, M>(256 / 32);
+    static const int resident = occupancy_blocks_smem(head_lpg_bwd_tma_kernel<T, R, D, M>, threads, smem);
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;
     if (blocks > max_blocks) blocks = max_blocks;
-    head_lpg_bwd_kernel<T, R, D, M><<<blocks, threads, 0, st>>>(p);
-    snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
+    head_lpg_bwd_tma_kernel<T, R, D, M><<<blocks, threads, smem, st>>>(p);
+    snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd_tma<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
     return check_launch("btslpg_reduce_backward");
 }
 

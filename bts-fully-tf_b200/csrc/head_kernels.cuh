@@ -166,37 +166,90 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
 // contiguous bytes per LDS (conflict-free).  After 8 chunks the 3-level butterfly leaves lane (g, s)
 // with pixel 4s+g; one index shuffle puts pixel L on lane L for coalesced coefficient / depth stores.
 // ------------------------------------------------------------------------------------------------
-template <int M> struct HeadTmaCfg {
+// A stage of a warp's ring is one bulk copy of ~2 KB: CPB consecutive 4-pixel chunks.
+template <typename T, int M> struct HeadTmaCfg {
     static constexpr int kStages = 4;
-    static constexpr int kChunkPx = 4;
+    static constexpr int kChunkPx = 4;                                        // pixels per chunk (= lane groups)
+    static constexpr int kPxBytes = 32 * M * (int)sizeof(T);
+    static constexpr int kChunkBytes = kChunkPx * kPxBytes;
+    static constexpr int kCPB = (2048 / kChunkBytes) < 1 ? 1 : ((2048 / kChunkBytes) > 8 ? 8 : (2048 / kChunkBytes));
+    static constexpr int kStageBytes = kCPB * kChunkBytes;                     // <= 2 KB
+    static constexpr int kStagesPerTile = 8 / kCPB;
 };
 
 template <typename T, int M> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
-    return warps * HeadTmaCfg<M>::kStages * (HeadTmaCfg<M>::kChunkPx * 32 * M * (int)sizeof(T) + 8);
+    return warps * HeadTmaCfg<T, M>::kStages * (HeadTmaCfg<T, M>::kStageBytes + 8);
 }
+
+// Per-warp ring of bulk-copied feature stages.  Stage sq (counted per warp) holds pixels
+// [px0, px0 + 4*CPB) of tile sq / SPT; lane 0 issues, all lanes wait on the stage's mbarrier.
+template <typename T, int M> struct FeatRing {
+    using Cfg = HeadTmaCfg<T, M>;
+    static constexpr int C = 32 * M;
+    unsigned char *ring;
+    uint64_t *bars;
+    const T *feat;
+    uint32_t npix, warp, nwarps, nstages;
+
+    __device__ __forceinline__ void init(unsigned char *smem, int wid, int nw, int lane, const T *feat_, uint32_t npix_, uint32_t warp_,
+                                         uint32_t nwarps_, uint32_t ntiles) {
+        ring = smem + (size_t)wid * Cfg::kStages * Cfg::kStageBytes;
+        bars = reinterpret_cast<uint64_t *>(smem + (size_t)nw * Cfg::kStages * Cfg::kStageBytes) + wid * Cfg::kStages;
+        feat = feat_; npix = npix_; warp = warp_; nwarps = nwarps_;
+        nstages = ntiles * Cfg::kStagesPerTile;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < Cfg::kStages; ++k) mbar_init(&bars[k], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < Cfg::kStages; ++k) issue(k);
+        }
+    }
+    __device__ __forceinline__ uint32_t stage_px0(uint32_t sq) const {
+        return (warp + (sq / Cfg::kStagesPerTile) * nwarps) * 32 + (sq % Cfg::kStagesPerTile) * (Cfg::kCPB * Cfg::kChunkPx);
+    }
+    __device__ __forceinline__ void issue(uint32_t sq) {      // lane 0 only
+        if (sq < nstages) {
+            const uint32_t px0 = stage_px0(sq);
+            if (px0 < npix) {
+                const uint32_t npx = min((uint32_t)(Cfg::kCPB * Cfg::kChunkPx), npix - px0);
+                uint64_t *bar = &bars[sq % Cfg::kStages];
+                mbar_arrive_expect_tx(bar, npx * Cfg::kPxBytes);
+                bulk_g2s(ring + (sq % Cfg::kStages) * Cfg::kStageBytes, feat + (size_t)px0 * C, npx * Cfg::kPxBytes, bar);
+            }
+        }
+    }
+    __device__ __forceinline__ void wait(uint32_t sq) { mbar_wait(&bars[sq % Cfg::kStages], (sq / Cfg::kStages) & 1); }
+    // every lane is done with stage sq: refill it with stage sq + kStages
+    __device__ __forceinline__ void release(uint32_t sq, int lane) {
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            issue(sq + Cfg::kStages);
+        }
+    }
+    // chunk c of stage sq, pixel g, channel offset ch
+    __device__ __forceinline__ const unsigned char *at(uint32_t sq, int c, int g, int ch) const {
+        return ring + (sq % Cfg::kStages) * Cfg::kStageBytes + c * Cfg::kChunkBytes + g * Cfg::kPxBytes + ch * (int)sizeof(T);
+    }
+};
 
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_constant__ HeadFwdParams<T> prm) {
+    using Cfg = HeadTmaCfg<T, M>;
     constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
-    constexpr int NS = HeadTmaCfg<M>::kStages;
-    constexpr int CPX = HeadTmaCfg<M>::kChunkPx;
-    constexpr uint32_t PX_BYTES = C * sizeof(T);
-    constexpr uint32_t CHUNK_BYTES = CPX * PX_BYTES;
     extern __shared__ __align__(128) unsigned char head_smem[];
 
     const int lane = threadIdx.x & 31, s = lane & 7, g = lane >> 3, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    unsigned char *ring = head_smem + (size_t)wid * NS * CHUNK_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(head_smem + (size_t)nw * NS * CHUNK_BYTES) + wid * NS;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NS; ++k) mbar_init(&bars[k], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
+    const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
+    FeatRing<T, M> fr;
+    fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, ntiles);
 
     float wk[M][4][3];
 #pragma unroll
@@ -206,41 +259,23 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
 #pragma unroll
             for (int k = 0; k < 3; ++k) wk[m][e][k] = __ldg(prm.kernel + (32 * m + 4 * s + e) * 3 + k);
 
-    // chunk q of this warp: tile (q >> 3), pixels [px0, px0 + 4)
-    const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
-    const uint32_t nchunks = ntiles * 8;
-    auto chunk_px0 = [&](uint32_t q) { return (warp + (q >> 3) * nwarps) * 32 + (q & 7) * CPX; };
-    auto issue = [&](uint32_t q) {          // lane 0 only
-        if (q < nchunks) {
-            const uint32_t px0 = chunk_px0(q);
-            if (px0 < prm.npix) {
-                const uint32_t npx = min((uint32_t)CPX, prm.npix - px0);
-                uint64_t *bar = &bars[q % NS];
-                mbar_arrive_expect_tx(bar, npx * PX_BYTES);
-                bulk_g2s(ring + (q % NS) * CHUNK_BYTES, prm.feat + (size_t)px0 * C, npx * PX_BYTES, bar);
-            }
-        }
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NS; ++k) issue(k);
-    }
-
-    uint32_t q = 0;
+    uint32_t sq = 0;
     for (uint32_t t = 0; t < ntiles; ++t) {
         const uint32_t p0 = (warp + t * nwarps) * 32;
         float acc[8][3];
 #pragma unroll
-        for (int it = 0; it < 8; ++it, ++q) {
-            acc[it][0] = acc[it][1] = acc[it][2] = 0.0f;
-            const uint32_t px0 = p0 + it * CPX;
-            if (px0 < prm.npix) {                                   // warp-uniform
-                mbar_wait(&bars[q % NS], (q / NS) & 1);
-                if (px0 + g < prm.npix) {
-                    const unsigned char *src = ring + (q % NS) * CHUNK_BYTES + g * PX_BYTES + 4 * s * sizeof(T);
+        for (int st = 0; st < Cfg::kStagesPerTile; ++st, ++sq) {
+            const uint32_t spx0 = p0 + st * (Cfg::kCPB * Cfg::kChunkPx);
+            const bool live = spx0 < prm.npix;                      // warp-uniform
+            if (live) fr.wait(sq);
+#pragma unroll
+            for (int c = 0; c < Cfg::kCPB; ++c) {
+                const int it = st * Cfg::kCPB + c;
+                acc[it][0] = acc[it][1] = acc[it][2] = 0.0f;
+                if (live && spx0 + c * Cfg::kChunkPx + g < prm.npix) {
                     float f[M][4];
 #pragma unroll
-                    for (int m = 0; m < M; ++m) lds_elems<T, 4>(src + 32 * m * sizeof(T), f[m]);
+                    for (int m = 0; m < M; ++m) lds_elems<T, 4>(fr.at(sq, c, g, 32 * m + 4 * s), f[m]);
 #pragma unroll
                     for (int m = 0; m < M; ++m)
 #pragma unroll
@@ -248,12 +283,8 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 3; ++k) acc[it][k] = fmaf(f[m][e], wk[m][e][k], acc[it][k]);
                 }
-                __syncwarp();                                       // every lane has read the stage
-                if (lane == 0) {
-                    fence_proxy_async();
-                    issue(q + NS);
-                }
             }
+            if (live) fr.release(sq, lane);
         }
         float z[3];
         butterfly8x3(acc, s, z);                                    // lane (g, s) holds pixel p0 + 4 s + g
@@ -283,6 +314,152 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
             LaneDirs<R, R> dir;
             lpg_expand_store<T, R, 1, R, D>(dir, 0, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged backward: same per-warp feature ring (feat is re-read for g_kernel); the patch gradients
+// and saved coefficients of a tile are small and loaded directly by lane L for pixel L.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int R, int D, int M>
+__global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_constant__ HeadBwdParams<T> prm) {
+    using Cfg = HeadTmaCfg<T, M>;
+    constexpr int C = 32 * M;
+    constexpr int NDS = D ? R / D : 0;
+    constexpr int kMaxWarps = 8;
+    extern __shared__ __align__(128) unsigned char head_smem[];
+    __shared__ float red[kMaxWarps][C * 3];
+    __shared__ bool is_last;
+
+    const int lane = threadIdx.x & 31, s = lane & 7, g = lane >> 3, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool want_gk = prm.g_kernel != nullptr, want_gf = prm.g_feat != nullptr;
+    const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
+    FeatRing<T, M> fr;
+    fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, want_gk ? ntiles : 0);
+
+    float wk[M][4][3], dw[M][4][3];
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                wk[m][e][k] = want_gf ? __ldg(prm.kernel + (32 * m + 4 * s + e) * 3 + k) : 0.0f;
+                dw[m][e][k] = 0.0f;
+            }
+
+    uint32_t sq = 0;
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t p0 = (warp + t * nwarps) * 32;
+        const uint32_t pix = p0 + lane;
+        float dz[3] = {0.0f, 0.0f, 0.0f};
+        if (pix < prm.npix) {                                       // lane L: LPG backward of pixel p0 + L
+            uint32_t row, j, b, i;
+            prm.w.divmod(pix, row, j);
+            prm.h.divmod(row, b, i);
+            float G[R][R];
+            const T *grow = prm.g_full ? prm.g_full + ((size_t)b * prm.gf_sB + (size_t)(i * R) * prm.gf_sH + j * R) : nullptr;
+            const T *drow = nullptr;
+            if constexpr (D > 0) {
+                if (prm.g_ds) drow = prm.g_ds + ((size_t)b * prm.gd_sB + (size_t)(i * NDS) * prm.gd_sH + j * NDS);
+            }
+            float x[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] = load1(prm.coef + (size_t)pix * 3 + k);
+            lpg_load_patch<T, R, 1, R, D>(0, grow, prm.gf_sH, drow, prm.gd_sH, G);
+            float gc[3], acc[4];
+            LaneDirs<R, R> dir;
+            Angles a;
+            decode_angles(x[0], x[1], a);
+            lpg_patch_partial<R, 1, R>(dir, G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
+            lpg_finish_grad(a, x[2], acc, gc);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (prm.g_coef_out) store1(prm.g_coef_out + (size_t)pix * 3 + k, gc[k]);
+                dz[k] = gc[k] * x[k] * (1.0f - x[k]);                    // sigmoid'
+            }
+        }
+#pragma unroll
+        for (int st = 0; st < Cfg::kStagesPerTile; ++st) {
+            const uint32_t spx0 = p0 + st * (Cfg::kCPB * Cfg::kChunkPx);
+            const bool live = spx0 < prm.npix;                      // warp-uniform
+            if (live && want_gk) fr.wait(sq);
+#pragma unroll
+            for (int c = 0; c < Cfg::kCPB; ++c) {
+                const int it = st * Cfg::kCPB + c;
+                float dzb[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dzb[k] = __shfl_sync(0xffffffffu, dz[k], 4 * it + g);   // pixel p0 + 4 it + g lives on that lane
+                const uint32_t pg = spx0 + c * Cfg::kChunkPx + g;
+                if (live && pg < prm.npix) {
+                    if (want_gk) {
+                        float f[M][4];
+#pragma unroll
+                        for (int m = 0; m < M; ++m) lds_elems<T, 4>(fr.at(sq, c, g, 32 * m + 4 * s), f[m]);
+#pragma unroll
+                        for (int m = 0; m < M; ++m)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) dw[m][e][k] = fmaf(f[m][e], dzb[k], dw[m][e][k]);
+                    }
+                    if (want_gf) {
+                        T *gp = prm.g_feat + (size_t)pg * C + 4 * s;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            float gf[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                gf[e] = fmaf(dzb[2], wk[m][e][2], fmaf(dzb[1], wk[m][e][1], dzb[0] * wk[m][e][0]));
+                            store_elems<T, 4>(gp + 32 * m, gf);
+                        }
+                    }
+                }
+            }
+            if (want_gk) {
+                if (live) fr.release(sq, lane);
+                ++sq;
+            }
+        }
+    }
+
+    if (!want_gk) return;   // uniform across the grid
+
+    // lanes -> warp: add the four lane groups (fixed order), lanes 0..7 then hold the warp totals
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float v = dw[m][e][k];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane < 8) red[wid][(32 * m + 4 * s + e) * 3 + k] = v;
+            }
+    __syncthreads();
+    for (int tt = threadIdx.x; tt < C * 3; tt += blockDim.x) {      // warps -> CTA
+        float v = 0.0f;
+        for (int w = 0; w < nw; ++w) v += red[w][tt];
+        prm.partial[(size_t)blockIdx.x * (C * 3) + tt] = v;
+    }
+    __threadfence();                                                // CTAs -> result: the last CTA sums in CTA order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(prm.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int tt = threadIdx.x; tt < C * 3; tt += blockDim.x) {
+            float v = 0.0f;
+            for (uint32_t blk = 0; blk < gridDim.x; ++blk) v += __ldcg(prm.partial + (size_t)blk * (C * 3) + tt);
+            prm.g_kernel[tt] = v;
+        }
+        if (threadIdx.x == 0) *prm.counter = 0u;   // leave the workspace header zero for the next launch
     }
 }
 

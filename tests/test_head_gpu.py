@@ -45,7 +45,7 @@ def test_fused_head_f32(B, h, w, C, r, d):
     f, k, gf = feat.to(DEV), kern.to(DEV), g_full.to(DEV)
     gd = g_ds.to(DEV) if d else None
     coef, full, ds = ops.reduce_lpg_forward(f, k, r, d)
-    assert ops.last_kernel().startswith("head_lpg_fwd<f32,r%d" % r), ops.last_kernel()
+    assert ops.last_kernel().startswith("head_lpg_fwd") and ("<f32,r%d," % r) in ops.last_kernel(), ops.last_kernel()
     ref_coef, ref_gc, ref_gf, ref_gw = oracle_head(feat, kern, g_full, g_ds, r, d, coef_seen=npf(coef))
     np.testing.assert_allclose(npf(coef), ref_coef, rtol=2e-6, atol=1e-7)
     parity.check_forward(npf(full), npf(coef), r, what="fused fwd")
@@ -56,7 +56,7 @@ def test_fused_head_f32(B, h, w, C, r, d):
         assert torch.equal(ds, ds2) and torch.equal(ds, full[:, ::d, ::d])
 
     g_feat, g_kern, g_coef = ops.reduce_lpg_backward(f, k, coef, gf, gd, r, d, need_g_coef=True)
-    assert ops.last_kernel().startswith("head_lpg_bwd<f32,r%d" % r), ops.last_kernel()
+    assert ops.last_kernel().startswith("head_lpg_bwd") and ("<f32,r%d," % r) in ops.last_kernel(), ops.last_kernel()
     # same per-pixel terms as the stand-alone kernel; at r=8 the latter adds the patch rows in a lane-group tree
     alone = ops.lpg_backward(coef, gf, gd, r, d)
     scale, _ = parity.backward_scale(npf(coef), npf(g_full), r, npf(g_ds) if d else None, d)
