@@ -13,7 +13,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbtslpg.so")
+LIB_PATH = os.environ.get("BTSLPG_LIB") or os.path.join(_HERE, "lib", "libbtslpg.so")   # BTSLPG_LIB: experiment builds
 
 BTSLPG_MAX_MULTI = 4
 

@@ -167,24 +167,39 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
 // with pixel 4s+g; one index shuffle puts pixel L on lane L for coalesced coefficient / depth stores.
 // ------------------------------------------------------------------------------------------------
 // A stage of a warp's ring is one bulk copy of ~2 KB: CPB consecutive 4-pixel chunks.
-template <typename T, int M> struct HeadTmaCfg {
-    static constexpr int kStages = 4;
+// Ring geometry, chosen from the sweep in profiles/r01_sweep_head_ring.md: forward 2 stages x 2 KB,
+// backward 3 stages x 4 KB (the backward also writes g_feat, so it wants more bytes in flight per warp).
+#ifndef BTSLPG_HEAD_FWD_STAGES
+#define BTSLPG_HEAD_FWD_STAGES 2
+#endif
+#ifndef BTSLPG_HEAD_FWD_STAGE_BYTES
+#define BTSLPG_HEAD_FWD_STAGE_BYTES 2048
+#endif
+#ifndef BTSLPG_HEAD_BWD_STAGES
+#define BTSLPG_HEAD_BWD_STAGES 3
+#endif
+#ifndef BTSLPG_HEAD_BWD_STAGE_BYTES
+#define BTSLPG_HEAD_BWD_STAGE_BYTES 4096
+#endif
+template <typename T, int M, bool FWD> struct HeadTmaCfg {
+    static constexpr int kStages = FWD ? BTSLPG_HEAD_FWD_STAGES : BTSLPG_HEAD_BWD_STAGES;
     static constexpr int kChunkPx = 4;                                        // pixels per chunk (= lane groups)
     static constexpr int kPxBytes = 32 * M * (int)sizeof(T);
     static constexpr int kChunkBytes = kChunkPx * kPxBytes;
-    static constexpr int kCPB = (2048 / kChunkBytes) < 1 ? 1 : ((2048 / kChunkBytes) > 8 ? 8 : (2048 / kChunkBytes));
-    static constexpr int kStageBytes = kCPB * kChunkBytes;                     // <= 2 KB
+    static constexpr int kWant = (FWD ? BTSLPG_HEAD_FWD_STAGE_BYTES : BTSLPG_HEAD_BWD_STAGE_BYTES) / kChunkBytes;
+    static constexpr int kCPB = kWant < 1 ? 1 : (kWant > 8 ? 8 : kWant);
+    static constexpr int kStageBytes = kCPB * kChunkBytes;
     static constexpr int kStagesPerTile = 8 / kCPB;
 };
 
-template <typename T, int M> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
-    return warps * HeadTmaCfg<T, M>::kStages * (HeadTmaCfg<T, M>::kStageBytes + 8);
+template <typename T, int M, bool FWD> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
+    return warps * HeadTmaCfg<T, M, FWD>::kStages * (HeadTmaCfg<T, M, FWD>::kStageBytes + 8);
 }
 
 // Per-warp ring of bulk-copied feature stages.  Stage sq (counted per warp) holds pixels
 // [px0, px0 + 4*CPB) of tile sq / SPT; lane 0 issues, all lanes wait on the stage's mbarrier.
-template <typename T, int M> struct FeatRing {
-    using Cfg = HeadTmaCfg<T, M>;
+template <typename T, int M, bool FWD> struct FeatRing {
+    using Cfg = HeadTmaCfg<T, M, FWD>;
     static constexpr int C = 32 * M;
     unsigned char *ring;
     uint64_t *bars;
@@ -239,7 +254,7 @@ template <typename T, int M> struct FeatRing {
 
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_constant__ HeadFwdParams<T> prm) {
-    using Cfg = HeadTmaCfg<T, M>;
+    using Cfg = HeadTmaCfg<T, M, true>;
     constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
     extern __shared__ __align__(128) unsigned char head_smem[];
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
-    FeatRing<T, M> fr;
+    FeatRing<T, M, true> fr;
     fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, ntiles);
 
     float wk[M][4][3];
@@ -323,7 +338,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_constant__ HeadBwdParams<T> prm) {
-    using Cfg = HeadTmaCfg<T, M>;
+    using Cfg = HeadTmaCfg<T, M, false>;
     constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
     constexpr int kMaxWarps = 8;
@@ -336,7 +351,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_cons
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const bool want_gk = prm.g_kernel != nullptr, want_gf = prm.g_feat != nullptr;
     const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
-    FeatRing<T, M> fr;
+    FeatRing<T, M, false> fr;
     fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, want_gk ? ntiles : 0);
 
     float wk[M][4][3], dw[M][4][3];
