@@ -131,8 +131,11 @@ template <int R, int ROWS> struct LaneDirs {
     const float *sw;   // shared-memory weights of this lane's first row
     float a0;          // row offset of the lane's first row minus off(0)
     __device__ __forceinline__ void init(int sub) {   // must be reached by every thread of the CTA
+        init_from(stage_dir_table<R>(), sub);
+    }
+    __device__ __forceinline__ void init_from(const float *tab, int sub) {
         a0 = (float)(sub * ROWS) * (1.0f / R);
-        sw = stage_dir_table<R>() + sub * ROWS * R;
+        sw = tab + sub * ROWS * R;
     }
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
     __device__ __forceinline__ float w(int k, int q) const { return sw[k * R + q]; }
@@ -140,6 +143,7 @@ template <int R, int ROWS> struct LaneDirs {
 };
 template <int R> struct LaneDirs<R, R> {
     __device__ __forceinline__ void init(int) {}
+    __device__ __forceinline__ void init_from(const float *, int) {}
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k); }
     __device__ __forceinline__ float w(int k, int q) const { return DirTable<R>::w(k * R + q); }
     __device__ __forceinline__ float v(int k, int q) const { return DirTable<R>::v(k * R + q); }
@@ -299,19 +303,11 @@ template <int R, int ROWS> __device__ __forceinline__ uint32_t slot_group(uint32
     return S::LPP == 1 ? slot : (slot >> 5) * S::GPW + ((slot & 31) % S::GPW);
 }
 
+// decode + expand + store for one lane's share of group `group`, coefficients already in registers
 template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
-    using S = Split<R, ROWS>;
+__device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, uint32_t group,
+                                                const float (&c)[PX * 3]) {
     constexpr int NDS = D ? R / D : 0;
-    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
-    const uint32_t group = slot_group<R, ROWS>(slot);
-    const bool active = group < prm.groups;
-    if (S::LPP == 1 && !active) return;
-    float c[PX * 3];
-    if (active) load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);                                  // CTA-wide barrier inside when the patch is split: every thread reaches it
-    if (!active) return;
     uint32_t row, jg, b, i;
     prm.wg.divmod(group, row, jg);
     prm.h.divmod(row, b, i);
@@ -331,6 +327,21 @@ __device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint3
         n4[px] = c[3 * px + 2];
     }
     lpg_expand_store<T, R, PX, ROWS, D>(dir, sub, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+}
+
+template <typename T, int R, int PX, int ROWS, int D>
+__device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
+    using S = Split<R, ROWS>;
+    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
+    const uint32_t group = slot_group<R, ROWS>(slot);
+    const bool active = group < prm.groups;
+    if (S::LPP == 1 && !active) return;
+    float c[PX * 3];
+    if (active) load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
+    LaneDirs<R, ROWS> dir;
+    dir.init(sub);                                  // CTA-wide barrier inside when the patch is split: every thread reaches it
+    if (!active) return;
+    lpg_fwd_compute<T, R, PX, ROWS, D>(prm, dir, sub, group, c);
 }
 
 template <typename T, int R, int PX, int ROWS, int D>

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Time the multi-layer kernels for every (slots-per-thread U, register-cap, block size) combination."""
+"""Time the multi-layer kernels: one-shot CTAs vs persistent TMA-staged warps (tuning key 8)."""
 import json
 import os
 import sys
@@ -23,24 +23,18 @@ def main():
         gen = torch.Generator(device=dev).manual_seed(0)
         sets = [DeviceSet(B, H, W, dtype, dev, generator=gen) for _ in range(4)]
         fwd_b, bwd_b, _ = algorithmic_bytes(B, H, W, es)
-        for threads in (64, 128):
-            for U in (1, 2):
-                for minb in (1, 0):
-                    if minb and threads > 128:
-                        continue
-                    ops.set_block_threads(threads, threads)
-                    ops.set_tuning(4, U)
-                    ops.set_tuning(5, minb)
-                    f = timed(lambda s: s.forward(True), sets)
-                    b = timed(lambda s: s.backward(True), sets)
-                    out.append(dict(dtype=name, threads=threads, U=U, minb=minb, fwd_us=round(f, 2), bwd_us=round(b, 2),
-                                    fwd_frac=round(fwd_b / f / 1e3 / peak, 3), bwd_frac=round(bwd_b / b / 1e3 / peak, 3),
-                                    step_frac=round((fwd_b + bwd_b) / (f + b) / 1e3 / peak, 3)))
+        for impl in (0, 1):
+            ops.set_tuning(8, impl)
+            f = timed(lambda s: s.forward(True), sets)
+            kf = ops.last_kernel()
+            b = timed(lambda s: s.backward(True), sets)
+            kb = ops.last_kernel()
+            out.append(dict(dtype=name, impl=impl, fwd=kf, bwd=kb, fwd_us=round(f, 2), bwd_us=round(b, 2),
+                            fwd_frac=round(fwd_b / f / 1e3 / peak, 3), bwd_frac=round(bwd_b / b / 1e3 / peak, 3),
+                            step_frac=round((fwd_b + bwd_b) / (f + b) / 1e3 / peak, 3)))
+        ops.set_tuning(8, 0)
         del sets
         torch.cuda.empty_cache()
-    ops.set_block_threads(0, 0)
-    ops.set_tuning(4, 0)
-    ops.set_tuning(5, 0)
     print(json.dumps(out))
 
 
