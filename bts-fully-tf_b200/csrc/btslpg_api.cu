@@ -11,7 +11,6 @@
 #include "../../include/btslpg.h"
 #include "head_kernels.cuh"
 #include "lpg_kernels.cuh"
-#include "lpg_persist.cuh"
 
 using namespace btslpg;
 
@@ -179,7 +178,7 @@ struct Variant {
     int px = 0, rows = 0;
     bool ok() const { return px > 0; }
 };
-std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0}, g_tune_r2_px{0}, g_tune_multi_impl{0};
+std::atomic<int> g_tune_r8_rows{0}, g_tune_r4_px{0}, g_tune_r2_px{0};
 
 int candidates(int dtype, int r, bool fwd, Variant *out) {
     int n = 0;
@@ -434,7 +433,6 @@ void btslpg_set_tuning(int key, int value) {
         case 1: g_bwd_threads.store(value); break;
         case 2: g_tune_r8_rows.store(value); break;   // float32 r=8: patch rows per lane (2, 4 or 8)
         case 3: g_tune_r4_px.store(value); break;     // float32 r=4: coarse pixels per thread (1 or 2)
-        case 8: g_tune_multi_impl.store(value); break; // multi-layer forward: 0 one-shot CTAs, 1 persistent TMA-staged warps
         case 7: g_tune_head_impl.store(value); break; // fused head forward: 0 TMA-staged, 1 register-staged
         case 6: g_tune_r2_px.store(value); break;     // float32 r=2: coarse pixels per thread (2 or 4)
         default: break;
@@ -506,27 +504,6 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
             m.block_end[k] = blocks;
         }
         m.n = n;
-        if (g_tune_multi_impl.load() == 1) {
-            // persistent variant: block_end becomes the prefix of warp items (32 lane slots each)
-            uint32_t items = 0;
-            for (int k = 0; k < n; ++k) {
-                items += threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, true)) / 32;
-                m.block_end[k] = items;
-            }
-            static const int grid = [] {
-                int sms = 0, dev = 0, per_sm = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaFuncSetAttribute(lpg_fwd_persist_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lpg_fwd_persist_kernel<T>, kMultiThreads, 0);
-                return (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
-            }();
-            uint32_t nblk = (items + kPersistWarps - 1) / kPersistWarps;
-            if (nblk > (uint32_t)grid) nblk = grid;
-            lpg_fwd_persist_kernel<T><<<nblk, kMultiThreads, 0, st>>>(m);
-            snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_persist<%s,n%d>", ElemTraits<T>::kName, n);
-            return check_launch("btslpg_forward_multi");
-        }
         lpg_fwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_forward_multi");

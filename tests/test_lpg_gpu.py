@@ -207,29 +207,6 @@ def test_multi_equals_single(dtype):
         assert torch.equal(lb["g_coef"], gc)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (3, 416, 544), (1, 32, 32)])
-def test_multi_persistent_tma_equals_single(dtype, B, H, W):
-    """Persistent TMA-staged forward (tuning key 8) == the one-shot kernels, bit for bit, including ragged last items."""
-    layers, singles = [], []
-    for k, (r, d) in enumerate(RS):
-        coef, _, _ = make_inputs(B, H // r, W // r, r, d, seed=70 + k, dtype=dtype)
-        c = coef.to(DEV)
-        full, ds = ops.lpg_forward(c, r, d)
-        singles.append((full, ds))
-        layers.append(dict(coef=c, upratio=r, ds_stride=d, out_full=torch.zeros_like(full), out_ds=torch.zeros_like(ds) if d else None))
-    ops.set_tuning(8, 1)
-    try:
-        ops.lpg_forward_multi(layers)
-        assert ops.last_kernel().startswith("lpg_fwd_persist"), ops.last_kernel()
-    finally:
-        ops.set_tuning(8, 0)
-    for (full, ds), L in zip(singles, layers):
-        assert torch.equal(L["out_full"], full)
-        if ds is not None:
-            assert torch.equal(L["out_ds"], ds)
-
-
 def test_multi_falls_back_per_layer():
     coef, _, _ = make_inputs(1, 5, 7, 3, 0)
     c = coef.to(DEV)
