@@ -185,4 +185,45 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed float32 pairs: Blackwell (sm_100) issues two IEEE fp32 FMAs / multiplies / adds in ONE
+// instruction on a 64-bit register pair (PTX fma.rn.f32x2, SASS FFMA2).  These kernels are limited by
+// instruction issue before they are limited by HBM, so everything that is done for two adjacent
+// pixels (or for the two angles of a coefficient) is done as a pair.  Per-lane results are bit-identical
+// to the scalar fmaf / * / + they replace.
+// ------------------------------------------------------------------------------------------------
+struct F2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ F2 f2(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ F2 f2(float x) { return f2(x, x); }
+__device__ __forceinline__ F2 f2(float2 x) { return f2(x.x, x.y); }
+__device__ __forceinline__ void unpack(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ float lo(F2 a) { float l, h; unpack(a, l, h); return l; }
+__device__ __forceinline__ float hi(F2 a) { float l, h; unpack(a, l, h); return h; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 rcp2(F2 a) {      // two MUFU.RCP; the pair stays in adjacent registers
+    float l, h;
+    unpack(a, l, h);
+    return f2(rcp_approx(l), rcp_approx(h));
+}
+
 }  // namespace btslpg

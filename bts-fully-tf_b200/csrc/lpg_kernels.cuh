@@ -35,6 +35,9 @@ template <> struct DirTable<2> {
     static __device__ __forceinline__ float off(int p) { return c_off2[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w2[k]; }
     static __device__ __forceinline__ float v(int k) { return c_v2[k]; }
+    static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off2[q])); }
+    static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w2[k])); }
+    static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v2[k])); }
     static __device__ __forceinline__ const float *gw() { return g_w2; }
     static __device__ __forceinline__ const float *gv() { return g_v2; }
 };
@@ -42,6 +45,9 @@ template <> struct DirTable<4> {
     static __device__ __forceinline__ float off(int p) { return c_off4[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w4[k]; }
     static __device__ __forceinline__ float v(int k) { return c_v4[k]; }
+    static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off4[q])); }
+    static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w4[k])); }
+    static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v4[k])); }
     static __device__ __forceinline__ const float *gw() { return g_w4; }
     static __device__ __forceinline__ const float *gv() { return g_v4; }
 };
@@ -49,6 +55,9 @@ template <> struct DirTable<8> {
     static __device__ __forceinline__ float off(int p) { return c_off8[p]; }
     static __device__ __forceinline__ float w(int k) { return c_w8[k]; }
     static __device__ __forceinline__ float v(int k) { return c_v8[k]; }
+    static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off8[q])); }
+    static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w8[k])); }
+    static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v8[k])); }
     static __device__ __forceinline__ const float *gw() { return g_w8; }
     static __device__ __forceinline__ const float *gv() { return g_v8; }
 };
@@ -66,20 +75,7 @@ struct Angles {
 // its large-argument path.  Angles outside the fast range (never produced by a sigmoid head) take
 // sincosf().
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sincos_quadrant(float a, float &sn_out, float &cs_out) {
-    const float kf = fmaf(a, 0x1.45f306p-1f, 12582912.0f);          // a*2/pi + 1.5*2^23
-    const float q = kf - 12582912.0f;
-    const int n = __float_as_int(kf);
-    float r = fmaf(q, -0x1.921fb6p+0f, a);
-    r = fmaf(q, 0x1.777a5cp-25f, r);
-    const float s = r * r;
-    float ps = fmaf(-0x1.9ac9e4p-13f, s, 0x1.110c2ap-7f);
-    ps = fmaf(ps, s, -0x1.555552p-3f);
-    const float sn = fmaf(ps, r * s, r);
-    float pc = fmaf(0x1.9a6f38p-16f, s, -0x1.6c0e08p-10f);
-    pc = fmaf(pc, s, 0x1.55554cp-5f);
-    pc = fmaf(pc, s, -0.5f);
-    const float cs = fmaf(pc, s, 1.0f);
+__device__ __forceinline__ void quadrant_fix(int n, float sn, float cs, float &sn_out, float &cs_out) {
     const bool swap = n & 1;
     const float so = swap ? cs : sn;
     const float co = swap ? sn : cs;
@@ -87,9 +83,31 @@ __device__ __forceinline__ void sincos_quadrant(float a, float &sn_out, float &c
     cs_out = __int_as_float(__float_as_int(co) ^ (((n + 1) << 30) & 0x80000000));
 }
 
-__device__ __noinline__ void decode_angles_slow(float phi, float theta, Angles &a) {
-    sincosf(phi, &a.sp, &a.cp);
-    sincosf(theta, &a.st, &a.ct);
+// both angles of a coefficient at once: every floating-point step is one packed instruction
+__device__ __forceinline__ void sincos_quadrant2(F2 a, Angles &o) {
+    const F2 kf = fma2(a, f2(0x1.45f306p-1f), f2(12582912.0f));     // a*2/pi + 1.5*2^23
+    const F2 q = add2(kf, f2(-12582912.0f));
+    F2 r = fma2(q, f2(-0x1.921fb6p+0f), a);
+    r = fma2(q, f2(0x1.777a5cp-25f), r);
+    const F2 s = mul2(r, r);
+    F2 ps = fma2(f2(-0x1.9ac9e4p-13f), s, f2(0x1.110c2ap-7f));
+    ps = fma2(ps, s, f2(-0x1.555552p-3f));
+    const F2 sn = fma2(ps, mul2(r, s), r);
+    F2 pc = fma2(f2(0x1.9a6f38p-16f), s, f2(-0x1.6c0e08p-10f));
+    pc = fma2(pc, s, f2(0x1.55554cp-5f));
+    pc = fma2(pc, s, f2(-0.5f));
+    const F2 cs = fma2(pc, s, f2(1.0f));
+    quadrant_fix(__float_as_int(lo(kf)), lo(sn), lo(cs), o.sp, o.cp);
+    quadrant_fix(__float_as_int(hi(kf)), hi(sn), hi(cs), o.st, o.ct);
+}
+
+// out-of-range path (huge, inf or NaN inputs): results come back in registers, so taking it does not
+// force the fast path's values through local memory
+__device__ __noinline__ float4 decode_angles_slow(float phi, float theta) {
+    float4 r;
+    sincosf(phi, &r.x, &r.y);
+    sincosf(theta, &r.z, &r.w);
+    return r;
 }
 
 // custom_layers.py:49 -- phi = x0*2*pi ; theta = x1*pi/3, both rounded to float32 exactly as the
@@ -97,15 +115,15 @@ __device__ __noinline__ void decode_angles_slow(float phi, float theta, Angles &
 // a correctly rounded division by 3 in three instructions (q = t/3 approx, one exact residual
 // step; verified against IEEE division in tools/fit_sincos.py).
 __device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
-    const float phi = x0 * (2.0f * BTSLPG_PI_F);
-    const float t = x1 * BTSLPG_PI_F;
+    const F2 pt = mul2(f2(x0, x1), f2(2.0f * BTSLPG_PI_F, BTSLPG_PI_F));   // (phi, x1*pi)
+    const float phi = lo(pt), t = hi(pt);
     const float q0 = t * 0x1.555556p-2f;
     const float theta = fmaf(fmaf(-3.0f, q0, t), 0x1.555556p-2f, q0);
     if (fmaxf(fabsf(phi), fabsf(theta)) <= 1000.0f) {
-        sincos_quadrant(phi, a.sp, a.cp);
-        sincos_quadrant(theta, a.st, a.ct);
-    } else {   // huge, inf or NaN inputs: IEEE division for theta as well (the 3-instruction form assumes no overflow)
-        decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(t, 3.0f), a);
+        sincos_quadrant2(f2(phi, theta), a);
+    } else {   // IEEE division for theta as well (the 3-instruction form assumes no overflow)
+        const float4 r = decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(t, 3.0f));
+        a.sp = r.x; a.cp = r.y; a.st = r.z; a.ct = r.w;
     }
 }
 
@@ -140,6 +158,8 @@ template <int R, int ROWS> struct LaneDirs {
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
     __device__ __forceinline__ float w(int k, int q) const { return sw[k * R + q]; }
     __device__ __forceinline__ float v(int k, int q) const { return sw[R * R + k * R + q]; }
+    __device__ __forceinline__ F2 w2(int k, int q) const { return f2(*reinterpret_cast<const float2 *>(&sw[k * R + q])); }
+    __device__ __forceinline__ F2 v2(int k, int q) const { return f2(*reinterpret_cast<const float2 *>(&sw[R * R + k * R + q])); }
 };
 template <int R> struct LaneDirs<R, R> {
     __device__ __forceinline__ void init(int) {}
@@ -147,6 +167,8 @@ template <int R> struct LaneDirs<R, R> {
     __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k); }
     __device__ __forceinline__ float w(int k, int q) const { return DirTable<R>::w(k * R + q); }
     __device__ __forceinline__ float v(int k, int q) const { return DirTable<R>::v(k * R + q); }
+    __device__ __forceinline__ F2 w2(int k, int q) const { return DirTable<R>::w2(k * R + q); }
+    __device__ __forceinline__ F2 v2(int k, int q) const { return DirTable<R>::v2(k * R + q); }
 };
 
 // does patch row (sub*ROWS + k) carry a down-sampled sample (row % D == 0)?
@@ -173,11 +195,12 @@ __device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, i
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
             const float A = fmaf(dir.a(k), n1[px], n3[px]);               // a_p*n1 + n3   (rows pair with n1)
+            const F2 A2 = f2(A), n2b = f2(n2[px]), n4b = f2(n4[px]);
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const float s = fmaf(Tab::off(q), n2[px], A);            // + b_q*n2      (columns pair with n2)
-                const float den = fmaf(dir.w(k, q), s, BTSLPG_EPS_F);    // custom_layers.py:55
-                o[px * R + q] = n4[px] * rcp_approx(den);                // custom_layers.py:56
+            for (int q = 0; q < R; q += 2) {                             // two adjacent pixels per packed instruction
+                const F2 s = fma2(Tab::off2(q), n2b, A2);                // + b_q*n2      (columns pair with n2)
+                const F2 den = fma2(dir.w2(k, q), s, f2(BTSLPG_EPS_F));  // custom_layers.py:55
+                unpack(mul2(n4b, rcp2(den)), o[px * R + q], o[px * R + q + 1]);   // custom_layers.py:56
             }
         }
         const int p = sub * ROWS + k;
@@ -234,25 +257,27 @@ __device__ __forceinline__ void lpg_patch_partial(const LaneDirs<R, ROWS> &dir, 
                                                   float n2, float n3, float (&acc)[4]) {
     using Tab = DirTable<R>;
     acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+    const F2 n2b = f2(n2);
 #pragma unroll
-    for (int k = 0; k < ROWS; ++k) {            // fixed order: columns inside a row, then rows
+    for (int k = 0; k < ROWS; ++k) {            // fixed order: column pairs inside a row, then the two halves, then rows
         const float ap = dir.a(k);
-        const float A = fmaf(ap, n1, n3);
-        float r2 = 0.f, r3 = 0.f, r4 = 0.f;
+        const F2 A2 = f2(fmaf(ap, n1, n3));
+        F2 r2 = f2(0.f), r3 = f2(0.f), r4 = f2(0.f);
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const float s = fmaf(Tab::off(q), n2, A);
-            const float inv = rcp_approx(fmaf(dir.w(k, q), s, BTSLPG_EPS_F));
-            const float u = G[k][px * R + q] * inv;
-            const float y = u * inv;
-            r4 += u;
-            r3 = fmaf(y, dir.w(k, q), r3);
-            r2 = fmaf(y, dir.v(k, q), r2);
+        for (int q = 0; q < R; q += 2) {        // two adjacent pixels per packed instruction (7 FFMA2-class + 2 MUFU per pair)
+            const F2 w = dir.w2(k, q);
+            const F2 inv = rcp2(fma2(w, fma2(Tab::off2(q), n2b, A2), f2(BTSLPG_EPS_F)));
+            const F2 u = mul2(f2(G[k][px * R + q], G[k][px * R + q + 1]), inv);
+            const F2 y = mul2(u, inv);
+            r4 = add2(r4, u);
+            r3 = fma2(y, w, r3);
+            r2 = fma2(y, dir.v2(k, q), r2);
         }
-        acc[0] = fmaf(ap, r3, acc[0]);
-        acc[1] += r2;
-        acc[2] += r3;
-        acc[3] += r4;
+        const float s3 = lo(r3) + hi(r3);
+        acc[0] = fmaf(ap, s3, acc[0]);
+        acc[1] += lo(r2) + hi(r2);
+        acc[2] += s3;
+        acc[3] += lo(r4) + hi(r4);
     }
 }
 
