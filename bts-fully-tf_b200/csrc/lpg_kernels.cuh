@@ -475,9 +475,15 @@ template <typename T> struct LpgBwdMulti {
 // MINB = minimum resident CTAs per SM asked of the compiler (caps registers: occupancy is what hides the
 // one-shot load latency of these kernels); block size is 128.
 constexpr int kMultiThreads = 128;
-// float32: 16 / 12 CTAs per SM (<= 32 / 40 registers); bfloat16 threads hold twice the pixels: 12 / 8
-template <typename T> constexpr int fwd_min_blocks() { return sizeof(T) == 4 ? 16 : 12; }
-template <typename T> constexpr int bwd_min_blocks() { return sizeof(T) == 4 ? 12 : 8; }
+// float32: 16 / 10 CTAs per SM (<= 32 / 48 registers; measured: profiles/experiments/README.md); bfloat16 threads hold twice the pixels: 12 / 8
+#ifndef BTSLPG_FWD_MINB
+#define BTSLPG_FWD_MINB 16
+#endif
+#ifndef BTSLPG_BWD_MINB
+#define BTSLPG_BWD_MINB 10
+#endif
+template <typename T> constexpr int fwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_FWD_MINB : 12; }
+template <typename T> constexpr int bwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_BWD_MINB : 8; }
 
 template <typename T>
 __global__ void __launch_bounds__(kMultiThreads, fwd_min_blocks<T>()) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
