@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
             if constexpr (D > 0) {
                 if (prm.ds) drow = prm.ds + ((size_t)b * prm.ds_sB + (size_t)(i * NDS) * prm.ds_sH + j * NDS);
             }
-            LaneDirs<R, R> dir;
-            lpg_expand_store<T, R, 1, R, D>(dir, 0, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+            lpg_expand_store<T, R, 1, R, D, 0>(n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
         }
     }
 }
@@ -326,8 +325,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
             if constexpr (D > 0) {
                 if (prm.ds) drow = prm.ds + ((size_t)b * prm.ds_sB + (size_t)(i * NDS) * prm.ds_sH + j * NDS);
             }
-            LaneDirs<R, R> dir;
-            lpg_expand_store<T, R, 1, R, D>(dir, 0, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+            lpg_expand_store<T, R, 1, R, D, 0>(n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
         }
     }
 }
@@ -383,12 +381,11 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_cons
             float x[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) x[k] = load1(prm.coef + (size_t)pix * 3 + k);
-            lpg_load_patch<T, R, 1, R, D>(0, grow, prm.gf_sH, drow, prm.gd_sH, G);
+            lpg_load_patch<T, R, 1, R, D, 0>(grow, prm.gf_sH, drow, prm.gd_sH, G);
             float gc[3], acc[4];
-            LaneDirs<R, R> dir;
             Angles a;
             decode_angles(x[0], x[1], a);
-            lpg_patch_partial<R, 1, R>(dir, G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
+            lpg_patch_partial<R, 1, R, 0>(G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
             lpg_finish_grad(a, x[2], acc, gc);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -519,12 +516,11 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_kernel(const __grid_constant
             float x[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) x[k] = load1(prm.coef + (size_t)pix * 3 + k);
-            lpg_load_patch<T, R, 1, R, D>(0, grow, prm.gf_sH, drow, prm.gd_sH, G);
+            lpg_load_patch<T, R, 1, R, D, 0>(grow, prm.gf_sH, drow, prm.gd_sH, G);
             float gc[3], acc[4];
-            LaneDirs<R, R> dir;
             Angles a;
             decode_angles(x[0], x[1], a);
-            lpg_patch_partial<R, 1, R>(dir, G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
+            lpg_patch_partial<R, 1, R, 0>(G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
             lpg_finish_grad(a, x[2], acc, gc);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {

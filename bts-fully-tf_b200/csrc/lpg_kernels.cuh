@@ -38,8 +38,6 @@ template <> struct DirTable<2> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off2[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w2[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v2[k])); }
-    static __device__ __forceinline__ const float *gw() { return g_w2; }
-    static __device__ __forceinline__ const float *gv() { return g_v2; }
 };
 template <> struct DirTable<4> {
     static __device__ __forceinline__ float off(int p) { return c_off4[p]; }
@@ -48,8 +46,6 @@ template <> struct DirTable<4> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off4[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w4[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v4[k])); }
-    static __device__ __forceinline__ const float *gw() { return g_w4; }
-    static __device__ __forceinline__ const float *gv() { return g_v4; }
 };
 template <> struct DirTable<8> {
     static __device__ __forceinline__ float off(int p) { return c_off8[p]; }
@@ -58,8 +54,6 @@ template <> struct DirTable<8> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off8[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w8[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v8[k])); }
-    static __device__ __forceinline__ const float *gw() { return g_w8; }
-    static __device__ __forceinline__ const float *gv() { return g_v8; }
 };
 
 struct Angles {
@@ -128,103 +122,92 @@ __device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Direction weights of the ROWS patch rows a lane owns.
-//   LPP == 1 (ROWS == R): compile-time indices -> constant-bank operands of the FFMAs, no registers.
-//   LPP  > 1: rows [sub*ROWS, sub*ROWS+ROWS) with a per-lane `sub`: the r*r table is staged once per
-//             CTA in shared memory and read on demand (a divergent __constant__ index would serialise,
-//             and keeping ROWS*R weights in registers costs occupancy, which these latency-bound
-//             kernels cannot afford).
+// Direction table of the ROWS patch rows [SUB*ROWS, SUB*ROWS+ROWS) a thread owns.  Every index is a
+// compile-time constant after unrolling, so the entries are constant-bank operands of the (packed)
+// FMAs: no loads, no registers.  When a patch is split over LPP = R/ROWS threads, SUB is the index
+// of the thread's WARP inside its group of LPP warps (warp-uniform, dispatched by a switch), never a
+// per-lane value -- a divergent table index would serialise the constant loads.
 // ------------------------------------------------------------------------------------------------
-template <int R> __device__ __forceinline__ const float *stage_dir_table() {
-    __shared__ float tab[2 * R * R];   // [0, R*R): w_pq ; [R*R, 2*R*R): v_pq = b_q * w_pq
-    for (int t = threadIdx.x; t < R * R; t += blockDim.x) {
-        tab[t] = DirTable<R>::gw()[t];
-        tab[R * R + t] = DirTable<R>::gv()[t];
-    }
-    __syncthreads();
-    return tab;
+template <int R, int ROWS, int SUB> struct Dirs {
+    using Tab = DirTable<R>;
+    static __device__ __forceinline__ float a(int k) { return Tab::off(SUB * ROWS + k); }
+    static __device__ __forceinline__ F2 w2(int k, int q) { return Tab::w2((SUB * ROWS + k) * R + q); }
+    static __device__ __forceinline__ F2 v2(int k, int q) { return Tab::v2((SUB * ROWS + k) * R + q); }
+};
+
+// does patch row (SUB*ROWS + k) carry a down-sampled sample (row % D == 0)?
+template <int ROWS, int D, int SUB> __device__ __forceinline__ constexpr bool ds_row(int k) {
+    return D != 0 && ((SUB * ROWS + k) % (D ? D : 1)) == 0;
 }
 
-template <int R, int ROWS> struct LaneDirs {
-    const float *sw;   // shared-memory weights of this lane's first row
-    float a0;          // row offset of the lane's first row minus off(0)
-    __device__ __forceinline__ void init(int sub) {   // must be reached by every thread of the CTA
-        init_from(stage_dir_table<R>(), sub);
-    }
-    __device__ __forceinline__ void init_from(const float *tab, int sub) {
-        a0 = (float)(sub * ROWS) * (1.0f / R);
-        sw = tab + sub * ROWS * R;
-    }
-    __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k) + a0; }   // exact (multiples of 1/2r)
-    __device__ __forceinline__ float w(int k, int q) const { return sw[k * R + q]; }
-    __device__ __forceinline__ float v(int k, int q) const { return sw[R * R + k * R + q]; }
-    __device__ __forceinline__ F2 w2(int k, int q) const { return f2(*reinterpret_cast<const float2 *>(&sw[k * R + q])); }
-    __device__ __forceinline__ F2 v2(int k, int q) const { return f2(*reinterpret_cast<const float2 *>(&sw[R * R + k * R + q])); }
+template <int V> struct IntC {
+    static constexpr int value = V;
 };
-template <int R> struct LaneDirs<R, R> {
-    __device__ __forceinline__ void init(int) {}
-    __device__ __forceinline__ void init_from(const float *, int) {}
-    __device__ __forceinline__ float a(int k) const { return DirTable<R>::off(k); }
-    __device__ __forceinline__ float w(int k, int q) const { return DirTable<R>::w(k * R + q); }
-    __device__ __forceinline__ float v(int k, int q) const { return DirTable<R>::v(k * R + q); }
-    __device__ __forceinline__ F2 w2(int k, int q) const { return DirTable<R>::w2(k * R + q); }
-    __device__ __forceinline__ F2 v2(int k, int q) const { return DirTable<R>::v2(k * R + q); }
-};
-
-// does patch row (sub*ROWS + k) carry a down-sampled sample (row % D == 0)?
-template <int ROWS, int D> __device__ __forceinline__ bool ds_row(int sub, int k) {
-    if constexpr (D == 0) return false;
-    else if constexpr (ROWS % D == 0) return k % D == 0;
-    else return k == 0 && (sub * ROWS) % D == 0;
+// call f(IntC<sub>) with `sub` (0 <= sub < N, warp-uniform) turned into a compile-time constant
+template <int N, typename F> __device__ __forceinline__ void dispatch_sub(int sub, F &&f) {
+    static_assert(N == 1 || N == 2 || N == 4, "patches are split over 1, 2 or 4 warps");
+    if constexpr (N == 1) {
+        f(IntC<0>{});
+    } else if constexpr (N == 2) {
+        if (sub == 0) f(IntC<0>{}); else f(IntC<1>{});
+    } else {
+        switch (sub) {
+            case 0: f(IntC<0>{}); break;
+            case 1: f(IntC<1>{}); break;
+            case 2: f(IntC<2>{}); break;
+            default: f(IntC<3>{}); break;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Expand PX decoded planes into rows [sub*ROWS, sub*ROWS+ROWS) of their r x r patches and store
+// Expand PX decoded planes into rows [SUB*ROWS, SUB*ROWS+ROWS) of their r x r patches and store
 // them; the down-sampled copy x[:, ::d, ::d] (bts_decoder.py:81,88) comes from the same registers.
 // orow / drow point at patch row 0 of the group (row stride out_sH / ds_sH).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_expand_store(const LaneDirs<R, ROWS> &dir, int sub, const float (&n1)[PX], const float (&n2)[PX],
-                                                 const float (&n3)[PX], const float (&n4)[PX], T *orow, uint32_t out_sH, T *drow,
-                                                 uint32_t ds_sH) {
+template <typename T, int R, int PX, int ROWS, int D, int SUB>
+__device__ __forceinline__ void lpg_expand_store(const float (&n1)[PX], const float (&n2)[PX], const float (&n3)[PX],
+                                                 const float (&n4)[PX], T *orow, uint32_t out_sH, T *drow, uint32_t ds_sH) {
     using Tab = DirTable<R>;
+    using Dir = Dirs<R, ROWS, SUB>;
     constexpr int NDS = D ? R / D : 0;
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
         float o[PX * R];
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
-            const float A = fmaf(dir.a(k), n1[px], n3[px]);               // a_p*n1 + n3   (rows pair with n1)
+            const float A = fmaf(Dir::a(k), n1[px], n3[px]);              // a_p*n1 + n3   (rows pair with n1)
             const F2 A2 = f2(A), n2b = f2(n2[px]), n4b = f2(n4[px]);
 #pragma unroll
             for (int q = 0; q < R; q += 2) {                             // two adjacent pixels per packed instruction
                 const F2 s = fma2(Tab::off2(q), n2b, A2);                // + b_q*n2      (columns pair with n2)
-                const F2 den = fma2(dir.w2(k, q), s, f2(BTSLPG_EPS_F));  // custom_layers.py:55
+                const F2 den = fma2(Dir::w2(k, q), s, f2(BTSLPG_EPS_F)); // custom_layers.py:55
                 unpack(mul2(n4b, rcp2(den)), o[px * R + q], o[px * R + q + 1]);   // custom_layers.py:56
             }
         }
-        const int p = sub * ROWS + k;
-        store_elems<T, PX * R>(orow + (size_t)p * out_sH, o);
+        constexpr int p0 = SUB * ROWS;
+        store_elems<T, PX * R>(orow + (size_t)(p0 + k) * out_sH, o);
         if constexpr (D > 0) {
-            if (drow && ds_row<ROWS, D>(sub, k)) {
+            if (ds_row<ROWS, D, SUB>(k) && drow) {
                 float dsv[PX * NDS];
 #pragma unroll
                 for (int px = 0; px < PX; ++px)
 #pragma unroll
                     for (int qq = 0; qq < NDS; ++qq) dsv[px * NDS + qq] = o[px * R + qq * D];
-                store_elems<T, PX * NDS>(drow + (size_t)(p / D) * ds_sH, dsv);
+                store_elems<T, PX * NDS>(drow + (size_t)((p0 + k) / D) * ds_sH, dsv);
             }
         }
     }
 }
 
-// Gather G = g_full + scatter(g_ds) for rows [sub*ROWS, sub*ROWS+ROWS) of the patches of PX coarse pixels.
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, uint32_t gf_sH, const T *drow, uint32_t gd_sH, float (&G)[ROWS][PX * R]) {
+// Gather G = g_full + scatter(g_ds) for rows [SUB*ROWS, SUB*ROWS+ROWS) of the patches of PX coarse pixels.
+template <typename T, int R, int PX, int ROWS, int D, int SUB>
+__device__ __forceinline__ void lpg_load_patch(const T *grow, uint32_t gf_sH, const T *drow, uint32_t gd_sH, float (&G)[ROWS][PX * R]) {
     constexpr int NDS = D ? R / D : 0;
+    constexpr int p0 = SUB * ROWS;
     if (grow) {
 #pragma unroll
-        for (int k = 0; k < ROWS; ++k) load_elems<T, PX * R>(grow + (size_t)(sub * ROWS + k) * gf_sH, G[k]);
+        for (int k = 0; k < ROWS; ++k) load_elems<T, PX * R>(grow + (size_t)(p0 + k) * gf_sH, G[k]);
     } else {
 #pragma unroll
         for (int k = 0; k < ROWS; ++k)
@@ -235,9 +218,9 @@ __device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, uint32_t 
         if (drow) {
 #pragma unroll
             for (int k = 0; k < ROWS; ++k) {
-                if (ds_row<ROWS, D>(sub, k)) {
+                if (ds_row<ROWS, D, SUB>(k)) {
                     float t[PX * NDS];
-                    load_elems<T, PX * NDS>(drow + (size_t)((sub * ROWS + k) / D) * gd_sH, t);
+                    load_elems<T, PX * NDS>(drow + (size_t)((p0 + k) / D) * gd_sH, t);
 #pragma unroll
                     for (int px = 0; px < PX; ++px)
 #pragma unroll
@@ -248,30 +231,30 @@ __device__ __forceinline__ void lpg_load_patch(int sub, const T *grow, uint32_t 
     }
 }
 
-// Partial sums of one lane over its ROWS rows of the patch of coarse pixel `px`:
+// Partial sums of one thread over its ROWS rows of the patch of coarse pixel `px`:
 //   inv = 1/den ; u = G*inv ; y = u*inv ; acc[3] += u ; acc[2] += y*w ; acc[1] += y*v ; acc[0] += a_p * (row sum of y*w)
-// (w, v = b_q*w from the direction table) so that, after the lanes of a group are added,
-// g1..g3 = -n4 * acc[0..2] and g4 = acc[3].  8 instructions per pixel: 2 FFMA (den), MUFU.RCP, 2 FMUL, FADD, 2 FFMA.
-template <int R, int PX, int ROWS>
-__device__ __forceinline__ void lpg_patch_partial(const LaneDirs<R, ROWS> &dir, const float (&G)[ROWS][PX * R], int px, float n1,
-                                                  float n2, float n3, float (&acc)[4]) {
+// (w, v = b_q*w from the direction table) so that, after the threads of a group are added,
+// g1..g3 = -n4 * acc[0..2] and g4 = acc[3].  Per PAIR of pixels: 7 packed instructions + 2 MUFU.RCP.
+template <int R, int PX, int ROWS, int SUB>
+__device__ __forceinline__ void lpg_patch_partial(const float (&G)[ROWS][PX * R], int px, float n1, float n2, float n3, float (&acc)[4]) {
     using Tab = DirTable<R>;
+    using Dir = Dirs<R, ROWS, SUB>;
     acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
     const F2 n2b = f2(n2);
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {            // fixed order: column pairs inside a row, then the two halves, then rows
-        const float ap = dir.a(k);
+        const float ap = Dir::a(k);
         const F2 A2 = f2(fmaf(ap, n1, n3));
         F2 r2 = f2(0.f), r3 = f2(0.f), r4 = f2(0.f);
 #pragma unroll
-        for (int q = 0; q < R; q += 2) {        // two adjacent pixels per packed instruction (7 FFMA2-class + 2 MUFU per pair)
-            const F2 w = dir.w2(k, q);
+        for (int q = 0; q < R; q += 2) {
+            const F2 w = Dir::w2(k, q);
             const F2 inv = rcp2(fma2(w, fma2(Tab::off2(q), n2b, A2), f2(BTSLPG_EPS_F)));
             const F2 u = mul2(f2(G[k][px * R + q], G[k][px * R + q + 1]), inv);
             const F2 y = mul2(u, inv);
             r4 = add2(r4, u);
             r3 = fma2(y, w, r3);
-            r2 = fma2(y, dir.v2(k, q), r2);
+            r2 = fma2(y, Dir::v2(k, q), r2);
         }
         const float s3 = lo(r3) + hi(r3);
         acc[0] = fmaf(ap, s3, acc[0]);
@@ -293,7 +276,9 @@ __device__ __forceinline__ void lpg_finish_grad(const Angles &a, float n4, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Vectorised kernels.  groups = B*h*(w/PX); a warp covers 32/LPP consecutive groups.
+// Vectorised kernels.  groups = B*h*(w/PX).  A warp covers 32 consecutive groups; when a patch is
+// split (LPP = R/ROWS > 1) LPP consecutive warps of a CTA cover the SAME 32 groups, warp s taking
+// rows [s*ROWS, (s+1)*ROWS).  The CTA size is a multiple of 32*LPP.
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct LpgFwdParams {
     const T *coef;
@@ -317,21 +302,25 @@ template <typename T> struct LpgBwdParams {
 };
 
 template <int R, int ROWS> struct Split {
-    static constexpr int LPP = R / ROWS;      // lanes per group
-    static constexpr int GPW = 32 / LPP;      // groups per warp
+    static constexpr int LPP = R / ROWS;      // warps per group of 32 coarse-pixel groups
     static_assert(R % ROWS == 0 && (LPP == 1 || LPP == 2 || LPP == 4), "bad row split");
 };
 
-// `slot` = index of this thread among the threads of its layer: one lane's share of one group.
-template <int R, int ROWS> __device__ __forceinline__ uint32_t slot_group(uint32_t slot) {
-    using S = Split<R, ROWS>;
-    return S::LPP == 1 ? slot : (slot >> 5) * S::GPW + ((slot & 31) % S::GPW);
+// `slot` = index of this thread among the threads of its layer
+template <int LPP> __device__ __forceinline__ void slot_to_group(uint32_t slot, uint32_t &group, int &sub) {
+    if constexpr (LPP == 1) {
+        group = slot;
+        sub = 0;
+    } else {
+        const uint32_t warp = slot >> 5;
+        sub = (int)(warp % LPP);
+        group = (warp / LPP) * 32 + (slot & 31);
+    }
 }
 
-// decode + expand + store for one lane's share of group `group`, coefficients already in registers
-template <typename T, int R, int PX, int ROWS, int D>
-__device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, const LaneDirs<R, ROWS> &dir, int sub, uint32_t group,
-                                                const float (&c)[PX * 3]) {
+// decode + expand + store for one thread's share of group `group`, coefficients already in registers
+template <typename T, int R, int PX, int ROWS, int D, int SUB>
+__device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, uint32_t group, const float (&c)[PX * 3]) {
     constexpr int NDS = D ? R / D : 0;
     uint32_t row, jg, b, i;
     prm.wg.divmod(group, row, jg);
@@ -351,37 +340,38 @@ __device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, cons
         n3[px] = a.ct;
         n4[px] = c[3 * px + 2];
     }
-    lpg_expand_store<T, R, PX, ROWS, D>(dir, sub, n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
+    lpg_expand_store<T, R, PX, ROWS, D, SUB>(n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
 }
 
 template <typename T, int R, int PX, int ROWS, int D>
 __device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
-    using S = Split<R, ROWS>;
-    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
-    const uint32_t group = slot_group<R, ROWS>(slot);
-    const bool active = group < prm.groups;
-    if (S::LPP == 1 && !active) return;
+    constexpr int LPP = Split<R, ROWS>::LPP;
+    uint32_t group;
+    int sub;
+    slot_to_group<LPP>(slot, group, sub);
+    if (group >= prm.groups) return;
     float c[PX * 3];
-    if (active) load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);                                  // CTA-wide barrier inside when the patch is split: every thread reaches it
-    if (!active) return;
-    lpg_fwd_compute<T, R, PX, ROWS, D>(prm, dir, sub, group, c);
+    load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
+    dispatch_sub<LPP>(sub, [&](auto S) { lpg_fwd_compute<T, R, PX, ROWS, D, decltype(S)::value>(prm, group, c); });
 }
 
+// Backward.  With LPP > 1 the LPP warps of a group exchange their partial sums through shared memory
+// and warp 0 of the group adds them in a fixed order ((s0+s1)+(s2+s3)): deterministic, no atomics.
+// Every thread of the CTA must call this function when LPP > 1 (it contains a CTA barrier).
 template <typename T, int R, int PX, int ROWS, int D>
 __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint32_t slot) {
-    using S = Split<R, ROWS>;
+    constexpr int LPP = Split<R, ROWS>::LPP;
     constexpr int NDS = D ? R / D : 0;
-    const int sub = S::LPP == 1 ? 0 : (int)(slot & 31) / S::GPW;
-    const uint32_t group = slot_group<R, ROWS>(slot);
+    uint32_t group;
+    int sub;
+    slot_to_group<LPP>(slot, group, sub);
     const bool active = group < prm.groups;
-    if (S::LPP == 1 && !active) return;            // with LPP > 1 every lane takes part in the shuffles
+    if (LPP == 1 && !active) return;
 
     float G[ROWS][PX * R];
     float c[PX * 3];
-    if (S::LPP == 1 || active) {
-        // issue every load of the lane first (memory-level parallelism), then compute
+    if (active) {
+        // issue every load of the thread first (memory-level parallelism), then compute
         uint32_t row, jg, b, i;
         prm.wg.divmod(group, row, jg);
         prm.h.divmod(row, b, i);
@@ -391,7 +381,7 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
             if (prm.g_ds) drow = prm.g_ds + ((size_t)b * prm.gd_sB + (size_t)(i * NDS) * prm.gd_sH + jg * (PX * NDS));
         }
         load_elems<T, PX * 3, 4, true>(prm.coef + (size_t)group * (PX * 3), c);
-        lpg_load_patch<T, R, PX, ROWS, D>(sub, grow, prm.gf_sH, drow, prm.gd_sH, G);
+        dispatch_sub<LPP>(sub, [&](auto S) { lpg_load_patch<T, R, PX, ROWS, D, decltype(S)::value>(grow, prm.gf_sH, drow, prm.gd_sH, G); });
     } else {
 #pragma unroll
         for (int e = 0; e < PX * 3; ++e) c[e] = 0.0f;
@@ -400,26 +390,43 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
 #pragma unroll
             for (int e = 0; e < PX * R; ++e) G[k][e] = 0.0f;
     }
-    LaneDirs<R, ROWS> dir;
-    dir.init(sub);                                  // after the loads are in flight: staging the table (and its
-                                                    // CTA barrier, when the patch is split) overlaps their latency
-    float gout[PX * 3];
+
+    Angles a[PX];
+    float acc[PX][4];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
-        Angles a;
-        decode_angles(c[3 * px], c[3 * px + 1], a);
-        float acc[4];
-        lpg_patch_partial<R, PX, ROWS>(dir, G, px, a.st * a.cp, a.st * a.sp, a.ct, acc);
-        if constexpr (S::LPP > 1) {                 // fixed xor tree over the lanes that share the group
+        decode_angles(c[3 * px], c[3 * px + 1], a[px]);
+        dispatch_sub<LPP>(sub, [&](auto S) {
+            lpg_patch_partial<R, PX, ROWS, decltype(S)::value>(G, px, a[px].st * a[px].cp, a[px].st * a[px].sp, a[px].ct, acc[px]);
+        });
+    }
+    if constexpr (LPP > 1) {
+        __shared__ float4 part[8][PX][32];                 // [warp of the CTA][px][lane]; CTA size <= 256
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+        for (int px = 0; px < PX; ++px) part[wid][px][lane] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+        __syncthreads();
+        if (sub != 0 || !active) return;
 #pragma unroll
-                for (int m = S::GPW; m < 32; m <<= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], m);
+        for (int px = 0; px < PX; ++px) {
+            float4 t[LPP];
+            t[0] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+#pragma unroll
+            for (int s2 = 1; s2 < LPP; ++s2) t[s2] = part[wid + s2][px][lane];
+            if constexpr (LPP == 2) {
+                acc[px][0] = t[0].x + t[1].x; acc[px][1] = t[0].y + t[1].y; acc[px][2] = t[0].z + t[1].z; acc[px][3] = t[0].w + t[1].w;
+            } else {
+                acc[px][0] = (t[0].x + t[1].x) + (t[2].x + t[3].x);
+                acc[px][1] = (t[0].y + t[1].y) + (t[2].y + t[3].y);
+                acc[px][2] = (t[0].z + t[1].z) + (t[2].z + t[3].z);
+                acc[px][3] = (t[0].w + t[1].w) + (t[2].w + t[3].w);
             }
         }
-        lpg_finish_grad(a, c[3 * px + 2], acc, &gout[3 * px]);
     }
-    if (active && sub == 0) store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
+    float gout[PX * 3];
+#pragma unroll
+    for (int px = 0; px < PX; ++px) lpg_finish_grad(a[px], c[3 * px + 2], acc[px], &gout[3 * px]);
+    store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
 }
 
 template <typename T, int R, int PX, int ROWS, int D>
@@ -449,8 +456,7 @@ template <typename T, int R, bool FWD> struct VecCfg {
 };
 // threads needed for `groups` groups
 __host__ __device__ inline uint32_t threads_for(uint32_t groups, int lpp) {
-    const uint32_t gpw = 32 / lpp;
-    return ((groups + gpw - 1) / gpw) * 32;
+    return ((groups + 31) / 32) * 32 * lpp;
 }
 
 // ------------------------------------------------------------------------------------------------
