@@ -482,6 +482,7 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
         if (int e = parse_layer_fwd(layers[k].coef, layers[k].upratio, layers[k].out_full, layers[k].out_ds, layers[k].ds_stride, g[k])) return e;
         fused = fused && multi_eligible(g[k], true) && g[k].coef.dtype == g[0].coef.dtype && g[k].coef.dev == g[0].coef.dev &&
                 g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
+        for (int j = 0; j < k; ++j) fused = fused && g[j].r != g[k].r;   // one layer per up-ratio slot
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!fused) {
@@ -497,13 +498,14 @@ int btslpg_forward_multi(const BtsLpgForwardArgs *layers, int n, void *stream) {
         LpgFwdMulti<T> m;
         memset(&m, 0, sizeof(m));
         uint32_t blocks = 0;
-        for (int k = 0; k < n; ++k) {
-            m.layer[k] = make_fwd_params<T>(g[k], px_max<T>(g[k].r));
-            m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, true)) + threads - 1) / threads;
-            m.block_end[k] = blocks;
+        for (int s = 0; s < kMultiSlots; ++s) {           // slot s <-> up-ratio 8 >> s
+            for (int k = 0; k < n; ++k) {
+                if (multi_slot(g[k].r) != s) continue;
+                m.layer[s] = make_fwd_params<T>(g[k], px_max<T>(g[k].r));
+                blocks += (threads_for(m.layer[s].groups, g[k].r / rows_default<T>(g[k].r, true)) + threads - 1) / threads;
+            }
+            m.block_end[s] = blocks;
         }
-        m.n = n;
         lpg_fwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_forward_multi");
@@ -521,6 +523,7 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
         if (int e = parse_layer_bwd(layers[k].coef, layers[k].g_full, layers[k].g_ds, layers[k].upratio, layers[k].ds_stride, layers[k].g_coef, g[k], gc[k])) return e;
         fused = fused && multi_eligible(g[k], false) && is_contig_nhwc(gc[k]) && gc[k].aligned(16) && g[k].coef.dtype == g[0].coef.dtype &&
                 g[k].coef.dev == g[0].coef.dev && g[k].coef.B * g[k].coef.H * g[k].coef.W > 0;
+        for (int j = 0; j < k; ++j) fused = fused && g[j].r != g[k].r;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!fused) {
@@ -536,13 +539,14 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
         LpgBwdMulti<T> m;
         memset(&m, 0, sizeof(m));
         uint32_t blocks = 0;
-        for (int k = 0; k < n; ++k) {
-            m.layer[k] = make_bwd_params<T>(g[k], gc[k], px_max<T>(g[k].r));
-            m.upratio[k] = g[k].r;
-            blocks += (threads_for(m.layer[k].groups, g[k].r / rows_default<T>(g[k].r, false)) + threads - 1) / threads;
-            m.block_end[k] = blocks;
+        for (int s = 0; s < kMultiSlots; ++s) {
+            for (int k = 0; k < n; ++k) {
+                if (multi_slot(g[k].r) != s) continue;
+                m.layer[s] = make_bwd_params<T>(g[k], gc[k], px_max<T>(g[k].r));
+                blocks += (threads_for(m.layer[s].groups, g[k].r / rows_default<T>(g[k].r, false)) + threads - 1) / threads;
+            }
+            m.block_end[s] = blocks;
         }
-        m.n = n;
         lpg_bwd_multi_kernel<T><<<blocks, threads, 0, st>>>(m);
         snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_multi<%s,n%d>", ElemTraits<T>::kName, n);
         return check_launch("btslpg_backward_multi");

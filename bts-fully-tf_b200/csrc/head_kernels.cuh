@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
             prm.w.divmod(pix, row, j);
             prm.h.divmod(row, b, i);
             Angles a;
-            decode_angles(x[0], x[1], a);
+            decode_angles_for<T>(x[0], x[1], a);
             float n1[1] = {a.st * a.cp}, n2[1] = {a.st * a.sp}, n3[1] = {a.ct}, n4[1] = {x[2]};
             T *orow = prm.out + ((size_t)b * prm.out_sB + (size_t)(i * R) * prm.out_sH + j * R);
             T *drow = nullptr;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
             prm.w.divmod(pix, row, j);
             prm.h.divmod(row, b, i);
             Angles a;
-            decode_angles(x[0], x[1], a);
+            decode_angles_for<T>(x[0], x[1], a);
             float n1[1] = {a.st * a.cp}, n2[1] = {a.st * a.sp}, n3[1] = {a.ct}, n4[1] = {x[2]};
             T *orow = prm.out + ((size_t)b * prm.out_sB + (size_t)(i * R) * prm.out_sH + j * R);
             T *drow = nullptr;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_cons
             lpg_load_patch<T, R, 1, R, D, 0>(grow, prm.gf_sH, drow, prm.gd_sH, G);
             float gc[3], acc[4];
             Angles a;
-            decode_angles(x[0], x[1], a);
+            decode_angles_for<T>(x[0], x[1], a);
             lpg_patch_partial<R, 1, R, 0>(G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
             lpg_finish_grad(a, x[2], acc, gc);
 #pragma unroll
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_kernel(const __grid_constant
             lpg_load_patch<T, R, 1, R, D, 0>(grow, prm.gf_sH, drow, prm.gd_sH, G);
             float gc[3], acc[4];
             Angles a;
-            decode_angles(x[0], x[1], a);
+            decode_angles_for<T>(x[0], x[1], a);
             lpg_patch_partial<R, 1, R, 0>(G, 0, a.st * a.cp, a.st * a.sp, a.ct, acc);
             lpg_finish_grad(a, x[2], acc, gc);
 #pragma unroll

@@ -38,6 +38,7 @@ template <> struct DirTable<2> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off2[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w2[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v2[k])); }
+    static __device__ __forceinline__ F2 u2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_u2[k])); }
 };
 template <> struct DirTable<4> {
     static __device__ __forceinline__ float off(int p) { return c_off4[p]; }
@@ -46,6 +47,7 @@ template <> struct DirTable<4> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off4[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w4[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v4[k])); }
+    static __device__ __forceinline__ F2 u2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_u4[k])); }
 };
 template <> struct DirTable<8> {
     static __device__ __forceinline__ float off(int p) { return c_off8[p]; }
@@ -54,6 +56,7 @@ template <> struct DirTable<8> {
     static __device__ __forceinline__ F2 off2(int q) { return f2(*reinterpret_cast<const float2 *>(&c_off8[q])); }
     static __device__ __forceinline__ F2 w2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_w8[k])); }
     static __device__ __forceinline__ F2 v2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_v8[k])); }
+    static __device__ __forceinline__ F2 u2(int k) { return f2(*reinterpret_cast<const float2 *>(&c_u8[k])); }
 };
 
 struct Angles {
@@ -108,17 +111,48 @@ __device__ __noinline__ float4 decode_angles_slow(float phi, float theta) {
 // reference rounds them: (x0*2)*pi == x0*(2*pi) bit for bit (scaling by 2 is exact), and x*pi/3 uses
 // a correctly rounded division by 3 in three instructions (q = t/3 approx, one exact residual
 // step; verified against IEEE division in tools/fit_sincos.py).
-__device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
-    const F2 pt = mul2(f2(x0, x1), f2(2.0f * BTSLPG_PI_F, BTSLPG_PI_F));   // (phi, x1*pi)
-    const float phi = lo(pt), t = hi(pt);
-    const float q0 = t * 0x1.555556p-2f;
-    const float theta = fmaf(fmaf(-3.0f, q0, t), 0x1.555556p-2f, q0);
-    if (fmaxf(fabsf(phi), fabsf(theta)) <= 1000.0f) {
-        sincos_quadrant2(f2(phi, theta), a);
-    } else {   // IEEE division for theta as well (the 3-instruction form assumes no overflow)
-        const float4 r = decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(t, 3.0f));
-        a.sp = r.x; a.cp = r.y; a.st = r.z; a.ct = r.w;
+//
+// SFU = true (bfloat16 I/O only): the four values come from MUFU.SIN / MUFU.COS (sin.approx, absolute
+// error <= 2^-20.9 on the fast range), three orders of magnitude below the 2^-9 resolution of the
+// bfloat16 outputs -- the bf16 kernels are instruction-issue-bound (half the bytes, same work), and
+// the polynomial decode is a third of a short thread's instructions.  float32 never takes this path.
+__device__ __forceinline__ float sin_sfu(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cos_sfu(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <bool SFU = false> __device__ __forceinline__ void decode_angles(float x0, float x1, Angles &a) {
+    if constexpr (SFU) {
+        const F2 pt = mul2(f2(x0, x1), f2(2.0f * BTSLPG_PI_F, BTSLPG_PI_F / 3.0f));
+        const float phi = lo(pt), theta = hi(pt);
+        if (fmaxf(fabsf(phi), fabsf(theta)) <= 1000.0f) {
+            a.sp = sin_sfu(phi); a.cp = cos_sfu(phi); a.st = sin_sfu(theta); a.ct = cos_sfu(theta);
+        } else {
+            const float4 r = decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(x1 * BTSLPG_PI_F, 3.0f));
+            a.sp = r.x; a.cp = r.y; a.st = r.z; a.ct = r.w;
+        }
+    } else {
+        const F2 pt = mul2(f2(x0, x1), f2(2.0f * BTSLPG_PI_F, BTSLPG_PI_F));   // (phi, x1*pi)
+        const float phi = lo(pt), t = hi(pt);
+        const float q0 = t * 0x1.555556p-2f;
+        const float theta = fmaf(fmaf(-3.0f, q0, t), 0x1.555556p-2f, q0);
+        if (fmaxf(fabsf(phi), fabsf(theta)) <= 1000.0f) {
+            sincos_quadrant2(f2(phi, theta), a);
+        } else {   // IEEE division for theta as well (the 3-instruction form assumes no overflow)
+            const float4 r = decode_angles_slow((x0 * 2.0f) * BTSLPG_PI_F, __fdiv_rn(t, 3.0f));
+            a.sp = r.x; a.cp = r.y; a.st = r.z; a.ct = r.w;
+        }
     }
+}
+// the decode a kernel with element type T uses
+template <typename T> __device__ __forceinline__ void decode_angles_for(float x0, float x1, Angles &a) {
+    decode_angles<sizeof(T) == 2>(x0, x1, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -133,6 +167,7 @@ template <int R, int ROWS, int SUB> struct Dirs {
     static __device__ __forceinline__ float a(int k) { return Tab::off(SUB * ROWS + k); }
     static __device__ __forceinline__ F2 w2(int k, int q) { return Tab::w2((SUB * ROWS + k) * R + q); }
     static __device__ __forceinline__ F2 v2(int k, int q) { return Tab::v2((SUB * ROWS + k) * R + q); }
+    static __device__ __forceinline__ F2 u2(int k, int q) { return Tab::u2((SUB * ROWS + k) * R + q); }
 };
 
 // does patch row (SUB*ROWS + k) carry a down-sampled sample (row % D == 0)?
@@ -232,47 +267,73 @@ __device__ __forceinline__ void lpg_load_patch(const T *grow, uint32_t gf_sH, co
 }
 
 // Partial sums of one thread over its ROWS rows of the patch of coarse pixel `px`:
-//   inv = 1/den ; u = G*inv ; y = u*inv ; acc[3] += u ; acc[2] += y*w ; acc[1] += y*v ; acc[0] += a_p * (row sum of y*w)
-// (w, v = b_q*w from the direction table) so that, after the threads of a group are added,
-// g1..g3 = -n4 * acc[0..2] and g4 = acc[3].  Per PAIR of pixels: 7 packed instructions + 2 MUFU.RCP.
+//   inv = 1/den ; t = G*inv ; y = t*inv ; acc[3] += t ; acc[2] += y*w ; acc[1] += y*v ; acc[0] += y*u
+// (u = a_p*w, v = b_q*w, w: the direction table) so that, after the threads of a group are added,
+// g1..g3 = -n4 * acc[0..2] and g4 = acc[3].  The four sums stay PACKED (even / odd columns) over the
+// whole patch and are folded once at the end: 8 packed instructions + 2 MUFU.RCP per pair of pixels,
+// 2 instructions per row, 4 per patch.  Fixed order: rows, then column pairs, then even + odd.
 template <int R, int PX, int ROWS, int SUB>
 __device__ __forceinline__ void lpg_patch_partial(const float (&G)[ROWS][PX * R], int px, float n1, float n2, float n3, float (&acc)[4]) {
     using Tab = DirTable<R>;
     using Dir = Dirs<R, ROWS, SUB>;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
     const F2 n2b = f2(n2);
+    F2 r1, r2, r3, r4;
 #pragma unroll
-    for (int k = 0; k < ROWS; ++k) {            // fixed order: column pairs inside a row, then the two halves, then rows
-        const float ap = Dir::a(k);
-        const F2 A2 = f2(fmaf(ap, n1, n3));
-        F2 r2 = f2(0.f), r3 = f2(0.f), r4 = f2(0.f);
+    for (int k = 0; k < ROWS; ++k) {
+        const F2 A2 = f2(fmaf(Dir::a(k), n1, n3));
 #pragma unroll
         for (int q = 0; q < R; q += 2) {
             const F2 w = Dir::w2(k, q);
             const F2 inv = rcp2(fma2(w, fma2(Tab::off2(q), n2b, A2), f2(BTSLPG_EPS_F)));
-            const F2 u = mul2(f2(G[k][px * R + q], G[k][px * R + q + 1]), inv);
-            const F2 y = mul2(u, inv);
-            r4 = add2(r4, u);
-            r3 = fma2(y, w, r3);
-            r2 = fma2(y, Dir::v2(k, q), r2);
+            const F2 t = mul2(f2(G[k][px * R + q], G[k][px * R + q + 1]), inv);
+            const F2 y = mul2(t, inv);
+            if (k == 0 && q == 0) {        // resolved at compile time (the loops are unrolled): no zero-initialised sums
+                r4 = t;
+                r3 = mul2(y, w);
+                r2 = mul2(y, Dir::v2(k, q));
+                r1 = mul2(y, Dir::u2(k, q));
+            } else {
+                r4 = add2(r4, t);
+                r3 = fma2(y, w, r3);
+                r2 = fma2(y, Dir::v2(k, q), r2);
+                r1 = fma2(y, Dir::u2(k, q), r1);
+            }
         }
-        const float s3 = lo(r3) + hi(r3);
-        acc[0] = fmaf(ap, s3, acc[0]);
-        acc[1] += lo(r2) + hi(r2);
-        acc[2] += s3;
-        acc[3] += lo(r4) + hi(r4);
     }
+    acc[0] = lo(r1) + hi(r1);
+    acc[1] = lo(r2) + hi(r2);
+    acc[2] = lo(r3) + hi(r3);
+    acc[3] = lo(r4) + hi(r4);
 }
 
 // acc (summed over the whole patch) -> d loss / d (x0, x1, x2)
 __device__ __forceinline__ void lpg_finish_grad(const Angles &a, float n4, const float (&acc)[4], float *gout) {
+    // explicit rounding steps (no compiler contraction): bit-identical to lpg_finish_grad2 below
     const float m = -n4;
-    const float g1 = acc[0] * m, g2 = acc[1] * m, g3 = acc[2] * m;
-    const float gph = a.st * (g2 * a.cp - g1 * a.sp);
-    const float gth = a.ct * (g1 * a.cp + g2 * a.sp) - g3 * a.st;
-    gout[0] = (2.0f * BTSLPG_PI_F) * gph;
-    gout[1] = (BTSLPG_PI_F / 3.0f) * gth;
+    const float g1 = __fmul_rn(acc[0], m), g1n = __fmul_rn(acc[0], n4);   // g1, -g1
+    const float g2 = __fmul_rn(acc[1], m);
+    const float g3n = __fmul_rn(acc[2], n4);                              // -g3
+    const float gph = __fmul_rn(a.st, fmaf(g1n, a.sp, __fmul_rn(g2, a.cp)));                      // st*(g2*cp - g1*sp)
+    const float gth = fmaf(a.ct, fmaf(g2, a.sp, __fmul_rn(g1, a.cp)), __fmul_rn(g3n, a.st));      // ct*(g1*cp + g2*sp) - g3*st
+    gout[0] = __fmul_rn(gph, 2.0f * BTSLPG_PI_F);
+    gout[1] = __fmul_rn(gth, BTSLPG_PI_F / 3.0f);
     gout[2] = acc[3];
+}
+// the same for two coarse pixels at once, every step one packed instruction
+__device__ __forceinline__ void lpg_finish_grad2(const Angles &a0, const Angles &a1, float n40, float n41, const float (&acc0)[4],
+                                                 const float (&acc1)[4], float *gout0, float *gout1) {
+    const F2 n4 = f2(n40, n41), m = f2(-n40, -n41);
+    const F2 A0 = f2(acc0[0], acc1[0]);
+    const F2 g1 = mul2(A0, m), g1n = mul2(A0, n4);                 // g1, -g1
+    const F2 g2 = mul2(f2(acc0[1], acc1[1]), m);
+    const F2 g3n = mul2(f2(acc0[2], acc1[2]), n4);                 // -g3
+    const F2 sp = f2(a0.sp, a1.sp), cp = f2(a0.cp, a1.cp), st = f2(a0.st, a1.st), ct = f2(a0.ct, a1.ct);
+    const F2 gph = mul2(st, fma2(g1n, sp, mul2(g2, cp)));          // st*(g2*cp - g1*sp)
+    const F2 gth = fma2(ct, fma2(g2, sp, mul2(g1, cp)), mul2(g3n, st));   // ct*(g1*cp + g2*sp) - g3*st
+    unpack(mul2(gph, f2(2.0f * BTSLPG_PI_F)), gout0[0], gout1[0]);
+    unpack(mul2(gth, f2(BTSLPG_PI_F / 3.0f)), gout0[1], gout1[1]);
+    gout0[2] = acc0[3];
+    gout1[2] = acc1[3];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,7 +395,7 @@ __device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, uint
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
         Angles a;
-        decode_angles(c[3 * px], c[3 * px + 1], a);
+        decode_angles_for<T>(c[3 * px], c[3 * px + 1], a);
         n1[px] = a.st * a.cp;   // custom_layers.py:50
         n2[px] = a.st * a.sp;
         n3[px] = a.ct;
@@ -395,7 +456,7 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
     float acc[PX][4];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
-        decode_angles(c[3 * px], c[3 * px + 1], a[px]);
+        decode_angles_for<T>(c[3 * px], c[3 * px + 1], a[px]);
         dispatch_sub<LPP>(sub, [&](auto S) {
             lpg_patch_partial<R, PX, ROWS, decltype(S)::value>(G, px, a[px].st * a[px].cp, a[px].st * a[px].sp, a[px].ct, acc[px]);
         });
@@ -424,8 +485,14 @@ __device__ __forceinline__ void lpg_bwd_thread(const LpgBwdParams<T> &prm, uint3
         }
     }
     float gout[PX * 3];
+    if constexpr (PX % 2 == 0) {
 #pragma unroll
-    for (int px = 0; px < PX; ++px) lpg_finish_grad(a[px], c[3 * px + 2], acc[px], &gout[3 * px]);
+        for (int px = 0; px < PX; px += 2)
+            lpg_finish_grad2(a[px], a[px + 1], c[3 * px + 2], c[3 * px + 5], acc[px], acc[px + 1], &gout[3 * px], &gout[3 * px + 3]);
+    } else {
+#pragma unroll
+        for (int px = 0; px < PX; ++px) lpg_finish_grad(a[px], c[3 * px + 2], acc[px], &gout[3 * px]);
+    }
     store_elems<T, PX * 3, 4>(prm.g_coef + (size_t)group * (PX * 3), gout);
 }
 
@@ -460,66 +527,65 @@ __host__ __device__ inline uint32_t threads_for(uint32_t groups, int lpp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Several layers in one launch (the three scales of the decoder).  Block ranges are assigned per
-// layer; the variant switch is block-uniform.
+// The three scales of one decoder in one launch.  Slot s holds the layer with up-ratio 8 >> s
+// (slot 0: r = 8 with ds stride 4, slot 1: r = 4 with ds stride 2, slot 2: r = 2, no ds); an empty
+// slot owns no blocks.  Because the slot index is static inside each branch, every parameter is a
+// constant-bank operand of the instruction that uses it (no indexed LDC, no register copies), and the
+// branch itself is block-uniform.  Blocks of the long r = 8 threads come first, the short r = 2
+// threads fill the tail of the grid.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxMulti = 4;
+constexpr int kMultiSlots = 3;
+__host__ __device__ constexpr int multi_slot(int r) { return r == 8 ? 0 : r == 4 ? 1 : r == 2 ? 2 : -1; }
 
 template <typename T> struct LpgFwdMulti {
-    LpgFwdParams<T> layer[kMaxMulti];
-    uint32_t block_end[kMaxMulti];  // exclusive prefix of blocks per layer
-    int32_t upratio[kMaxMulti];
-    int32_t n;
+    LpgFwdParams<T> layer[kMultiSlots];
+    uint32_t block_end[kMultiSlots];  // exclusive prefix of blocks per slot
 };
 template <typename T> struct LpgBwdMulti {
-    LpgBwdParams<T> layer[kMaxMulti];
-    uint32_t block_end[kMaxMulti];
-    int32_t upratio[kMaxMulti];
-    int32_t n;
+    LpgBwdParams<T> layer[kMultiSlots];
+    uint32_t block_end[kMultiSlots];
 };
 
 // MINB = minimum resident CTAs per SM asked of the compiler (caps registers: occupancy is what hides the
 // one-shot load latency of these kernels); block size is 128.
 constexpr int kMultiThreads = 128;
-// float32: 16 / 10 CTAs per SM (<= 32 / 48 registers; measured: profiles/experiments/README.md); bfloat16 threads hold twice the pixels: 12 / 8
+// float32: 16 / 12 CTAs per SM (<= 32 / 40 registers; measured: profiles/experiments/README.md); bfloat16 threads hold twice the pixels: 12 / 8
 #ifndef BTSLPG_FWD_MINB
 #define BTSLPG_FWD_MINB 16
 #endif
 #ifndef BTSLPG_BWD_MINB
-#define BTSLPG_BWD_MINB 10
+#define BTSLPG_BWD_MINB 12
 #endif
-template <typename T> constexpr int fwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_FWD_MINB : 12; }
-template <typename T> constexpr int bwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_BWD_MINB : 8; }
+#ifndef BTSLPG_FWD_MINB_BF16
+#define BTSLPG_FWD_MINB_BF16 12
+#endif
+#ifndef BTSLPG_BWD_MINB_BF16
+#define BTSLPG_BWD_MINB_BF16 8
+#endif
+template <typename T> constexpr int fwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_FWD_MINB : BTSLPG_FWD_MINB_BF16; }
+template <typename T> constexpr int bwd_min_blocks() { return sizeof(T) == 4 ? BTSLPG_BWD_MINB : BTSLPG_BWD_MINB_BF16; }
 
 template <typename T>
 __global__ void __launch_bounds__(kMultiThreads, fwd_min_blocks<T>()) lpg_fwd_multi_kernel(const __grid_constant__ LpgFwdMulti<T> m) {
-    int l = 0;
-    uint32_t first = 0;
-#pragma unroll
-    for (int k = 0; k < kMaxMulti - 1; ++k)
-        if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
-    const LpgFwdParams<T> &prm = m.layer[l];
-    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
-    switch (m.upratio[l]) {
-        case 8: lpg_fwd_thread<T, 8, VecCfg<T, 8, true>::PX, VecCfg<T, 8, true>::ROWS, 4>(prm, slot); break;
-        case 4: lpg_fwd_thread<T, 4, VecCfg<T, 4, true>::PX, VecCfg<T, 4, true>::ROWS, 2>(prm, slot); break;
-        default: lpg_fwd_thread<T, 2, VecCfg<T, 2, true>::PX, VecCfg<T, 2, true>::ROWS, 0>(prm, slot); break;
+    const uint32_t blk = blockIdx.x;
+    if (blk < m.block_end[0]) {
+        lpg_fwd_thread<T, 8, VecCfg<T, 8, true>::PX, VecCfg<T, 8, true>::ROWS, 4>(m.layer[0], blk * kMultiThreads + threadIdx.x);
+    } else if (blk < m.block_end[1]) {
+        lpg_fwd_thread<T, 4, VecCfg<T, 4, true>::PX, VecCfg<T, 4, true>::ROWS, 2>(m.layer[1], (blk - m.block_end[0]) * kMultiThreads + threadIdx.x);
+    } else {
+        lpg_fwd_thread<T, 2, VecCfg<T, 2, true>::PX, VecCfg<T, 2, true>::ROWS, 0>(m.layer[2], (blk - m.block_end[1]) * kMultiThreads + threadIdx.x);
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kMultiThreads, bwd_min_blocks<T>()) lpg_bwd_multi_kernel(const __grid_constant__ LpgBwdMulti<T> m) {
-    int l = 0;
-    uint32_t first = 0;
-#pragma unroll
-    for (int k = 0; k < kMaxMulti - 1; ++k)
-        if (k < m.n - 1 && blockIdx.x >= m.block_end[k]) { l = k + 1; first = m.block_end[k]; }
-    const LpgBwdParams<T> &prm = m.layer[l];
-    const uint32_t slot = (blockIdx.x - first) * blockDim.x + threadIdx.x;
-    switch (m.upratio[l]) {
-        case 8: lpg_bwd_thread<T, 8, VecCfg<T, 8, false>::PX, VecCfg<T, 8, false>::ROWS, 4>(prm, slot); break;
-        case 4: lpg_bwd_thread<T, 4, VecCfg<T, 4, false>::PX, VecCfg<T, 4, false>::ROWS, 2>(prm, slot); break;
-        default: lpg_bwd_thread<T, 2, VecCfg<T, 2, false>::PX, VecCfg<T, 2, false>::ROWS, 0>(prm, slot); break;
+    const uint32_t blk = blockIdx.x;
+    if (blk < m.block_end[0]) {
+        lpg_bwd_thread<T, 8, VecCfg<T, 8, false>::PX, VecCfg<T, 8, false>::ROWS, 4>(m.layer[0], blk * kMultiThreads + threadIdx.x);
+    } else if (blk < m.block_end[1]) {
+        lpg_bwd_thread<T, 4, VecCfg<T, 4, false>::PX, VecCfg<T, 4, false>::ROWS, 2>(m.layer[1], (blk - m.block_end[0]) * kMultiThreads + threadIdx.x);
+    } else {
+        lpg_bwd_thread<T, 2, VecCfg<T, 2, false>::PX, VecCfg<T, 2, false>::ROWS, 0>(m.layer[2], (blk - m.block_end[1]) * kMultiThreads + threadIdx.x);
     }
 }
 

@@ -1,18 +1,20 @@
 #!/bin/bash
+# A/B session: parity tests on the default build, then the LPG microbench (f32 + bf16) for the default
+# build and every experiment build lib/libbtslpg_<tag>.so named in $TAGS.
 mkdir -p gpurun_out/ab
-X=$PWD/bts-fully-tf_b200/lib/libbtslpg_x.so
-BTSLPG_LIB=$X python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/ab/pytest_x.log 2>&1; echo "pytest x exit $?"; tail -3 gpurun_out/ab/pytest_x.log
-for i in 1 2; do
-timeout 300 python bench.py --skip-cpu --skip-e2e > gpurun_out/ab/bench_v5_$i.json 2> gpurun_out/ab/bench_v5_$i.err; echo "v5 exit $?"
-BTSLPG_LIB=$X timeout 300 python bench.py --skip-cpu --skip-e2e > gpurun_out/ab/bench_x_$i.json 2> gpurun_out/ab/bench_x_$i.err; echo "x exit $?"
+LIBDIR=$PWD/bts-fully-tf_b200/lib
+python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/ab/pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/ab/pytest.log
+for tag in default $TAGS; do
+  if [ $tag = default ]; then unset BTSLPG_LIB; else export BTSLPG_LIB=$LIBDIR/libbtslpg_$tag.so; fi
+  timeout 300 python bench.py --skip-cpu --skip-e2e > gpurun_out/ab/bench_${tag}_f32.json 2> gpurun_out/ab/bench_${tag}_f32.err; echo "$tag f32 exit $?"
+  timeout 300 python bench.py --skip-cpu --skip-e2e --dtype bf16 > gpurun_out/ab/bench_${tag}_bf16.json 2> gpurun_out/ab/bench_${tag}_bf16.err; echo "$tag bf16 exit $?"
 done
-timeout 300 python bench.py --skip-cpu --skip-e2e --dtype bf16 > gpurun_out/ab/bench_v5_bf16.json 2>/dev/null
-BTSLPG_LIB=$X timeout 300 python bench.py --skip-cpu --skip-e2e --dtype bf16 > gpurun_out/ab/bench_x_bf16.json 2>/dev/null
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/ab/bench_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, d['value'], d['extras']['per_pass'])
+        pp=d['extras']['per_pass']
+        print("%-44s %8.1f GB/s  fwd %6.2f us (%.3f)  bwd %6.2f us (%.3f)" % (f.split('/')[-1], d['value'], pp['fwd']['us'], pp['fwd']['frac_of_peak'], pp['bwd']['us'], pp['bwd']['frac_of_peak']))
     except Exception as e: print(f, 'ERR', e)
 PY
