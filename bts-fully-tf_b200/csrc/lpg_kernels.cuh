@@ -5,19 +5,22 @@
 // (1,H,W,3) constant of unit pixel directions, sum, add eps, divide.  ~1.1 GB of HBM traffic for
 // 44-69 MB of algorithmic bytes at B=32, 480x640.
 //
-// What these kernels do.  A "group" is PX horizontally adjacent coarse pixels; LPP = r/ROWS lanes
-// of one warp share a group, each owning ROWS rows of its r x r patches (LPP = 1 for r = 2, 4;
-// LPP = 4 for r = 8 so that every thread produces ~16 output pixels and the grid has several
-// waves of short threads).  A lane reads the group's 3*PX coefficients once, decodes the planes,
-// and produces its rows; each row of PX*r outputs is one 16- or 32-byte store, so a warp writes
-// 256-1024 contiguous bytes per row and instruction.  Loops over the patch are fully unrolled:
-// with LPP = 1 the direction table is read as constant-bank operands of the FFMAs themselves;
-// with LPP > 1 a lane keeps the weights of its rows in registers.  The (1,H,W,3) constant of the
-// reference is never materialised.  The strided down-sampled copy (bts_decoder.py:81,88) is
-// written from the same registers.
+// What these kernels do.  A "group" is PX horizontally adjacent coarse pixels.  One thread owns a
+// group and ROWS rows of its r x r patches: ROWS = r (the whole patch) everywhere except the
+// float32 r = 8 backward and the bfloat16 r = 8 kernels, where a patch is split over LPP = r/ROWS
+// consecutive WARPS of a CTA (warp s takes rows [s*ROWS, (s+1)*ROWS)) so that no thread has to hold
+// 64+ gradients in registers.  A thread reads the group's 3*PX coefficients once, decodes the
+// planes, and produces its rows; each row of PX*r outputs is one 16- or 32-byte store, so a warp
+// writes 256-1024 contiguous bytes per row and instruction.  Loops over the patch are fully
+// unrolled and the row index is a compile-time constant (the warp-uniform split index is turned
+// into one by a switch), so the direction table is read as constant-bank operands of the packed
+// FMAs themselves: no loads, no registers.  The (1,H,W,3) constant of the reference is never
+// materialised.  The strided down-sampled copy (bts_decoder.py:81,88) is written from the same
+// registers.
 //
 // Backward keeps the same ownership: the patch reduction is a fixed-order sum
-// inside each lane followed, for LPP > 1, by a fixed xor-shuffle tree over the LPP lanes:
+// inside each thread (packed even/odd column sums over the rows, folded once) followed, for
+// LPP > 1, by a fixed-order add of the LPP warps' partials exchanged through shared memory:
 // deterministic, no atomics.
 //
 // Arithmetic:  den = w_pq * (a_p*n1 + b_q*n2 + n3) + eps   with (a_p*w_pq, b_q*w_pq, w_pq) the
