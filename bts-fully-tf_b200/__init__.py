@@ -6,6 +6,8 @@ Only what the path needs lives here:
   _cabi.py     ctypes binding (BtsTensor == DLTensor, zero copy)
   ops.py       functional ops + autograd glue
   layers.py    LocalPlanarGuidance / ReductionLPG with the reference's layer protocol
+  losses.py    si_log_loss_wrapper (bts.py:27-41) / fused sigmoid*max_depth + loss
+  eval_metrics.py  metrics_list_factory (custom_eval_metrics.py) from one fused pass
   decoder.py   decoder_model(...) wiring of bts_decoder.py around the fused ops (torch/cuDNN glue)
   parallel.py  batch sharding + gradient bucket all-reduce (one process per GPU, NCCL)
   host_io.py   pinned-host staging for callers whose tensors live in host memory

@@ -62,6 +62,13 @@ SYMBOLS = {
     "btslpg_reduce_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
     "btslpg_reduce_backward": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, ctypes.c_int, ctypes.c_int, _TP, _TP, _TP,
                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "btslpg_tail_workspace_bytes": (ctypes.c_size_t, []),
+    "btslpg_silog_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, _TP, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.c_void_p]),
+    "btslpg_silog_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_int, _TP, ctypes.c_void_p]),
+    "btslpg_eval_metrics": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p]),
     "btslpg_launch_count": (ctypes.c_uint64, []),
     "btslpg_reset_launch_count": (None, []),
     "btslpg_last_kernel": (ctypes.c_char_p, []),

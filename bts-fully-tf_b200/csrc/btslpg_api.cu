@@ -11,6 +11,7 @@
 #include "../../include/btslpg.h"
 #include "head_kernels.cuh"
 #include "lpg_kernels.cuh"
+#include "tail_kernels.cuh"
 
 using namespace btslpg;
 
@@ -557,3 +558,4 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 }  // extern "C"
 
 #include "head_api.inl"
+#include "tail_api.inl"

@@ -1,0 +1,166 @@
+// tail_api.inl -- C ABI for the decoder-tail entry points (silog loss, eval metrics); included by btslpg_api.cu.
+
+namespace {
+
+// flat (B,H,W[,1]) map: contiguous, 16-byte aligned
+int parse_flat(const BtsTensor *t, const char *name, View &v, int64_t &n) {
+    if (int e = parse_map(t, name, v)) return e;
+    n = v.B * v.H * v.W;
+    // strides of extent-1 dimensions carry no information (torch reports arbitrary values there)
+    if (n > 0 && !((v.W == 1 || v.sW == 1) && (v.H == 1 || v.sH == v.W) && (v.B == 1 || v.sB == v.H * v.W)))
+        return fail(BTSLPG_ELAYOUT, "%s: must be contiguous", name);
+    if (!v.aligned(16)) return fail(BTSLPG_ELAYOUT, "%s: must be 16-byte aligned", name);
+    return 0;
+}
+
+int same_as(const View &a, int64_t na, const View &ref, int64_t nref, const char *name, const char *ref_name) {
+    if (na != nref || a.B != ref.B || a.H != ref.H || a.W != ref.W) return fail(BTSLPG_ESHAPE, "%s: shape differs from %s", name, ref_name);
+    if (a.dtype != ref.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", name, ref_name);
+    if (a.dev != ref.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", name, ref_name);
+    return 0;
+}
+
+// float32 device vector with at least `need` elements
+int parse_f32_vec(const BtsTensor *t, const char *name, int64_t need, int dev, float *&ptr) {
+    View v;
+    if (int e = parse_common(t, name, v)) return e;
+    if (v.dtype != kF32) return fail(BTSLPG_EDTYPE, "%s: must be float32", name);
+    if (v.dev != dev) return fail(BTSLPG_EDEVICE, "%s: on a different device", name);
+    int64_t n = 1;
+    for (int k = 0; k < t->ndim; ++k) n *= t->shape[k];
+    if (n < need) return fail(BTSLPG_ESHAPE, "%s: needs at least %lld float32 elements, got %lld", name, (long long)need, (long long)n);
+    if (t->strides && t->ndim > 0 && t->shape[t->ndim - 1] > 1 && t->strides[t->ndim - 1] != 1)
+        return fail(BTSLPG_ELAYOUT, "%s: must be contiguous", name);
+    if (!v.aligned(4)) return fail(BTSLPG_ELAYOUT, "%s: misaligned", name);
+    ptr = reinterpret_cast<float *>(v.ptr);
+    return 0;
+}
+
+int tail_blocks(int64_t n, int elems_per_vec) {
+    const int64_t nvec = n / elems_per_vec;
+    int64_t b = (nvec + kTailThreads - 1) / kTailThreads;
+    if (b < 1) b = 1;
+    if (b > kTailMaxBlocks) b = kTailMaxBlocks;
+    return (int)b;
+}
+
+int check_tail_ws(const void *ws, size_t bytes, const char *what) {
+    if (!ws) return fail(BTSLPG_EWORKSPACE, "%s: workspace is NULL", what);
+    if (bytes < kTailWorkspaceBytes) return fail(BTSLPG_EWORKSPACE, "%s: workspace needs %zu bytes, got %zu", what, (size_t)kTailWorkspaceBytes, bytes);
+    if (reinterpret_cast<uintptr_t>(ws) % 16) return fail(BTSLPG_EWORKSPACE, "%s: workspace must be 16-byte aligned", what);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t btslpg_tail_workspace_bytes(void) { return kTailWorkspaceBytes; }
+
+int btslpg_silog_forward(const BtsTensor *logit, const BtsTensor *y_true, float max_depth, float gt_threshold, BtsTensor *depth_est,
+                         BtsTensor *loss, void *workspace, size_t workspace_bytes, void *stream) {
+    View z, yt, y;
+    int64_t n = 0, nyt = 0, nz = 0;
+    if (!logit && !y_true) return fail(BTSLPG_EINVAL, "silog_forward: logit and y_true are both NULL (nothing to compute)");
+    if (int e = parse_flat(depth_est, "depth_est", y, n)) return e;
+    if (logit) {
+        if (int e = parse_flat(logit, "logit", z, nz)) return e;
+        if (int e = same_as(z, nz, y, n, "logit", "depth_est")) return e;
+    }
+    z.dtype = y.dtype; z.dev = y.dev;
+    float *loss_ptr = nullptr;
+    if (y_true) {
+        if (int e = parse_flat(y_true, "y_true", yt, nyt)) return e;
+        if (int e = same_as(yt, nyt, y, n, "y_true", "depth_est")) return e;
+        if (!loss) return fail(BTSLPG_EINVAL, "loss: tensor is NULL (required with y_true)");
+        if (int e = parse_f32_vec(loss, "loss", 1, z.dev, loss_ptr)) return e;
+        if (int e = check_tail_ws(workspace, workspace_bytes, "btslpg_silog_forward")) return e;
+    }
+    DeviceGuard guard(z.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", z.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        SilogFwdParams<T> p;
+        p.logit = logit ? reinterpret_cast<const T *>(z.ptr) : nullptr;
+        p.y_true = y_true ? reinterpret_cast<const T *>(yt.ptr) : nullptr;
+        p.depth = reinterpret_cast<T *>(y.ptr);
+        p.loss = loss_ptr;
+        p.workspace = workspace;
+        p.n = (uint64_t)n;
+        p.max_depth = max_depth;
+        p.threshold = gt_threshold;
+        silog_fwd_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "silog_fwd<%s,%s>", ElemTraits<T>::kName, !y_true ? "depth" : logit ? "depth+loss" : "loss");
+        return check_launch("btslpg_silog_forward");
+    };
+    return z.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+int btslpg_silog_backward(const BtsTensor *depth_est, const BtsTensor *y_true, float max_depth, float gt_threshold, const BtsTensor *g_loss,
+                          const void *workspace, size_t workspace_bytes, int wrt_logit, BtsTensor *g_out, void *stream) {
+    View y, yt, g;
+    int64_t n = 0, nyt = 0, ng = 0;
+    if (int e = parse_flat(depth_est, "depth_est", y, n)) return e;
+    if (int e = parse_flat(y_true, "y_true", yt, nyt)) return e;
+    if (int e = same_as(yt, nyt, y, n, "y_true", "depth_est")) return e;
+    if (int e = parse_flat(g_out, "g_out", g, ng)) return e;
+    if (int e = same_as(g, ng, y, n, "g_out", "depth_est")) return e;
+    float *gl = nullptr;
+    if (g_loss)
+        if (int e = parse_f32_vec(g_loss, "g_loss", 1, y.dev, gl)) return e;
+    if (int e = check_tail_ws(workspace, workspace_bytes, "btslpg_silog_backward")) return e;
+    DeviceGuard guard(y.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", y.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        SilogBwdParams<T> p;
+        p.depth = reinterpret_cast<const T *>(y.ptr);
+        p.y_true = reinterpret_cast<const T *>(yt.ptr);
+        p.g_loss = gl;
+        p.workspace = workspace;
+        p.g_logit = reinterpret_cast<T *>(g.ptr);
+        p.n = (uint64_t)n;
+        p.max_depth = max_depth;
+        p.threshold = gt_threshold;
+        p.wrt_logit = wrt_logit ? 1 : 0;
+        silog_bwd_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "silog_bwd<%s,%s>", ElemTraits<T>::kName, wrt_logit ? "logit" : "depth");
+        return check_launch("btslpg_silog_backward");
+    };
+    return y.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval, float max_depth_eval, BtsTensor *metrics,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    View yt, yp;
+    int64_t n = 0, np_ = 0;
+    if (int e = parse_flat(y_true, "y_true", yt, n)) return e;
+    if (int e = parse_flat(y_pred, "y_pred", yp, np_)) return e;
+    if (int e = same_as(yp, np_, yt, n, "y_pred", "y_true")) return e;
+    float *out = nullptr;
+    if (!metrics) return fail(BTSLPG_EINVAL, "metrics: tensor is NULL");
+    if (int e = parse_f32_vec(metrics, "metrics", 10, yt.dev, out)) return e;
+    if (int e = check_tail_ws(workspace, workspace_bytes, "btslpg_eval_metrics")) return e;
+    DeviceGuard guard(yt.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", yt.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        MetricsParams<T> p;
+        p.y_true = reinterpret_cast<const T *>(yt.ptr);
+        p.y_pred = reinterpret_cast<const T *>(yp.ptr);
+        p.out = out;
+        p.workspace = workspace;
+        p.n = (uint64_t)n;
+        p.min_depth = min_depth_eval;
+        p.max_depth = max_depth_eval;
+        eval_metrics_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "eval_metrics<%s>", ElemTraits<T>::kName);
+        return check_launch("btslpg_eval_metrics");
+    };
+    return yt.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+}  // extern "C"

@@ -8,6 +8,8 @@ Reference lines replaced:
   lpg_forward / LpgFunction     custom_layers.py:47-56 (+ the slices bts_decoder.py:81,88)
   reduce_lpg / ReduceLpgFunction bts_decoder.py:79-81, 86-88, 93-94
   lpg_forward_multi / lpg_backward_multi   the three layers of one decoder in one launch
+  depth_silog / si_log_loss      bts_decoder.py:102-103 + bts.py:27-41
+  eval_metrics                   custom_eval_metrics.py:24-88
 """
 import ctypes
 
@@ -243,6 +245,112 @@ def reduce_lpg(feat, kernel, upratio, ds_stride=0, g_kernel_out=None):
     g_kernel_out: optional float32 view (same numel as kernel) that receives d loss / d kernel in backward."""
     coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride), g_kernel_out)
     return (coef, full, ds) if ds_stride else (coef, full)
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder tail: sigmoid * max_depth + si_log_loss, eval metrics
+# ---------------------------------------------------------------------------------------------
+def tail_workspace(device):
+    """A fresh workspace for one silog forward/backward pair or one metrics call (header zeroed).  The
+    forward leaves its statistics in it for the backward, so it is NOT shared between calls."""
+    return torch.zeros(int(load().btslpg_tail_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def silog_forward(logit, y_true, max_depth, gt_threshold, depth_est=None, workspace=None):
+    """depth_est = sigmoid(logit)*max_depth (logit given) and loss = si_log_loss(y_true, depth_est) (y_true given),
+    one kernel.  Returns (depth_est, loss-or-None, workspace-or-None)."""
+    lib = load()
+    src = logit if logit is not None else depth_est
+    if depth_est is None:
+        depth_est = torch.empty_like(logit, memory_format=torch.contiguous_format)
+    loss = None
+    if y_true is not None:
+        loss = torch.empty((), dtype=torch.float32, device=src.device)
+        if workspace is None:
+            workspace = tail_workspace(src.device)
+    rz, rt, ry, rl = as_ref(logit), as_ref(y_true), as_ref(depth_est), as_ref(loss)
+    check(lib.btslpg_silog_forward(ptr_or_null(rz), ptr_or_null(rt), float(max_depth), float(gt_threshold), ry.ptr, ptr_or_null(rl),
+                                   ctypes.c_void_p(workspace.data_ptr() if workspace is not None else 0),
+                                   workspace.numel() if workspace is not None else 0, current_stream_ptr(src.device)))
+    return depth_est, loss, workspace
+
+
+def silog_backward(depth_est, y_true, max_depth, gt_threshold, workspace, g_loss=None, wrt_logit=True, g_out=None):
+    """d loss / d logit (wrt_logit) or d loss / d depth_est, scaled by the device scalar g_loss (None = 1)."""
+    lib = load()
+    if g_out is None:
+        g_out = torch.empty_like(depth_est, memory_format=torch.contiguous_format)
+    if g_loss is not None:
+        g_loss = g_loss.reshape(1).float()
+    ry, rt, rg, ro = as_ref(depth_est), as_ref(y_true), as_ref(g_loss), as_ref(g_out)
+    check(lib.btslpg_silog_backward(ry.ptr, rt.ptr, float(max_depth), float(gt_threshold), ptr_or_null(rg),
+                                    ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), 1 if wrt_logit else 0, ro.ptr,
+                                    current_stream_ptr(depth_est.device)))
+    return g_out
+
+
+class DepthSilogFunction(torch.autograd.Function):
+    """(logit, y_true) -> (depth_est, loss): the last activation, the depth_est Lambda and the loss fused.
+    depth_est is returned for inspection / metrics; only `loss` carries gradient."""
+
+    @staticmethod
+    def forward(ctx, logit, y_true, max_depth, gt_threshold):
+        depth_est, loss, ws = silog_forward(logit.contiguous(), y_true.contiguous(), max_depth, gt_threshold)
+        ctx.save_for_backward(depth_est, y_true.contiguous(), ws)
+        ctx.max_depth, ctx.gt_threshold = max_depth, gt_threshold
+        ctx.mark_non_differentiable(depth_est)
+        return depth_est, loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _g_depth, g_loss):
+        depth_est, y_true, ws = ctx.saved_tensors
+        return silog_backward(depth_est, y_true, ctx.max_depth, ctx.gt_threshold, ws, g_loss, wrt_logit=True), None, None, None
+
+
+class SilogLossFunction(torch.autograd.Function):
+    """(y_true, y_pred) -> loss: bts.py:27-41 at the reference's own function boundary."""
+
+    @staticmethod
+    def forward(ctx, y_true, y_pred, gt_threshold):
+        yt, yp = y_true.contiguous(), y_pred.contiguous()
+        _, loss, ws = silog_forward(None, yt, 1.0, gt_threshold, depth_est=yp)
+        ctx.save_for_backward(yp, yt, ws)
+        ctx.gt_threshold = gt_threshold
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_loss):
+        yp, yt, ws = ctx.saved_tensors
+        return None, silog_backward(yp, yt, 1.0, ctx.gt_threshold, ws, g_loss, wrt_logit=False), None
+
+
+def depth_silog(logit, y_true, max_depth, gt_threshold):
+    """Fused decoder tail with autograd: returns (depth_est, loss)."""
+    return DepthSilogFunction.apply(logit, y_true, float(max_depth), float(gt_threshold))
+
+
+def si_log_loss(y_true, y_pred, gt_threshold):
+    """si_log_loss(y_true, y_pred) of bts.py:31-38 with autograd (gradient with respect to y_pred)."""
+    return SilogLossFunction.apply(y_true, y_pred, float(gt_threshold))
+
+
+METRIC_NAMES = ("silog", "abs_rel", "log10", "rmse", "sq_rel", "rmse_log", "d1", "d2", "d3")   # custom_eval_metrics.py:88
+
+
+def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, out=None, workspace=None):
+    """All nine eval metrics of custom_eval_metrics.py in one pass.  Returns a float32 device tensor
+    [silog, abs_rel, log10, rmse, sq_rel, rmse_log, d1, d2, d3, n_valid]."""
+    lib = load()
+    if out is None:
+        out = torch.empty(10, dtype=torch.float32, device=y_true.device)
+    if workspace is None:
+        workspace = tail_workspace(y_true.device)
+    rt, rp, ro = as_ref(y_true.contiguous()), as_ref(y_pred.contiguous()), as_ref(out)
+    check(lib.btslpg_eval_metrics(rt.ptr, rp.ptr, float(min_depth_eval), float(max_depth_eval), ro.ptr,
+                                  ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), current_stream_ptr(y_true.device)))
+    return out
 
 
 def launch_count():

@@ -166,6 +166,45 @@ BTSLPG_API int btslpg_reduce_backward(const BtsTensor *feat, const BtsTensor *ke
                                       void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Decoder tail: the full-resolution passes after the last convolution.
+ * All maps are contiguous, 16-byte aligned (B,H,W[,1]) tensors of one dtype (float32 / bfloat16,
+ * float32 arithmetic, float64 cross-CTA sums).  `workspace` is btslpg_tail_workspace_bytes() bytes
+ * of device memory whose first 256 bytes were zeroed once after allocation (every launch leaves
+ * them zero).  Reductions are deterministic: fixed-order sums, no float atomics.
+ *
+ * btslpg_silog_forward -- replaces bts_decoder.py:102-103 (sigmoid activation of the last Conv2D
+ * and the `depth_est` Lambda) and bts.py:27-41 (si_log_loss) in ONE pass:
+ *   depth_est = sigmoid(logit) * max_depth                                    (written)
+ *   mask = y_true > gt_threshold ; d = log(y_true + 1e-7) - log(depth_est + 1e-7) over the mask
+ *   loss = sqrt(mean(d^2) - 0.85 * mean(d)^2) * 10                            (float32 device scalar)
+ *   logit NULL  : the loss alone on a given depth_est (the reference's si_log_loss(y_true, y_pred))
+ *   y_true NULL : depth_est only (inference); loss / workspace may be NULL
+ * gt_threshold: 0.1 nyu / matterport, 1.0 kitti (bts.py:28).  An empty mask yields NaN like the
+ * reference.  The forward leaves (n, mean d, variance term) in the workspace for the backward.
+ *
+ * btslpg_silog_backward -- TF autodiff of the above: g_out = g_loss * d loss / d logit (wrt_logit
+ * != 0, through the sigmoid) or d loss / d depth_est (wrt_logit == 0).  g_loss: float32 device
+ * scalar, NULL = 1.  `workspace` must be the forward's, untouched in between.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API size_t btslpg_tail_workspace_bytes(void);
+BTSLPG_API int btslpg_silog_forward(const BtsTensor *logit, const BtsTensor *y_true, float max_depth,
+                                    float gt_threshold, BtsTensor *depth_est, BtsTensor *loss,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+BTSLPG_API int btslpg_silog_backward(const BtsTensor *depth_est, const BtsTensor *y_true, float max_depth,
+                                     float gt_threshold, const BtsTensor *g_loss, const void *workspace,
+                                     size_t workspace_bytes, int wrt_logit, BtsTensor *g_out, void *stream);
+
+/* btslpg_eval_metrics -- replaces custom_eval_metrics.py:24-88: the nine metrics, each of which the
+ * reference computes with its own masked pass (pre_eval re-run every time), from ONE pass:
+ *   mask = min_depth_eval < y_true < max_depth_eval
+ *   pred = clip(where(isfinite(y_pred), y_pred, max_depth_eval), min_depth_eval, max_depth_eval)
+ *   metrics[0..8] = silog, abs_rel, log10, rmse, sq_rel, rmse_log, d1, d2, d3 (the reference's list
+ *   order, custom_eval_metrics.py:88); metrics[9] = number of valid pixels.  float32[>=10] device. */
+BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval,
+                                   float max_depth_eval, BtsTensor *metrics, void *workspace,
+                                   size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").

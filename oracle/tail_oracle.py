@@ -1,0 +1,78 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, float64 unless told otherwise) of the decoder
+tail rows of SURVEY 8(f): N2 `si_log_loss` (/root/reference/bts.py:27-41) behind the final activation
+(/root/reference/bts_decoder.py:102-103) and N4 the eval metrics
+(/root/reference/custom_eval_metrics.py:21-88).
+
+Pinned by tests/golden/tail_*.npz, which tests/golden/make_golden.py produces by executing the
+UNMODIFIED reference files over oracle/tf_shim (same status as the LPG oracle: pinned to the
+reference's own source run over a stand-in runtime; TensorFlow's kernel rounding is not pinned).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+import numpy as np
+
+EPS = 1e-7                                                   # K.epsilon()
+GT_TH = {"nyu": 0.1, "kitti": 1.0, "matterport": 0.1}        # bts.py:28
+METRIC_NAMES = ("silog", "abs_rel", "log10", "rmse", "sq_rel", "rmse_log", "d1", "d2", "d3")   # custom_eval_metrics.py:88
+
+
+def depth_est(logit, max_depth, dtype=np.float64):
+    """bts_decoder.py:102-103: sigmoid activation of the last Conv2D, then the `depth_est` Lambda."""
+    z = np.asarray(logit, dtype)
+    return (dtype(1) / (dtype(1) + np.exp(-z))) * dtype(max_depth)
+
+
+def si_log_loss(y_true, y_pred, threshold, dtype=np.float64):
+    """bts.py:31-38.  Returns (loss, stats) with stats = (n, mean d, mean d^2 - 0.85 mean(d)^2)."""
+    yt, yp = np.asarray(y_true, dtype).ravel(), np.asarray(y_pred, dtype).ravel()
+    mask = yt > dtype(threshold)                                            # :32
+    d = np.log(yt[mask] + dtype(EPS)) - np.log(yp[mask] + dtype(EPS))       # :34-37
+    with np.errstate(invalid="ignore", divide="ignore"):
+        m1 = d.mean() if d.size else dtype(np.nan)
+        m2 = (d * d).mean() if d.size else dtype(np.nan)
+        var = m2 - dtype(0.85) * m1 * m1
+        loss = np.sqrt(var) * dtype(10.0)                                   # :38
+    return loss, (d.size, m1, var)
+
+
+def si_log_loss_grad(y_true, y_pred, threshold, g_loss=1.0, max_depth=None):
+    """Analytic gradient of the loss (float64): with respect to y_pred, or -- when max_depth is given and
+    y_pred = sigmoid(z)*max_depth -- with respect to the logit z (chain rule through bts_decoder.py:102-103)."""
+    yt, yp = np.asarray(y_true, np.float64), np.asarray(y_pred, np.float64)
+    mask = yt > threshold
+    _, (n, m1, var) = si_log_loss(yt, yp, threshold)
+    g = np.zeros_like(yp)
+    d = np.log(yt[mask] + EPS) - np.log(yp[mask] + EPS)
+    gd = g_loss * 10.0 * (d - 0.85 * m1) / (n * np.sqrt(var))
+    g[mask] = -gd / (yp[mask] + EPS)
+    if max_depth is not None:
+        g = g * yp * (1.0 - yp / max_depth)
+    return g
+
+
+def pre_eval(y_true, y_pred, min_depth_eval, max_depth_eval, dtype=np.float64):
+    """custom_eval_metrics.py:24-42 (the crop helper :27-37 is dead code in the reference)."""
+    yt, yp = np.asarray(y_true, dtype).ravel(), np.asarray(y_pred, dtype).ravel()
+    mask = (yt < dtype(max_depth_eval)) & (yt > dtype(min_depth_eval))      # :39
+    yp = np.where(np.isfinite(yp), yp, dtype(max_depth_eval))               # :40
+    yp = np.clip(yp, dtype(min_depth_eval), dtype(max_depth_eval))          # :41
+    return yt[mask], yp[mask]                                               # :42
+
+
+def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, dtype=np.float64):
+    """custom_eval_metrics.py:44-88 -> dict name -> value, plus n_valid."""
+    gt, pred = pre_eval(y_true, y_pred, min_depth_eval, max_depth_eval, dtype)
+    ratio = np.maximum(gt / pred, pred / gt)
+    d = np.log(gt) - np.log(pred)
+    out = {
+        "d1": (ratio < 1.25).astype(dtype).mean(),                         # :47
+        "d2": (ratio < 1.25 ** 2).astype(dtype).mean(),                    # :51
+        "d3": (ratio < 1.25 ** 3).astype(dtype).mean(),                    # :55
+        "rmse": np.sqrt(((gt - pred) ** 2).mean()),                        # :60
+        "rmse_log": np.sqrt((d ** 2).mean()),                              # :64-65
+        "abs_rel": (np.abs(gt - pred) / gt).mean(),                        # :70
+        "sq_rel": (((gt - pred) ** 2) / gt).mean(),                        # :74
+        "silog": np.sqrt((d ** 2).mean() - d.mean() ** 2) * 100,           # :79-80
+        "log10": np.abs(d).mean() / np.log(10.0),                          # :85-86
+        "n_valid": gt.size,
+    }
+    return out

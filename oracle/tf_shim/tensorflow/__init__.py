@@ -50,3 +50,57 @@ def function(*a, **k):  # tf.function() decorator: eager is fine for an oracle
 
 def boolean_mask(tensor, mask):
     return tensor[mask]
+
+
+# ---- symbols used by /root/reference/custom_eval_metrics.py (TensorFlow documentation semantics) ----
+def logical_and(a, b):
+    return _torch.logical_and(a, b)
+
+
+def where(condition, x, y):
+    """tf.where(cond, x, y) with broadcasting; python scalars take the other operand's dtype."""
+    if not isinstance(x, _torch.Tensor):
+        x = _torch.tensor(x, dtype=y.dtype)
+    if not isinstance(y, _torch.Tensor):
+        y = _torch.tensor(y, dtype=x.dtype)
+    return _torch.where(condition, x, y)
+
+
+def clip_by_value(t, clip_value_min, clip_value_max):
+    return _torch.clamp(t, min=clip_value_min, max=clip_value_max)
+
+
+def reduce_mean(x):
+    return _torch.mean(x)
+
+
+def cast(x, dtype):
+    return x.to(dtype)
+
+
+def maximum(a, b):
+    return _torch.maximum(a, b)
+
+
+def sqrt(x):
+    return _torch.sqrt(x)
+
+
+def abs(x):  # noqa: A001 - mirrors the tf name
+    return _torch.abs(x)
+
+
+def zeros_like(x):
+    return _torch.zeros_like(x)
+
+
+class math:  # noqa: N801 - tf.math namespace
+    @staticmethod
+    def is_finite(x):
+        return _torch.isfinite(x)
+
+    @staticmethod
+    def log(x):
+        if not isinstance(x, _torch.Tensor):
+            x = _torch.tensor(x, dtype=_torch.float64)
+        return _torch.log(x)

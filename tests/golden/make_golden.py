@@ -15,6 +15,11 @@ Files written
   lpg_pole_r8.npz     U(0,1) coefficients that reach the theta->pi/3 pole (den <= 0)
   decoder_small.npz   bts_decoder.py:26-105 whole, num_filters=32, float64 run on
                       float32-representable inputs/weights, inference BN and training BN
+  tail_silog.npz      bts.py:27-41 si_log_loss (nyu and kitti thresholds) on depth_est =
+                      sigmoid(logit)*max_depth (bts_decoder.py:102-103): loss and autograd gradients
+                      with respect to depth_est and to the logit, fp32 and float64 runs
+  tail_metrics.npz    custom_eval_metrics.py:21-88, the nine metrics on maps that contain
+                      out-of-range ground truth and NaN / inf / out-of-range predictions
 """
 import os
 import sys
@@ -31,6 +36,8 @@ sys.path.insert(0, REF)
 
 import custom_layers  # noqa: E402  (the reference file, unmodified)
 import bts_decoder  # noqa: E402    (the reference file, unmodified)
+import bts  # noqa: E402            (the reference file, unmodified: si_log_loss_wrapper)
+import custom_eval_metrics  # noqa: E402  (the reference file, unmodified)
 from tensorflow.keras import layers as shim_layers  # noqa: E402
 
 
@@ -121,7 +128,55 @@ def golden_decoder():
     print("decoder_small: %d convs, depth %s" % (out["n_convs"], out["infer_depth_est"].shape))
 
 
+def golden_tail():
+    g = torch.Generator().manual_seed(2024)
+    out = {}
+    for dataset, max_depth, shape in (("nyu", 10.0, (2, 13, 18, 1)), ("kitti", 80.0, (1, 11, 23, 1))):
+        logit = torch.randn(shape, generator=g) * 1.5
+        y_true = torch.rand(shape, generator=g) * max_depth * 1.05
+        y_true[torch.rand(shape, generator=g) < 0.3] = 0.0                 # missing ground truth (below the threshold)
+        loss_fn = bts.si_log_loss_wrapper(dataset)
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            z = logit.detach().clone().to(dt).requires_grad_(True)
+            y_pred = torch.sigmoid(z) * max_depth                          # bts_decoder.py:102-103
+            y_pred.retain_grad()
+            loss = loss_fn(y_true.to(dt), y_pred)
+            loss.backward()
+            out["%s_%s_loss" % (dataset, tag)] = loss.detach().numpy()
+            out["%s_%s_depth_est" % (dataset, tag)] = y_pred.detach().numpy()
+            out["%s_%s_g_depth" % (dataset, tag)] = y_pred.grad.numpy()
+            out["%s_%s_g_logit" % (dataset, tag)] = z.grad.numpy()
+        out[dataset + "_logit"] = logit.numpy()
+        out[dataset + "_y_true"] = y_true.numpy()
+        out[dataset + "_max_depth"] = max_depth
+        print("tail_silog %s: loss %.6f" % (dataset, float(out[dataset + "_f64_loss"])))
+    np.savez(os.path.join(HERE, "tail_silog.npz"), **out)
+
+    class Args:                                                            # the argparse names bts_eval.py passes
+        min_depth_eval, max_depth_eval = 1e-3, 10.0
+        garg_crop = eigen_crop = False
+        dataset = "nyu"
+    shape = (2, 17, 22, 1)
+    y_true = torch.rand(shape, generator=g) * 12.0                         # some beyond max_depth_eval
+    y_true[torch.rand(shape, generator=g) < 0.25] = 0.0
+    y_pred = y_true * torch.exp(torch.randn(shape, generator=g) * 0.3) + 0.05
+    y_pred.view(-1)[3] = float("nan")
+    y_pred.view(-1)[10] = float("inf")
+    y_pred.view(-1)[20] = -float("inf")
+    y_pred.view(-1)[30] = 50.0
+    y_pred.view(-1)[40] = -1.0
+    y_true.view(-1)[[3, 10, 20, 30, 40]] = torch.tensor([2.0, 3.0, 4.0, 5.0, 6.0])
+    out = {"y_true": y_true.numpy(), "y_pred": y_pred.numpy(), "min_depth_eval": Args.min_depth_eval, "max_depth_eval": Args.max_depth_eval}
+    fns = custom_eval_metrics.metrics_list_factory(Args)
+    out["names"] = np.array([f.__name__ for f in fns])
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        out["values_" + tag] = np.array([float(f(y_true.to(dt), y_pred.to(dt))) for f in fns], np.float64)
+    np.savez(os.path.join(HERE, "tail_metrics.npz"), **out)
+    print("tail_metrics:", dict(zip(out["names"], np.round(out["values_f64"], 5))))
+
+
 if __name__ == "__main__":
+    golden_tail()
     golden_lpg()
     golden_pole()
     golden_decoder()
