@@ -331,6 +331,49 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTAs -> result for g_kernel: the last CTA to finish adds the per-CTA partial sums [nblk][C*3] in a
+// fixed order.  The 256 threads are laid out as (C*3/4 float4 columns) x (S slices of the CTA range); a
+// thread walks its slice with eight 16-byte L2 loads in flight (a one-entry-per-thread loop is a chain of
+// ~300 dependent L2 round trips, several microseconds at the end of a 30-200 us kernel), then the S slice
+// sums are combined in slice order through shared memory.  Order: CTAs s, s+S, s+2S, ... inside slice s,
+// then slices 0..S-1 -- fixed for a given grid size, no atomics.
+// ------------------------------------------------------------------------------------------------
+template <int C> __device__ __forceinline__ void head_reduce_partials(const float *partial, uint32_t nblk, float *g_kernel) {
+    constexpr int NCOL = C * 3 / 4;          // 24, 48 or 96 float4 columns
+    constexpr int S = 256 / NCOL;            // 10, 5 or 2 slices
+    __shared__ float4 comb[S][NCOL];
+    const int col = threadIdx.x % NCOL, sl = threadIdx.x / NCOL;
+    if (sl < S) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *p4 = reinterpret_cast<const float4 *>(partial) + col;
+        uint32_t blk = sl;
+        for (; blk + 7 * S < nblk; blk += 8 * S) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p4 + (size_t)(blk + u * S) * NCOL);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { v.x += t[u].x; v.y += t[u].y; v.z += t[u].z; v.w += t[u].w; }
+        }
+        for (; blk < nblk; blk += S) {
+            const float4 t = __ldcg(p4 + (size_t)blk * NCOL);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        comb[sl][col] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NCOL) {
+        float4 v = comb[0][threadIdx.x];
+#pragma unroll
+        for (int q = 1; q < S; ++q) {
+            const float4 t = comb[q][threadIdx.x];
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        float *o = g_kernel + 4 * threadIdx.x;        // g_kernel may be a 4-byte-aligned slice of a gradient bucket
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA-staged backward: same per-warp feature ring (feat is re-read for g_kernel); the patch gradients
 // and saved coefficients of a tile are small and loaded directly by lane L for pixel L.
 // ------------------------------------------------------------------------------------------------
@@ -466,11 +509,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_cons
     __syncthreads();
     if (is_last) {
         __threadfence();
-        for (int tt = threadIdx.x; tt < C * 3; tt += blockDim.x) {
-            float v = 0.0f;
-            for (uint32_t blk = 0; blk < gridDim.x; ++blk) v += __ldcg(prm.partial + (size_t)blk * (C * 3) + tt);
-            prm.g_kernel[tt] = v;
-        }
+        head_reduce_partials<C>(prm.partial, gridDim.x, prm.g_kernel);
         if (threadIdx.x == 0) *prm.counter = 0u;   // leave the workspace header zero for the next launch
     }
 }
@@ -594,11 +633,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_kernel(const __grid_constant
     __syncthreads();
     if (is_last) {
         __threadfence();
-        for (int t = threadIdx.x; t < C * 3; t += blockDim.x) {
-            float v = 0.0f;
-            for (uint32_t blk = 0; blk < gridDim.x; ++blk) v += __ldcg(prm.partial + (size_t)blk * (C * 3) + t);
-            prm.g_kernel[t] = v;
-        }
+        head_reduce_partials<C>(prm.partial, gridDim.x, prm.g_kernel);
         if (threadIdx.x == 0) *prm.counter = 0u;   // leave the workspace header zero for the next launch
     }
 }

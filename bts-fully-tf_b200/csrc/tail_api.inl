@@ -36,11 +36,14 @@ int parse_f32_vec(const BtsTensor *t, const char *name, int64_t need, int dev, f
     return 0;
 }
 
-int tail_blocks(int64_t n, int elems_per_vec) {
+// persistent grid: one wave of resident CTAs (occupancy of this kernel x SMs), never more than the work needs
+template <typename KernelT> int tail_blocks(KernelT kernel, int64_t n, int elems_per_vec) {
     const int64_t nvec = n / elems_per_vec;
-    int64_t b = (nvec + kTailThreads - 1) / kTailThreads;
-    if (b < 1) b = 1;
+    int64_t b = (nvec + 2 * kTailThreads - 1) / (2 * kTailThreads);      // two vectors per thread and iteration
+    static const int64_t resident = occupancy_blocks(kernel, kTailThreads);   // queried once per kernel
+    if (b > resident) b = resident;
     if (b > kTailMaxBlocks) b = kTailMaxBlocks;
+    if (b < 1) b = 1;
     return (int)b;
 }
 
@@ -90,7 +93,7 @@ int btslpg_silog_forward(const BtsTensor *logit, const BtsTensor *y_true, float 
         p.n = (uint64_t)n;
         p.max_depth = max_depth;
         p.threshold = gt_threshold;
-        silog_fwd_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        silog_fwd_kernel<T><<<tail_blocks(silog_fwd_kernel<T>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
         snprintf(tl_kernel, sizeof(tl_kernel), "silog_fwd<%s,%s>", ElemTraits<T>::kName, !y_true ? "depth" : logit ? "depth+loss" : "loss");
         return check_launch("btslpg_silog_forward");
     };
@@ -125,7 +128,7 @@ int btslpg_silog_backward(const BtsTensor *depth_est, const BtsTensor *y_true, f
         p.max_depth = max_depth;
         p.threshold = gt_threshold;
         p.wrt_logit = wrt_logit ? 1 : 0;
-        silog_bwd_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        silog_bwd_kernel<T><<<tail_blocks(silog_bwd_kernel<T>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
         snprintf(tl_kernel, sizeof(tl_kernel), "silog_bwd<%s,%s>", ElemTraits<T>::kName, wrt_logit ? "logit" : "depth");
         return check_launch("btslpg_silog_backward");
     };
@@ -156,7 +159,7 @@ int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_pred, float 
         p.n = (uint64_t)n;
         p.min_depth = min_depth_eval;
         p.max_depth = max_depth_eval;
-        eval_metrics_kernel<T><<<tail_blocks(n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+        eval_metrics_kernel<T><<<tail_blocks(eval_metrics_kernel<T>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
         snprintf(tl_kernel, sizeof(tl_kernel), "eval_metrics<%s>", ElemTraits<T>::kName);
         return check_launch("btslpg_eval_metrics");
     };

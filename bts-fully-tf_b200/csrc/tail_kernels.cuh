@@ -41,7 +41,6 @@ struct TailWorkspace {
 // with the totals in tot[] (shared memory); false elsewhere.  Fixed order at every level.
 template <int NV> __device__ __forceinline__ bool tail_grid_sum(const float (&v)[NV], const TailWorkspace &ws, double *tot /* shared [NV] */) {
     __shared__ double red[kTailThreads / 32][NV];
-    __shared__ double fin[kTailThreads];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float w[NV];
@@ -71,19 +70,15 @@ template <int NV> __device__ __forceinline__ bool tail_grid_sum(const float (&v)
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-#pragma unroll 1
-    for (int k = 0; k < NV; ++k) {
+    // one warp per sum: lanes walk the CTA partials (independent loads), then a fixed xor tree in float64
+    for (int k = wid; k < NV; k += kTailThreads / 32) {
         double s = 0.0;
-        for (uint32_t blk = threadIdx.x; blk < gridDim.x; blk += kTailThreads) s += __ldcg(ws.partial + (size_t)blk * NV + k);
-        fin[threadIdx.x] = s;
-        __syncthreads();
-        for (int stride = kTailThreads / 2; stride > 0; stride >>= 1) {
-            if ((int)threadIdx.x < stride) fin[threadIdx.x] += fin[threadIdx.x + stride];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) tot[k] = fin[0];
-        __syncthreads();
+        for (uint32_t blk = lane; blk < gridDim.x; blk += 32) s += __ldcg(ws.partial + (size_t)blk * NV + k);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0) tot[k] = s;
     }
+    __syncthreads();
     if (threadIdx.x == 0) *ws.counter = 0u;     // leave the header zero for the next launch
     return true;
 }
@@ -146,20 +141,37 @@ template <typename T> __global__ void __launch_bounds__(kTailThreads) silog_fwd_
     const uint64_t nvec = prm.n / N;
     const uint64_t stride = (uint64_t)gridDim.x * kTailThreads;
     float acc[3] = {0.0f, 0.0f, 0.0f};
-    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += stride) {
-        float z[N], yt[N], y[N];
-        if (prm.logit) load_elems<T, N, 4>(prm.logit + i * N, z);
-        else load_elems<T, N, 4>(prm.depth + i * N, y);
-        if (prm.y_true) load_elems<T, N, 4>(prm.y_true + i * N, yt);
+    // two vectors per thread and iteration: all four loads are issued before the first use
+    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+        const uint64_t i2 = i + stride;
+        const bool two = i2 < nvec;
+        float z[2][N], yt[2][N], y[2][N];
         if (prm.logit) {
-#pragma unroll
-            for (int e = 0; e < N; ++e) y[e] = tail_sigmoid(z[e]) * prm.max_depth;   // bts_decoder.py:102-103
-            store_elems<T, N, 4>(prm.depth + i * N, y);
+            load_elems<T, N, 4>(prm.logit + i * N, z[0]);
+            if (two) load_elems<T, N, 4>(prm.logit + i2 * N, z[1]);
+        } else {
+            load_elems<T, N, 4>(prm.depth + i * N, y[0]);
+            if (two) load_elems<T, N, 4>(prm.depth + i2 * N, y[1]);
         }
         if (prm.y_true) {
-            // the loss sees depth_est as stored (rounded to T), exactly what a downstream loss op would read
+            load_elems<T, N, 4>(prm.y_true + i * N, yt[0]);
+            if (two) load_elems<T, N, 4>(prm.y_true + i2 * N, yt[1]);
+        }
 #pragma unroll
-            for (int e = 0; e < N; ++e) silog_accum(yt[e], sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(y[e])) : y[e], prm.threshold, acc);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const uint64_t iu = u ? i2 : i;
+            if (prm.logit) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) y[u][e] = tail_sigmoid(z[u][e]) * prm.max_depth;   // bts_decoder.py:102-103
+                store_elems<T, N, 4>(prm.depth + iu * N, y[u]);
+            }
+            if (prm.y_true) {
+                // the loss sees depth_est as stored (rounded to T), exactly what a downstream loss op would read
+#pragma unroll
+                for (int e = 0; e < N; ++e)
+                    silog_accum(yt[u][e], sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(y[u][e])) : y[u][e], prm.threshold, acc);
+            }
         }
     }
     // ragged tail (n % N elements), one thread
@@ -224,13 +236,24 @@ template <typename T> __global__ void __launch_bounds__(kTailThreads) silog_bwd_
     const float inv_md = prm.wrt_logit ? 1.0f / prm.max_depth : 0.0f;
     const uint64_t nvec = prm.n / N;
     const uint64_t stride = (uint64_t)gridDim.x * kTailThreads;
-    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += stride) {
-        float y[N], yt[N], g[N];
-        load_elems<T, N, 4>(prm.depth + i * N, y);
-        load_elems<T, N, 4>(prm.y_true + i * N, yt);
+    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+        const uint64_t i2 = i + stride;
+        const bool two = i2 < nvec;
+        float y[2][N], yt[2][N], g[N];
+        load_elems<T, N, 4>(prm.depth + i * N, y[0]);
+        load_elems<T, N, 4>(prm.y_true + i * N, yt[0]);
+        if (two) {
+            load_elems<T, N, 4>(prm.depth + i2 * N, y[1]);
+            load_elems<T, N, 4>(prm.y_true + i2 * N, yt[1]);
+        }
 #pragma unroll
-        for (int e = 0; e < N; ++e) g[e] = silog_grad(yt[e], y[e], prm.threshold, c1, m1s, inv_md);
+        for (int e = 0; e < N; ++e) g[e] = silog_grad(yt[0][e], y[0][e], prm.threshold, c1, m1s, inv_md);
         store_elems<T, N, 4>(prm.g_logit + i * N, g);
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) g[e] = silog_grad(yt[1][e], y[1][e], prm.threshold, c1, m1s, inv_md);
+            store_elems<T, N, 4>(prm.g_logit + i2 * N, g);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (uint64_t i = nvec * N; i < prm.n; ++i)
@@ -287,12 +310,22 @@ template <typename T> __global__ void __launch_bounds__(kTailThreads) eval_metri
     float acc[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
-    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += stride) {
-        float gt[N], pr[N];
-        load_elems<T, N, 4>(prm.y_true + i * N, gt);
-        load_elems<T, N, 4>(prm.y_pred + i * N, pr);
+    for (uint64_t i = (uint64_t)blockIdx.x * kTailThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+        const uint64_t i2 = i + stride;
+        const bool two = i2 < nvec;
+        float gt[2][N], pr[2][N];
+        load_elems<T, N, 4>(prm.y_true + i * N, gt[0]);
+        load_elems<T, N, 4>(prm.y_pred + i * N, pr[0]);
+        if (two) {
+            load_elems<T, N, 4>(prm.y_true + i2 * N, gt[1]);
+            load_elems<T, N, 4>(prm.y_pred + i2 * N, pr[1]);
+        }
 #pragma unroll
-        for (int e = 0; e < N; ++e) metrics_accum(gt[e], pr[e], prm.min_depth, prm.max_depth, acc);
+        for (int e = 0; e < N; ++e) metrics_accum(gt[0][e], pr[0][e], prm.min_depth, prm.max_depth, acc);
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) metrics_accum(gt[1][e], pr[1][e], prm.min_depth, prm.max_depth, acc);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (uint64_t i = nvec * N; i < prm.n; ++i) metrics_accum(load1(prm.y_true + i), load1(prm.y_pred + i), prm.min_depth, prm.max_depth, acc);

@@ -141,8 +141,9 @@ class BtsDecoder(nn.Module):
         return out
 
     # --- forward -------------------------------------------------------------------------------
-    def forward(self, decoder_inputs):
-        """decoder_inputs: NHWC [dense_features, skip_2, skip_4, skip_8, skip_16] -> depth_est NHWC (B,H,W,1)."""
+    def forward(self, decoder_inputs, return_logit=False):
+        """decoder_inputs: NHWC [dense_features, skip_2, skip_4, skip_8, skip_16] -> depth_est NHWC (B,H,W,1)
+        (return_logit: the pre-activation of the last Conv2D instead, for the fused loss)."""
         dense, s2, s4, s8, s16 = [_to_nchw(t) for t in decoder_inputs]
         iconv5 = self.block5(dense, s16)
         iconv4 = self.block4(iconv5, s8)
@@ -168,10 +169,21 @@ class BtsDecoder(nn.Module):
         up1 = F.elu(self.upconv1(F.interpolate(iconv2, scale_factor=2, mode="nearest")))
         concat1 = torch.cat([up1, _to_nchw(d2), _to_nchw(d4), _to_nchw(d8)], 1)        # bts_decoder.py:99
         iconv1 = F.elu(self.iconv1(concat1))
-        depth = torch.sigmoid(self.depth_conv(iconv1)) * self.max_depth                # bts_decoder.py:102-103
+        logit = self.depth_conv(iconv1)                                                # (B,1,H,W): same memory as NHWC (B,H,W,1)
         self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
                               "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
+        if return_logit:
+            return _nhwc_view(logit)
+        depth = torch.sigmoid(logit) * self.max_depth                                  # bts_decoder.py:102-103
         return _nhwc_view(depth)
+
+    def forward_loss(self, decoder_inputs, y_true, dataset):
+        """Training-step form: (depth_est, loss) with the last activation, the depth_est Lambda
+        (bts_decoder.py:102-103) and si_log_loss (bts.py:27-41) as ONE kernel forward and ONE backward
+        (losses.depth_silog); gradient flows from `loss` into the decoder."""
+        from . import losses
+        logit = self.forward(decoder_inputs, return_logit=True)
+        return losses.depth_silog(logit, y_true, self.max_depth, dataset)
 
 
 def decoder_model(decoder_inputs, max_depth, num_filters=256, is_training=False, decoder=None):

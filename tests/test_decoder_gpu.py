@@ -70,3 +70,29 @@ def test_fused_heads_equal_unfused_composition():
         np.testing.assert_array_equal(layer(red).cpu().numpy(), dec.intermediates["depth_%dx%d_scaled" % (r, r)].detach().cpu().numpy())
     depth = depth.detach()
     assert torch.isfinite(depth).all() and float(depth.max()) <= 10.0 and float(depth.min()) >= 0.0
+
+
+@pytest.mark.parametrize("dataset,max_depth", [("nyu", 10.0), ("kitti", 80.0)])
+def test_forward_loss_equals_unfused_training_step(dataset, max_depth):
+    """decoder.forward_loss (fused sigmoid*max_depth + si_log_loss kernels) == forward() + the torch
+    restatement of bts.py:27-41, for the loss and for every decoder gradient."""
+    from bts_fully_tf_b200.decoder import si_log_loss
+    torch.manual_seed(1)
+    B, H, W, F = 2, 64, 96, 64
+    chans = [24, 8, 8, 12, 16]
+    feats = [torch.randn(B, H // s, W // s, c, device=DEV) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    gt = torch.rand(B, H, W, 1, device=DEV) * max_depth
+    gt[:, :10] = 0.0
+    dec = BtsDecoder(chans, max_depth, num_filters=F).to(DEV).train()
+    depth_a, loss_a = dec.forward_loss(feats, gt, dataset)
+    loss_a.backward()
+    grads_a = [p.grad.clone() for p in dec.parameters()]
+    dec.zero_grad(set_to_none=True)
+    depth_b = dec(feats)
+    loss_b = si_log_loss(gt, depth_b, dataset)
+    loss_b.backward()
+    np.testing.assert_allclose(depth_a.cpu().numpy(), depth_b.detach().cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(float(loss_a.detach()), float(loss_b.detach()), rtol=1e-5)
+    for ga, p in zip(grads_a, dec.parameters()):
+        scale = float(p.grad.abs().max())
+        assert float((ga - p.grad).abs().max()) <= 2e-4 * scale + 1e-9

@@ -86,8 +86,10 @@ def run(cfg_id, a, rank, local_rank, world):
     def step():
         if cfg["train"]:
             bucket.zero()
-            depth = dec(feats)
-            loss = si_log_loss(gt, depth, cfg["dataset"])
+            if a.lpg == "fused":
+                _, loss = dec.forward_loss(feats, gt, cfg["dataset"])      # fused sigmoid*max_depth + si_log_loss kernels
+            else:
+                loss = si_log_loss(gt, dec(feats), cfg["dataset"])
             loss.backward()
             bucket.all_reduce(average=True)            # the one exchange step: decoder gradients only
             bucket.wait()

@@ -103,6 +103,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--sets", type=int, default=4)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain launches (for ncu)")
+    ap.add_argument("--skip-literal", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     dtype = torch.float32 if a.dtype == "f32" else torch.bfloat16
@@ -137,14 +139,14 @@ def main():
         fwd(i)
     ops.reset_launch_count()
     for name, fn, maps in (("silog_fwd", fwd, 3), ("silog_bwd", bwd, 3), ("eval_metrics", met, 2)):
-        us = time_gpu(fn, a.sets, a.steps, a.warmup)
+        us = time_gpu(fn, a.sets, a.steps, a.warmup, graph=not a.no_graph)
         nbytes = maps * n * es
         res[name] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
                      "kernel": ops.last_kernel()}
     launches = ops.launch_count()
 
     # the same work as torch ops on the GPU (a port without custom kernels)
-    if a.dtype == "f32":
+    if a.dtype == "f32" and not a.skip_literal:
         lit_f = time_gpu(lambda i: literal_silog(sets[i]["logit"], sets[i]["y_true"], md, th), a.sets, max(3, a.steps // 5), 2, graph=False)
         lit_m = time_gpu(lambda i: literal_metrics(sets[i]["y_true"], sets[i]["depth"], lo, hi), a.sets, max(3, a.steps // 5), 2, graph=False)
         res["torch_gpu_literal"] = {"silog_fwd_bwd_us": round(lit_f, 1), "eval_metrics_us": round(lit_m, 1),
@@ -171,7 +173,7 @@ def main():
         res["cpu_baseline"] = {"kind": "port", "cores": cores, "sample": "%d of %d images, silog fwd+bwd, torch-CPU literal" % (sb, a.batch),
                                "GBps": round(6 * sb * a.height * a.width * 4 / dt * 1e-9, 2)}
     print(json.dumps({"bench": "decoder tail (SURVEY 8(f) N2, N4)", "workload": "batch %d at %dx%d, %s" % (a.batch, a.height, a.width, a.dtype),
-                      "peak_GBps": pk, "peak_source": pk_src, "sets": a.sets, "steps": a.steps, "cuda_graph": True, "gpu_launches": launches, **res}))
+                      "peak_GBps": pk, "peak_source": pk_src, "sets": a.sets, "steps": a.steps, "cuda_graph": not a.no_graph, "gpu_launches": launches, **res}))
 
 
 if __name__ == "__main__":

@@ -38,6 +38,14 @@ def timed(fn, nsets, n=40):
 
 
 def main():
+    # --tune KEY=VALUE (btslpg_set_tuning, e.g. 7=1: register-staged loads instead of the TMA ring), --only-r R
+    only_r = None
+    for i, arg in enumerate(sys.argv[1:]):
+        if arg == "--tune":
+            k, v = sys.argv[i + 2].split("=")
+            ops.set_tuning(int(k), int(v))
+        if arg == "--only-r":
+            only_r = int(sys.argv[i + 2])
     dev = torch.device("cuda:0")
     B, H, W = 32, 480, 640
     peak = 6533.8
@@ -50,6 +58,8 @@ def main():
     for dtype, es, name in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
         for enc, chans in (("densenet161", (128, 128, 64)), ("resnet50", (64, 64, 32))):
             for (r, d), C in zip(((8, 4), (4, 2), (2, 0)), chans):
+                if only_r is not None and r != only_r:
+                    continue
                 h, w = H // r, W // r
                 gen = torch.Generator(device=dev).manual_seed(0)
                 feats = [torch.nn.functional.elu(torch.randn(B, h, w, C, device=dev, generator=gen)).to(dtype) for _ in range(nsets)]
