@@ -1,0 +1,172 @@
+"""Out-of-bounds detection without a sanitizer (compute-sanitizer is closed on the GPU pool): every tensor
+of a call is carved from the middle of a larger buffer.  Input padding holds NaN -- an out-of-bounds READ
+poisons a result, which the parity check then catches; output padding holds a sentinel -- an out-of-bounds
+WRITE changes it.  Shapes are ragged on purpose (odd widths, pixel counts that are not multiples of the
+vector widths / warp tiles / ring stages)."""
+import numpy as np
+import pytest
+import torch
+
+from bts_fully_tf_b200 import ops
+from oracle import c_oracle, tail_oracle
+import lpg_parity as parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PAD = 4096            # elements of padding on both sides (a multiple of every vector width -> alignment preserved)
+SENTINEL = -12288.0      # exactly representable in bfloat16
+
+
+class Arena:
+    """Hands out tensors surrounded by guard bands and checks the bands afterwards."""
+
+    def __init__(self):
+        self.items = []
+
+    def _carve(self, shape, dtype, fill):
+        n = int(np.prod(shape))
+        n_al = (n + 7) // 8 * 8
+        buf = torch.full((PAD + n_al + PAD,), fill, dtype=dtype, device=DEV)
+        view = buf[PAD:PAD + n].view(shape)
+        self.items.append((buf, n, fill))
+        return view
+
+    def input(self, t):
+        v = self._carve(tuple(t.shape), t.dtype, float("nan"))
+        v.copy_(t.to(DEV))
+        return v
+
+    def output(self, shape, dtype=torch.float32):
+        return self._carve(shape, dtype, SENTINEL)
+
+    def check(self):
+        torch.cuda.synchronize()
+        for buf, n, fill in self.items:
+            lo, hi = buf[:PAD], buf[PAD + (n + 7) // 8 * 8:]
+            slack = buf[PAD + n:PAD + (n + 7) // 8 * 8]
+            for band in (lo, hi, slack):
+                if band.numel() == 0:
+                    continue
+                if fill != fill:
+                    assert torch.isnan(band).all(), "input guard band was overwritten"
+                else:
+                    assert (band.float() == fill).all(), "write outside the output tensor"
+
+
+def npf(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("r,d", [(8, 4), (4, 2), (2, 0)])
+@pytest.mark.parametrize("B,h,w", [(1, 1, 1), (1, 3, 5), (2, 7, 9), (1, 5, 33), (3, 9, 34)])
+def test_lpg_guard_bands(r, d, B, h, w, dtype):
+    g = torch.Generator().manual_seed(h * 100 + w)
+    coef = torch.sigmoid(torch.randn(B, h, w, 3, generator=g)).to(dtype)
+    g_full = torch.randn(B, h * r, w * r, 1, generator=g).to(dtype)
+    g_ds = torch.randn(B, h * r // d, w * r // d, 1, generator=g).to(dtype) if d else None
+    rtol = 1e-5 if dtype == torch.float32 else 1e-2
+    A = Arena()
+    c = A.input(coef)
+    full = A.output((B, h * r, w * r, 1), dtype)
+    ds = A.output((B, h * r // d, w * r // d, 1), dtype) if d else None
+    ops.lpg_forward(c, r, d, out_full=full, out_ds=ds)
+    gc = A.output((B, h, w, 3), dtype)
+    ops.lpg_backward(c, A.input(g_full), A.input(g_ds) if d else None, r, d, g_coef=gc)
+    A.check()
+    parity.check_forward(npf(full), npf(coef), r, rtol=rtol, what="guarded fwd")
+    parity.check_backward(npf(gc), npf(coef), npf(g_full), r, npf(g_ds) if d else None, d, rtol=rtol, what="guarded bwd")
+    if d:
+        assert torch.equal(ds, full[:, ::d, ::d])
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 2, 3), (2, 5, 7)])
+def test_lpg_multi_guard_bands(B, h, w):
+    """the three scales of one decoder in one launch (static layer slots), ragged sizes"""
+    g = torch.Generator().manual_seed(11)
+    A = Arena()
+    fw, bw, keep = [], [], []
+    for r, d in ((8, 4), (4, 2), (2, 0)):
+        hh, ww = h * (8 // r), w * (8 // r)
+        coef = torch.sigmoid(torch.randn(B, hh, ww, 3, generator=g))
+        g_full = torch.randn(B, hh * r, ww * r, 1, generator=g)
+        g_ds = torch.randn(B, hh * r // d, ww * r // d, 1, generator=g) if d else None
+        c = A.input(coef)
+        full = A.output((B, hh * r, ww * r, 1))
+        ds = A.output((B, hh * r // d, ww * r // d, 1)) if d else None
+        gc = A.output((B, hh, ww, 3))
+        fw.append(dict(coef=c, upratio=r, ds_stride=d, out_full=full, out_ds=ds))
+        bw.append(dict(coef=c, g_full=A.input(g_full), g_ds=A.input(g_ds) if d else None, upratio=r, ds_stride=d, g_coef=gc))
+        keep.append((r, d, coef, g_full, g_ds, full, gc))
+    ops.lpg_forward_multi(fw)
+    ops.lpg_backward_multi(bw)
+    A.check()
+    for r, d, coef, g_full, g_ds, full, gc in keep:
+        parity.check_forward(npf(full), coef.numpy(), r, what="guarded multi fwd r=%d" % r)
+        parity.check_backward(npf(gc), coef.numpy(), g_full.numpy(), r, g_ds.numpy() if d else None, d, what="guarded multi bwd r=%d" % r)
+
+
+@pytest.mark.parametrize("r,d", [(8, 4), (4, 2), (2, 0)])
+@pytest.mark.parametrize("C", [32, 64, 128])
+@pytest.mark.parametrize("B,h,w", [(1, 1, 1), (1, 3, 11), (2, 5, 13)])
+def test_head_guard_bands(r, d, C, B, h, w):
+    """fused head: pixel counts that are not multiples of 32 (warp tile) or of the TMA ring stage"""
+    g = torch.Generator().manual_seed(C + r + w)
+    feat = torch.nn.functional.elu(torch.randn(B, h, w, C, generator=g))
+    kern = (torch.rand(C, 3, generator=g) * 2 - 1) * (6.0 / (C + 3)) ** 0.5
+    g_full = torch.randn(B, h * r, w * r, 1, generator=g)
+    g_ds = torch.randn(B, h * r // d, w * r // d, 1, generator=g) if d else None
+    A = Arena()
+    f, k = A.input(feat), A.input(kern)
+    coef = A.output((B, h, w, 3))
+    full = A.output((B, h * r, w * r, 1))
+    ds = A.output((B, h * r // d, w * r // d, 1)) if d else None
+    ops.reduce_lpg_forward(f, k, r, d, out_full=full, out_ds=ds, coef_out=coef)
+    assert ops.last_kernel().startswith("head_lpg_fwd")
+    gk = A.output((C, 3))
+    g_feat, g_kern, g_coef = ops.reduce_lpg_backward(f, k, coef, A.input(g_full), A.input(g_ds) if d else None, r, d,
+                                                    g_kernel_out=gk, need_g_coef=True)
+    A.check()
+    ref = c_oracle.head_forward_f64(feat.numpy(), kern.numpy())
+    np.testing.assert_allclose(npf(coef), ref, rtol=2e-6, atol=1e-7)
+    parity.check_forward(npf(full), npf(coef), r, what="guarded head fwd")
+    assert torch.isfinite(g_feat).all() and torch.isfinite(gk).all() and torch.isfinite(g_coef).all()
+    parity.check_backward(npf(g_coef), npf(coef), g_full.numpy(), r, g_ds.numpy() if d else None, d, what="guarded head bwd")
+    # head gradients from the kernel's own g_coef (float64 restatement of SURVEY 8(a) a8)
+    x = npf(coef).astype(np.float64)
+    dz = npf(g_coef).astype(np.float64) * x * (1 - x)
+    ref_gf = dz.reshape(-1, 3) @ kern.numpy().astype(np.float64).T
+    ref_gk = feat.numpy().astype(np.float64).reshape(-1, C).T @ dz.reshape(-1, 3)
+    assert np.abs(npf(g_feat).reshape(-1, C) - ref_gf).max() <= 1e-5 * max(np.abs(ref_gf).max(), 1e-30)
+    assert np.abs(npf(gk) - ref_gk).max() <= 2e-5 * max(np.abs(ref_gk).max(), 1e-30)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 7, 8, 1023, 1025, 65537])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tail_guard_bands(n, dtype):
+    g = torch.Generator().manual_seed(n)
+    shape = (1, 1, n, 1)
+    logit = (torch.randn(shape, generator=g) * 1.5).to(dtype)
+    y_true = (torch.rand(shape, generator=g) * 10.5).to(dtype)
+    if n > 4:
+        y_true[0, 0, ::3] = 0
+    A = Arena()
+    z, yt = A.input(logit), A.input(y_true)
+    depth = A.output(shape, dtype)
+    ws = ops.tail_workspace(DEV)
+    _, loss, _ = ops.silog_forward(z, yt, 10.0, 0.1, depth_est=depth, workspace=ws)
+    gz = A.output(shape, dtype)
+    ops.silog_backward(depth, yt, 10.0, 0.1, ws, None, True, g_out=gz)
+    m = A.output((10,))
+    ops.eval_metrics(yt, depth, 1e-3, 10.0, out=m)
+    A.check()
+    rtol = 1e-5 if dtype == torch.float32 else 1e-2
+    ref_loss, (nv, _, var) = tail_oracle.si_log_loss(npf(y_true), npf(depth), 0.1)
+    if nv >= 2 and var > 1e-6:
+        np.testing.assert_allclose(float(loss), ref_loss, rtol=rtol)
+        ref_g = tail_oracle.si_log_loss_grad(npf(y_true), npf(depth), 0.1, max_depth=10.0)
+        assert np.abs(npf(gz) - ref_g).max() <= rtol * np.abs(ref_g).max()
+    ref_m = tail_oracle.eval_metrics(npf(y_true), npf(depth), 1e-3, 10.0)
+    assert int(m[9]) == ref_m["n_valid"]
+    if ref_m["n_valid"]:
+        np.testing.assert_allclose(float(m[3]), ref_m["rmse"], rtol=2e-5 if dtype == torch.float32 else 1e-2)
