@@ -87,7 +87,7 @@ template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdPara
         snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_fwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
         return check_launch("btslpg_reduce_forward");
     }
-    constexpr int smem = head_tma_smem_bytes<T, M, true>(256 / 32);
+    constexpr int smem = head_tma_smem_bytes<T, R, M, true>(256 / 32);
     static const int resident = occupancy_blocks_smem(head_lpg_fwd_tma_kernel<T, R, D, M>, threads, smem);
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;
@@ -107,7 +107,7 @@ template <typename T, int R, int D, int M> int launch_head_bwd(HeadBwdParams<T> 
         snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
         return check_launch("btslpg_reduce_backward");
     }
-    constexpr int smem = head_tma_smem_bytes<T, M, false>(256 / 32);
+    constexpr int smem = head_tma_smem_bytes<T, R, M, false>(256 / 32);
     static const int resident = occupancy_blocks_smem(head_lpg_bwd_tma_kernel<T, R, D, M>, threads, smem);
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;

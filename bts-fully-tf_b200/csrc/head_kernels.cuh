@@ -165,14 +165,24 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
 // contiguous bytes per LDS (conflict-free).  After 8 chunks the 3-level butterfly leaves lane (g, s)
 // with pixel 4s+g; one index shuffle puts pixel L on lane L for coalesced coefficient / depth stores.
 // ------------------------------------------------------------------------------------------------
-// A stage of a warp's ring is one bulk copy of ~2 KB: CPB consecutive 4-pixel chunks.
-// Ring geometry, chosen from the sweep in profiles/r01_sweep_head_ring.md: forward 2 stages x 2 KB,
-// backward 3 stages x 4 KB (the backward also writes g_feat, so it wants more bytes in flight per warp).
+// A stage of a warp's ring is one bulk copy of 2-4 KB: CPB consecutive 4-pixel chunks.
+// Ring geometry (measured: profiles/r01_sweep_head_ring.md, profiles/experiments/README.md):
+//   forward             2 stages x 2 KB  (many resident warps: registers are the limit, a small ring keeps occupancy)
+//   forward  r = 8 with 512-byte pixels (float32, C = 128)   3 stages x 4 KB: a lane expands 64 pixels -> ~100
+//                       registers -> 16 warps per SM; with 2 x 2 KB those warps keep 2 KB each in flight, ~4 TB/s
+//                       for the whole GPU (0.755 -> 0.840 of peak; narrower pixels measured slightly worse with it)
+//   backward            3 stages x 4 KB  (it also writes g_feat, so it wants more bytes in flight per warp)
 #ifndef BTSLPG_HEAD_FWD_STAGES
 #define BTSLPG_HEAD_FWD_STAGES 2
 #endif
 #ifndef BTSLPG_HEAD_FWD_STAGE_BYTES
 #define BTSLPG_HEAD_FWD_STAGE_BYTES 2048
+#endif
+#ifndef BTSLPG_HEAD_FWD8_STAGES
+#define BTSLPG_HEAD_FWD8_STAGES 3
+#endif
+#ifndef BTSLPG_HEAD_FWD8_STAGE_BYTES
+#define BTSLPG_HEAD_FWD8_STAGE_BYTES 4096
 #endif
 #ifndef BTSLPG_HEAD_BWD_STAGES
 #define BTSLPG_HEAD_BWD_STAGES 3
@@ -180,25 +190,27 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_kernel(const __grid_constant
 #ifndef BTSLPG_HEAD_BWD_STAGE_BYTES
 #define BTSLPG_HEAD_BWD_STAGE_BYTES 4096
 #endif
-template <typename T, int M, bool FWD> struct HeadTmaCfg {
-    static constexpr int kStages = FWD ? BTSLPG_HEAD_FWD_STAGES : BTSLPG_HEAD_BWD_STAGES;
+template <typename T, int R, int M, bool FWD> struct HeadTmaCfg {
     static constexpr int kChunkPx = 4;                                        // pixels per chunk (= lane groups)
     static constexpr int kPxBytes = 32 * M * (int)sizeof(T);
+    static constexpr bool kDeepFwd = FWD && R == 8 && kPxBytes >= 512;        // float32, C = 128
+    static constexpr int kStages = !FWD ? BTSLPG_HEAD_BWD_STAGES : (kDeepFwd ? BTSLPG_HEAD_FWD8_STAGES : BTSLPG_HEAD_FWD_STAGES);
+    static constexpr int kWantBytes = !FWD ? BTSLPG_HEAD_BWD_STAGE_BYTES : (kDeepFwd ? BTSLPG_HEAD_FWD8_STAGE_BYTES : BTSLPG_HEAD_FWD_STAGE_BYTES);
     static constexpr int kChunkBytes = kChunkPx * kPxBytes;
-    static constexpr int kWant = (FWD ? BTSLPG_HEAD_FWD_STAGE_BYTES : BTSLPG_HEAD_BWD_STAGE_BYTES) / kChunkBytes;
+    static constexpr int kWant = kWantBytes / kChunkBytes;
     static constexpr int kCPB = kWant < 1 ? 1 : (kWant > 8 ? 8 : kWant);
     static constexpr int kStageBytes = kCPB * kChunkBytes;
     static constexpr int kStagesPerTile = 8 / kCPB;
 };
 
-template <typename T, int M, bool FWD> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
-    return warps * HeadTmaCfg<T, M, FWD>::kStages * (HeadTmaCfg<T, M, FWD>::kStageBytes + 8);
+template <typename T, int R, int M, bool FWD> __host__ __device__ constexpr int head_tma_smem_bytes(int warps) {
+    return warps * HeadTmaCfg<T, R, M, FWD>::kStages * (HeadTmaCfg<T, R, M, FWD>::kStageBytes + 8);
 }
 
 // Per-warp ring of bulk-copied feature stages.  Stage sq (counted per warp) holds pixels
 // [px0, px0 + 4*CPB) of tile sq / SPT; lane 0 issues, all lanes wait on the stage's mbarrier.
-template <typename T, int M, bool FWD> struct FeatRing {
-    using Cfg = HeadTmaCfg<T, M, FWD>;
+template <typename T, int R, int M, bool FWD> struct FeatRing {
+    using Cfg = HeadTmaCfg<T, R, M, FWD>;
     static constexpr int C = 32 * M;
     unsigned char *ring;
     uint64_t *bars;
@@ -253,7 +265,7 @@ template <typename T, int M, bool FWD> struct FeatRing {
 
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_constant__ HeadFwdParams<T> prm) {
-    using Cfg = HeadTmaCfg<T, M, true>;
+    using Cfg = HeadTmaCfg<T, R, M, true>;
     constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
     extern __shared__ __align__(128) unsigned char head_smem[];
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_cons
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
-    FeatRing<T, M, true> fr;
+    FeatRing<T, R, M, true> fr;
     fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, ntiles);
 
     float wk[M][4][3];
@@ -379,7 +391,7 @@ template <int C> __device__ __forceinline__ void head_reduce_partials(const floa
 // ------------------------------------------------------------------------------------------------
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_constant__ HeadBwdParams<T> prm) {
-    using Cfg = HeadTmaCfg<T, M, false>;
+    using Cfg = HeadTmaCfg<T, R, M, false>;
     constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
     constexpr int kMaxWarps = 8;
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(256) head_lpg_bwd_tma_kernel(const __grid_cons
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const bool want_gk = prm.g_kernel != nullptr, want_gf = prm.g_feat != nullptr;
     const uint32_t ntiles = warp < prm.iters ? (prm.iters - warp + nwarps - 1) / nwarps : 0;
-    FeatRing<T, M, false> fr;
+    FeatRing<T, R, M, false> fr;
     fr.init(head_smem, wid, nw, lane, prm.feat, prm.npix, warp, nwarps, want_gk ? ntiles : 0);
 
     float wk[M][4][3], dw[M][4][3];
