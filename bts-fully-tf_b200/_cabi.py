@@ -69,6 +69,8 @@ SYMBOLS = {
                                              ctypes.c_int, _TP, ctypes.c_void_p]),
     "btslpg_eval_metrics": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p, ctypes.c_size_t,
                                            ctypes.c_void_p]),
+    "btslpg_concat_forward": (ctypes.c_int, [_TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int, _TP, ctypes.c_void_p]),
+    "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, _TP, ctypes.POINTER(_TP), ctypes.c_int, ctypes.c_void_p]),
     "btslpg_launch_count": (ctypes.c_uint64, []),
     "btslpg_reset_launch_count": (None, []),
     "btslpg_last_kernel": (ctypes.c_char_p, []),

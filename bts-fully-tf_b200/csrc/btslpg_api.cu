@@ -12,6 +12,7 @@
 #include "head_kernels.cuh"
 #include "lpg_kernels.cuh"
 #include "tail_kernels.cuh"
+#include "concat_kernels.cuh"
 
 using namespace btslpg;
 
@@ -559,3 +560,4 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 
 #include "head_api.inl"
 #include "tail_api.inl"
+#include "concat_api.inl"

@@ -1,0 +1,221 @@
+// concat_kernels.cuh -- the decoder's full-resolution concat (bts_decoder.py:98-99) as ONE streaming pass (sm_100a):
+//
+//     upconv1 = Conv2D(F/16, 3, activation='elu')(upsample1)                              # :98  (the activation)
+//     concat1 = Concatenate(axis=3)([upconv1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled])   # :99
+//
+// the reference re-copies every input of the concat, after a separate ELU pass over
+// the (B,H,W,F/16) conv output.  Here the raw conv output is read once, ELU applied in registers, and the
+// F/16 + 3 channel NHWC pixel written once -- with the three LPG planes landing in their channel slots
+// (order is load-bearing).  The same kernel covers the conv_block concat [upconv, skip, lpg_ds]
+// (bts_decoder.py:42) with activation off.  Backward: d concat -> d conv output (times ELU', taken from
+// the saved concat output: y > 0 ? 1 : y + 1), d skip, d planes, again one pass.
+//
+// Layout problem and answer: an output pixel is CT = CA + CB + NP elements (35 floats = 140 bytes), so
+// pixel starts are not 16-byte aligned and neither source maps to the destination with a fixed vector
+// shift.  A CTA therefore stages a run of P consecutive pixels in shared memory as the final [P][CT]
+// image -- sources are read with flat, aligned 16-byte loads and scattered into it (row stride CT:
+// odd strides are bank-conflict-free) -- and then streams the image out with flat, aligned 16-byte
+// stores (P is a multiple of 8, so P*CT elements start and end on 16-byte boundaries for both dtypes).
+// Algorithmic bytes per pixel: (CA + CB + NP) read + CT written = 2 * CT elements forward;
+// backward reads CT (gradient) + CT (saved output, only when the activation is on) and writes CT.
+#pragma once
+
+#include "common.cuh"
+
+namespace btslpg {
+
+constexpr int kConcatThreads = 256;
+constexpr int kConcatMaxPlanes = 3;
+constexpr int kConcatSmemBytes = 24 * 1024;       // per staged image (the backward stages two: 48 KB, no opt-in needed); P is derived from it
+
+template <typename T> struct ConcatParams {
+    const T *a;                         // (npix, CA) dense source, activation applied when act != 0
+    const T *b;                         // (npix, CB) dense source or NULL
+    const T *plane[kConcatMaxPlanes];   // (npix) single-channel sources
+    T *out;                             // (npix, CT)
+    // backward (same geometry): g_out -> g_a, g_b, g_plane; y = saved forward output (needed when act != 0)
+    const T *g_out;
+    const T *y;
+    T *g_a;
+    T *g_b;
+    T *g_plane[kConcatMaxPlanes];
+    uint64_t npix;
+    uint32_t ca, cb, np, ct;
+    uint32_t tile_px;                   // P: pixels per CTA iteration (multiple of 8)
+    FastDiv div_ca, div_cb;
+    int act;                            // 1: ELU(alpha = 1) on source a (Keras activation='elu')
+    int vec;                            // CA and CB are multiples of the 16-byte vector width: dense sources use vector accesses
+};
+
+// Keras / TF elu: x > 0 ? x : expm1(x).  expm1 for x <= 0 in ~12 branch-free instructions instead of libm's
+// ~25 (the pass is 8 bytes per element: every instruction counts): the Taylor series through x^7 on
+// [-ln2/2, 0] (truncation < 2e-8 relative) and exp(x) - 1 from MUFU.EX2 below it (result <= -0.29, so the
+// SFU's ~1e-7 absolute error is <= 4e-7 relative).  x -> -inf gives -1, NaN propagates.
+__device__ __forceinline__ float expm1_nonpos(float x) {
+    float p = fmaf(x, 1.0f / 5040.0f, 1.0f / 720.0f);
+    p = fmaf(p, x, 1.0f / 120.0f);
+    p = fmaf(p, x, 1.0f / 24.0f);
+    p = fmaf(p, x, 1.0f / 6.0f);
+    p = fmaf(p, x, 0.5f);
+    p = fmaf(p, x, 1.0f);
+    p = p * x;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.442695040888963407f));
+    return x < -0.34657359f ? e - 1.0f : p;
+}
+__device__ __forceinline__ float elu_fwd(float x) { return x > 0.0f ? x : expm1_nonpos(x); }
+// derivative from the OUTPUT y = elu(x): 1 for y > 0, exp(x) = y + 1 otherwise
+__device__ __forceinline__ float elu_grad_from_output(float y) { return y > 0.0f ? 1.0f : y + 1.0f; }
+
+template <typename T> __device__ __forceinline__ float smem_get(const T *s, uint32_t i);
+template <> __device__ __forceinline__ float smem_get<float>(const float *s, uint32_t i) { return s[i]; }
+template <> __device__ __forceinline__ float smem_get<__nv_bfloat16>(const __nv_bfloat16 *s, uint32_t i) { return __bfloat162float(s[i]); }
+template <typename T> __device__ __forceinline__ void smem_put(T *s, uint32_t i, float v);
+template <> __device__ __forceinline__ void smem_put<float>(float *s, uint32_t i, float v) { s[i] = v; }
+template <> __device__ __forceinline__ void smem_put<__nv_bfloat16>(__nv_bfloat16 *s, uint32_t i, float v) { s[i] = __float2bfloat16_rn(v); }
+
+// flat copy global -> shared of n elements (n and both addresses 16-byte granular)
+template <typename T> __device__ __forceinline__ void flat_g2s(const T *g, T *s, uint32_t n) {
+    constexpr int V = 16 / (int)sizeof(T);
+    for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+        uint32_t w[4];
+        ldg_nc<4>(g + i, w);
+        *reinterpret_cast<uint4 *>(s + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+template <typename T> __device__ __forceinline__ void flat_s2g(const T *s, T *g, uint32_t n) {
+    constexpr int V = 16 / (int)sizeof(T);
+    for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(s + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        stg<4>(g + i, w);
+    }
+}
+
+// scatter a dense source tile (npx pixels x C channels, contiguous) into image rows at channel offset c0
+template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(const T *src, T *img, uint32_t npx, uint32_t C, const FastDiv &divC,
+                                                                              uint32_t ct, uint32_t c0) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const uint32_t n = npx * C;
+    for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+        float v[V];
+        load_elems<T, V, 4>(src + i, v);
+        uint32_t p, c;
+        divC.divmod(i, p, c);                          // C is a multiple of V: the V elements belong to one pixel
+#pragma unroll
+        for (int e = 0; e < V; ++e) smem_put<T>(img, p * ct + c0 + c + e, ACT ? elu_fwd(v[e]) : v[e]);
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_fwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char concat_smem[];
+    T *img = reinterpret_cast<T *>(concat_smem);
+    const uint32_t P = prm.tile_px, ct = prm.ct;
+    const uint64_t ntiles = (prm.npix + P - 1) / P;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t p0 = t * P;
+        const uint32_t npx = (uint32_t)min((uint64_t)P, prm.npix - p0);
+        const bool full_out = (npx % 8) == 0;          // vector paths need 16-byte granular runs
+        const bool full = full_out && prm.vec;
+        if (full) {
+            if (prm.act) scatter_dense<T, true>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0);
+            else scatter_dense<T, false>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0);
+            if (prm.b) scatter_dense<T, false>(prm.b + p0 * prm.cb, img, npx, prm.cb, prm.div_cb, ct, prm.ca);
+        } else {
+            for (uint32_t i = threadIdx.x; i < npx * prm.ca; i += kConcatThreads) {
+                uint32_t p, c;
+                prm.div_ca.divmod(i, p, c);
+                const float v = load1(prm.a + p0 * prm.ca + i);
+                smem_put<T>(img, p * ct + c, prm.act ? elu_fwd(v) : v);
+            }
+            if (prm.b)
+                for (uint32_t i = threadIdx.x; i < npx * prm.cb; i += kConcatThreads) {
+                    uint32_t p, c;
+                    prm.div_cb.divmod(i, p, c);
+                    smem_put<T>(img, p * ct + prm.ca + c, load1(prm.b + p0 * prm.cb + i));
+                }
+        }
+        for (uint32_t k = 0; k < prm.np; ++k)
+            for (uint32_t p = threadIdx.x; p < npx; p += kConcatThreads) smem_put<T>(img, p * ct + prm.ca + prm.cb + k, load1(prm.plane[k] + p0 + p));
+        __syncthreads();
+        if (full_out) {
+            flat_s2g<T>(img, prm.out + p0 * ct, npx * ct);
+        } else {
+            for (uint32_t i = threadIdx.x; i < npx * ct; i += kConcatThreads) prm.out[p0 * ct + i] = img[i];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_bwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char concat_smem[];
+    const uint32_t P = prm.tile_px, ct = prm.ct;
+    T *gimg = reinterpret_cast<T *>(concat_smem);
+    T *yimg = gimg + (size_t)P * ct;                    // only used when the activation is on
+    constexpr int V = 16 / (int)sizeof(T);
+    const uint64_t ntiles = (prm.npix + P - 1) / P;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t p0 = t * P;
+        const uint32_t npx = (uint32_t)min((uint64_t)P, prm.npix - p0);
+        const bool full_in = (npx % 8) == 0;
+        const bool full = full_in && prm.vec;
+        if (full_in) {
+            flat_g2s<T>(prm.g_out + p0 * ct, gimg, npx * ct);
+            if (prm.act) flat_g2s<T>(prm.y + p0 * ct, yimg, npx * ct);
+        } else {
+            for (uint32_t i = threadIdx.x; i < npx * ct; i += kConcatThreads) {
+                gimg[i] = prm.g_out[p0 * ct + i];
+                if (prm.act) yimg[i] = prm.y[p0 * ct + i];
+            }
+        }
+        __syncthreads();
+        if (prm.g_a) {
+            if (full) {
+                const uint32_t n = npx * prm.ca;
+                for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+                    uint32_t p, c;
+                    prm.div_ca.divmod(i, p, c);
+                    float v[V];
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const float g = smem_get<T>(gimg, p * ct + c + e);
+                        v[e] = prm.act ? g * elu_grad_from_output(smem_get<T>(yimg, p * ct + c + e)) : g;
+                    }
+                    store_elems<T, V, 4>(prm.g_a + p0 * prm.ca + i, v);
+                }
+            } else {
+                for (uint32_t i = threadIdx.x; i < npx * prm.ca; i += kConcatThreads) {
+                    uint32_t p, c;
+                    prm.div_ca.divmod(i, p, c);
+                    const float g = smem_get<T>(gimg, p * ct + c);
+                    store1(prm.g_a + p0 * prm.ca + i, prm.act ? g * elu_grad_from_output(smem_get<T>(yimg, p * ct + c)) : g);
+                }
+            }
+        }
+        if (prm.g_b) {
+            if (full) {
+                const uint32_t n = npx * prm.cb;
+                for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+                    uint32_t p, c;
+                    prm.div_cb.divmod(i, p, c);
+                    float v[V];
+#pragma unroll
+                    for (int e = 0; e < V; ++e) v[e] = smem_get<T>(gimg, p * ct + prm.ca + c + e);
+                    store_elems<T, V, 4>(prm.g_b + p0 * prm.cb + i, v);
+                }
+            } else {
+                for (uint32_t i = threadIdx.x; i < npx * prm.cb; i += kConcatThreads) {
+                    uint32_t p, c;
+                    prm.div_cb.divmod(i, p, c);
+                    store1(prm.g_b + p0 * prm.cb + i, smem_get<T>(gimg, p * ct + prm.ca + c));
+                }
+            }
+        }
+        for (uint32_t k = 0; k < prm.np; ++k)
+            if (prm.g_plane[k])
+                for (uint32_t p = threadIdx.x; p < npx; p += kConcatThreads) store1(prm.g_plane[k] + p0 + p, smem_get<T>(gimg, p * ct + prm.ca + prm.cb + k));
+        __syncthreads();
+    }
+}
+
+}  // namespace btslpg

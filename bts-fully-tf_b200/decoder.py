@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .layers import ReductionLPG
 
 BN_EPS = 1.1e-5          # bts_decoder.py:27
@@ -166,8 +167,11 @@ class BtsDecoder(nn.Module):
         iconv2 = self.block2(iconv3, s2, _to_nchw(d4_ds))
         red2, d2 = self.reduction_2x2(_nhwc_view(iconv2.contiguous(memory_format=torch.channels_last)))
 
-        up1 = F.elu(self.upconv1(F.interpolate(iconv2, scale_factor=2, mode="nearest")))
-        concat1 = torch.cat([up1, _to_nchw(d2), _to_nchw(d4), _to_nchw(d8)], 1)        # bts_decoder.py:99
+        # bts_decoder.py:98-99: upconv1's ELU and concat1 = [upconv1, d2, d4, d8] as ONE pass (ops.concat_nhwc):
+        # the raw conv output is read once and the F/16+3 channel NHWC pixel written once, LPG planes in their slots
+        up1_raw = self.upconv1(F.interpolate(iconv2, scale_factor=2, mode="nearest"))
+        up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
+        concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True))
         iconv1 = F.elu(self.iconv1(concat1))
         logit = self.depth_conv(iconv1)                                                # (B,1,H,W): same memory as NHWC (B,H,W,1)
         self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,

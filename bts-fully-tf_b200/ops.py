@@ -10,6 +10,7 @@ Reference lines replaced:
   lpg_forward_multi / lpg_backward_multi   the three layers of one decoder in one launch
   depth_silog / si_log_loss      bts_decoder.py:102-103 + bts.py:27-41
   eval_metrics                   custom_eval_metrics.py:24-88
+  concat_nhwc                    bts_decoder.py:98-99 (ELU of upconv1 + concat1) and :42
 """
 import ctypes
 
@@ -351,6 +352,74 @@ def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, out=None, works
     check(lib.btslpg_eval_metrics(rt.ptr, rp.ptr, float(min_depth_eval), float(max_depth_eval), ro.ptr,
                                   ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), current_stream_ptr(y_true.device)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# fused activation + NHWC concat (concat1, conv_block concat)
+# ---------------------------------------------------------------------------------------------
+def _tensor_ptr_array(refs):
+    arr = (_cabi._TP * max(len(refs), 1))()
+    for k, r in enumerate(refs):
+        arr[k] = r.ptr if r is not None else None
+    return arr
+
+
+def concat_forward(a, planes=(), b=None, act=False, out=None):
+    """out[..., :CA] = elu(a) if act else a ; out[..., CA:CA+CB] = b ; then one channel per plane.  One kernel."""
+    lib = load()
+    B, H, W, ca = a.shape
+    cb = b.shape[-1] if b is not None else 0
+    if out is None:
+        out = torch.empty((B, H, W, ca + cb + len(planes)), dtype=a.dtype, device=a.device)
+    ra, rb, ro = as_ref(a), as_ref(b), as_ref(out)
+    rp = [as_ref(p) for p in planes]
+    check(lib.btslpg_concat_forward(ra.ptr, 1 if act else 0, ptr_or_null(rb), _tensor_ptr_array(rp), len(rp), ro.ptr,
+                                    current_stream_ptr(a.device)))
+    return out
+
+
+def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=None):
+    """Split d concat into (g_a [* elu'(y)], g_b, [g_plane ...]); entries not needed come back as None."""
+    lib = load()
+    B, H, W, _ = g_out.shape
+    need_planes = [True] * n_planes if need_planes is None else list(need_planes)
+    g_a = torch.empty((B, H, W, ca), dtype=g_out.dtype, device=g_out.device)
+    g_b = torch.empty((B, H, W, cb), dtype=g_out.dtype, device=g_out.device) if (cb and need_b) else None
+    g_p = [torch.empty((B, H, W, 1), dtype=g_out.dtype, device=g_out.device) if need_planes[k] else None for k in range(n_planes)]
+    if cb and not need_b:
+        raise ValueError("concat_backward: the kernel needs g_b's geometry; pass need_b=True when CB > 0")
+    rg, ry, ra, rb = as_ref(g_out), as_ref(y if act else None), as_ref(g_a), as_ref(g_b)
+    rp = [as_ref(p) for p in g_p]
+    check(lib.btslpg_concat_backward(rg.ptr, ptr_or_null(ry), 1 if act else 0, ra.ptr, ptr_or_null(rb), _tensor_ptr_array(rp), n_planes,
+                                     current_stream_ptr(g_out.device)))
+    return g_a, g_b, g_p
+
+
+class ConcatFunction(torch.autograd.Function):
+    """(a, b-or-None, planes...) -> NHWC concat with the activation of `a` fused."""
+
+    @staticmethod
+    def forward(ctx, a, b, act, *planes):
+        a_c = a.contiguous()
+        b_c = b.contiguous() if b is not None else None
+        out = concat_forward(a_c, [p.contiguous() for p in planes], b_c, act)
+        ctx.act, ctx.ca, ctx.cb, ctx.np = act, a_c.shape[-1], (b_c.shape[-1] if b_c is not None else 0), len(planes)
+        if act:
+            ctx.save_for_backward(out)          # elu' is taken from the output: nothing else is kept alive
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        y = ctx.saved_tensors[0] if ctx.act else None
+        need_planes = [ctx.needs_input_grad[3 + k] for k in range(ctx.np)]
+        g_a, g_b, g_p = concat_backward(g_out.contiguous(), y, ctx.act, ctx.ca, ctx.cb, ctx.np, need_b=True, need_planes=need_planes)
+        return (g_a, g_b, None) + tuple(g_p)
+
+
+def concat_nhwc(a, planes=(), b=None, act=False):
+    """Fused `Concatenate(axis=3)([act(a), b, *planes])` with autograd (bts_decoder.py:98-99, :42)."""
+    return ConcatFunction.apply(a, b, bool(act), *planes)
 
 
 def launch_count():

@@ -205,6 +205,28 @@ BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_p
                                    size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused activation + channel concat of NHWC tensors -- replaces bts_decoder.py:98-99
+ *     upconv1 = Conv2D(..., activation='elu')(upsample1)        (the activation: pass the conv's linear output as `a`)
+ *     concat1 = Concatenate(axis=3)([upconv1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled])
+ * and, with act = 0, the conv_block concat [upconv, skip, lpg_ds] of bts_decoder.py:42 -- one pass
+ * instead of a separate ELU pass plus a re-copy of every input.  Channel order = argument order.
+ *   a       (B,H,W,CA)  dense source; act = 1 applies ELU(alpha=1) to it on the way (0 = identity)
+ *   b       (B,H,W,CB)  second dense source, nullable
+ *   planes  n_planes (<= 3) single-channel maps (B,H,W[,1]), e.g. the LPG outputs
+ *   out     (B,H,W,CA+CB+n_planes)
+ * All tensors contiguous, 16-byte aligned, one dtype (float32 / bfloat16).  CA, CB multiples of 4 (8 for
+ * bfloat16) take the vectorised path; other channel counts are accepted and run with scalar accesses.
+ *
+ * Backward (TF autodiff of the above): g_a = g_out[..., :CA] * elu'(.) with elu' taken from the saved
+ * output y (required iff act = 1: y > 0 ? 1 : y + 1), g_b and g_planes[k] are slices of g_out.
+ * g_b / g_planes[k] may be NULL to skip them.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *b, const BtsTensor *const *planes,
+                                     int n_planes, BtsTensor *out, void *stream);
+BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, BtsTensor *g_b,
+                                      BtsTensor *const *g_planes, int n_planes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").

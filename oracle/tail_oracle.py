@@ -76,3 +76,24 @@ def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, dtype=np.float6
         "n_valid": gt.size,
     }
     return out
+
+
+def concat_elu(a, planes=(), b=None, act=False, dtype=np.float64):
+    """bts_decoder.py:98-99 (activation='elu' of upconv1, then Concatenate(axis=3)) and :42 (act=False):
+    channel order = [a, b, *planes].  Keras elu: x > 0 ? x : exp(x) - 1."""
+    a = np.asarray(a, dtype)
+    parts = [np.where(a > 0, a, np.expm1(np.minimum(a, 0))) if act else a]
+    if b is not None:
+        parts.append(np.asarray(b, dtype))
+    parts += [np.asarray(p, dtype).reshape(a.shape[:3] + (1,)) for p in planes]
+    return np.concatenate(parts, axis=3)
+
+
+def concat_elu_grad(g_out, a, ca, cb, n_planes, act=False):
+    """Gradients of concat_elu with respect to (a, b, planes) for upstream g_out (float64)."""
+    g = np.asarray(g_out, np.float64)
+    a = np.asarray(a, np.float64)
+    g_a = g[..., :ca] * (np.where(a > 0, 1.0, np.exp(np.minimum(a, 0))) if act else 1.0)
+    g_b = g[..., ca:ca + cb] if cb else None
+    g_p = [g[..., ca + cb + k:ca + cb + k + 1] for k in range(n_planes)]
+    return g_a, g_b, g_p

@@ -170,3 +170,28 @@ def test_tail_guard_bands(n, dtype):
     assert int(m[9]) == ref_m["n_valid"]
     if ref_m["n_valid"]:
         np.testing.assert_allclose(float(m[3]), ref_m["rmse"], rtol=2e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", [True, False])
+@pytest.mark.parametrize("B,H,W,ca,cb,n_planes", [(1, 1, 1, 8, 0, 3), (1, 3, 5, 32, 0, 3), (2, 7, 9, 16, 24, 1), (1, 13, 31, 32, 0, 3)])
+def test_concat_guard_bands(B, H, W, ca, cb, n_planes, act, dtype):
+    g = torch.Generator().manual_seed(ca + W)
+    a = (torch.randn(B, H, W, ca, generator=g) * 2).to(dtype)
+    b = torch.randn(B, H, W, cb, generator=g).to(dtype) if cb else None
+    planes = [torch.randn(B, H, W, 1, generator=g).to(dtype) for _ in range(n_planes)]
+    g_out = torch.randn(B, H, W, ca + cb + n_planes, generator=g).to(dtype)
+    A = Arena()
+    out = A.output((B, H, W, ca + cb + n_planes), dtype)
+    ops.concat_forward(A.input(a), [A.input(p) for p in planes], A.input(b) if cb else None, act, out=out)
+    A.check()
+    ref = tail_oracle.concat_elu(npf(a), [npf(p) for p in planes], None if b is None else npf(b), act)
+    tol = 1e-6 if dtype == torch.float32 else 2 ** -8
+    np.testing.assert_allclose(npf(out), ref, rtol=tol, atol=tol * 1e-2)
+    B2 = Arena()
+    g_a, g_b, g_p = ops.concat_backward(B2.input(g_out), B2.input(out) if act else None, act, ca, cb, n_planes)
+    B2.check()
+    ga, gb, gp = tail_oracle.concat_elu_grad(npf(g_out), npf(a), ca, cb, n_planes, act)
+    assert np.abs(npf(g_a) - ga).max() <= (2e-6 if dtype == torch.float32 else 2 ** -6) * max(np.abs(ga).max(), 1e-30)
+    for k in range(n_planes):
+        np.testing.assert_array_equal(npf(g_p[k]), gp[k])

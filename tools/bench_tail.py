@@ -105,6 +105,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain launches (for ncu)")
     ap.add_argument("--skip-literal", action="store_true")
+    ap.add_argument("--skip-concat", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     dtype = torch.float32 if a.dtype == "f32" else torch.bfloat16
@@ -143,6 +144,38 @@ def main():
         nbytes = maps * n * es
         res[name] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
                      "kernel": ops.last_kernel()}
+    # fused ELU + concat1 (bts_decoder.py:98-99): [upconv1 (32 ch), d2, d4, d8] -> 35 channels
+    if not a.skip_concat:
+        ca, npl, nset_c = 32, 3, 2
+        csets = []
+        for _ in range(nset_c):
+            csets.append(dict(a=torch.randn(a.batch, a.height, a.width, ca, generator=g, device=dev).to(dtype),
+                              planes=[torch.randn(shape, generator=g, device=dev).to(dtype) for _ in range(npl)],
+                              out=torch.empty(a.batch, a.height, a.width, ca + npl, device=dev, dtype=dtype)))
+        g_cat = torch.randn(a.batch, a.height, a.width, ca + npl, generator=g, device=dev).to(dtype)
+
+        def cfwd(i):
+            s = csets[i]
+            ops.concat_forward(s["a"], s["planes"], act=True, out=s["out"])
+        us = time_gpu(cfwd, nset_c, max(8, a.steps // 4), 2, graph=not a.no_graph)
+        nbytes = (ca + npl + ca + npl) * n * es
+        res["concat1_fwd"] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
+                              "kernel": ops.last_kernel()}
+        # the backward allocates its outputs: time it with plain launches (1.4 ms kernels: launch overhead is < 1 %)
+        us = time_gpu(lambda i: ops.concat_backward(g_cat, csets[i]["out"], True, ca, 0, npl), nset_c, max(8, a.steps // 8), 2, graph=False)
+        nbytes = (2 * (ca + npl) + ca + npl) * n * es
+        res["concat1_bwd"] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
+                              "kernel": ops.last_kernel()}
+        if a.dtype == "f32" and not a.skip_literal:
+            def lit(i):
+                x = csets[i]["a"].detach().requires_grad_(True)
+                y = torch.cat([torch.nn.functional.elu(x)] + csets[i]["planes"], 3)
+                y.backward(g_cat)
+            us_l = time_gpu(lit, nset_c, 6, 2, graph=False)
+            res["concat1_torch_gpu_literal_fwd_bwd_us"] = round(us_l, 1)
+            res["concat1_speedup"] = round(us_l / (res["concat1_fwd"]["us"] + res["concat1_bwd"]["us"]), 2)
+        del csets, g_cat
+        torch.cuda.empty_cache()
     launches = ops.launch_count()
 
     # the same work as torch ops on the GPU (a port without custom kernels)
