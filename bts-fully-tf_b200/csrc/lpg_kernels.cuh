@@ -407,11 +407,28 @@ __device__ __forceinline__ void lpg_fwd_compute(const LpgFwdParams<T> &prm, uint
     lpg_expand_store<T, R, PX, ROWS, D, SUB>(n1, n2, n3, n4, orow, prm.out_sH, drow, prm.ds_sH);
 }
 
+// One wave ahead: the forward is store-dominated, and what a CTA waits for at its start is the DRAM latency of
+// its few coefficient bytes (ncu: long_scoreboard is the top stall).  Every fourth lane asks L2 for the line
+// that the thread `PF` slots further on will read -- roughly the CTAs that become resident when the current
+// ones retire -- so that their first loads are L2 hits.  No registers, no dependency, a handful of instructions.
+#ifndef BTSLPG_FWD_PF_CTAS
+#define BTSLPG_FWD_PF_CTAS 2368          // 16 resident CTAs x 148 SMs; 0 disables the prefetch
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <typename T, int R, int PX, int ROWS, int D>
 __device__ __forceinline__ void lpg_fwd_thread(const LpgFwdParams<T> &prm, uint32_t slot) {
     constexpr int LPP = Split<R, ROWS>::LPP;
     uint32_t group;
     int sub;
+    if constexpr (BTSLPG_FWD_PF_CTAS > 0) {
+        if ((threadIdx.x & 3) == 0) {
+            uint32_t g2;
+            int s2;
+            slot_to_group<LPP>(slot + BTSLPG_FWD_PF_CTAS * 128u, g2, s2);
+            if (g2 < prm.groups && s2 == 0) prefetch_l2(prm.coef + (size_t)g2 * (PX * 3));
+        }
+    }
     slot_to_group<LPP>(slot, group, sub);
     if (group >= prm.groups) return;
     float c[PX * 3];
