@@ -100,3 +100,135 @@ if HAVE_TF:  # pragma: no cover
             base_config = super().get_config()
             config = {"upratio": self.upratio}
             return dict(list(base_config.items()) + list(config.items()))
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder tail and concat (INTEGRATION.md sections 3a, 3b): same C ABI, TF-allocated buffers
+# ---------------------------------------------------------------------------------------------
+GT_TH = {"nyu": 0.1, "kitti": 1.0, "matterport": 0.1}      # bts.py:28
+
+
+def _ref(t):  # pragma: no cover
+    return _cabi.from_dlpack_capsule(_capsule(t)) if t is not None else None
+
+
+def _tail_workspace(device):  # pragma: no cover
+    with tf.device(device):
+        return tf.zeros([int(_cabi.load().btslpg_tail_workspace_bytes())], tf.uint8)
+
+
+def si_log_loss_wrapper(dataset):  # pragma: no cover
+    """Drop-in for reference bts.py:27-41: same name, argument and assertion; one kernel forward, one backward."""
+    _require_tf()
+    assert dataset in GT_TH
+
+    @tf.custom_gradient
+    def si_log_loss(y_true, y_pred):
+        lib = _cabi.load()
+        state = {}
+
+        def fwd(yt, yp):
+            ws = _tail_workspace(yp.device)
+            with tf.device(yp.device):
+                loss = tf.zeros([1], tf.float32)
+            state["ws"] = ws
+            rt, rp, rl, rw = _ref(yt), _ref(yp), _ref(loss), _ref(ws)
+            _cabi.check(lib.btslpg_silog_forward(None, rt.ptr, 1.0, GT_TH[dataset], rp.ptr, rl.ptr,
+                                                 ctypes.c_void_p(rw.struct.data), int(ws.shape[0]), ctypes.c_void_p(0)))
+            return loss[0]
+
+        loss = tf.py_function(fwd, [y_true, y_pred], tf.float32)
+        loss.set_shape([])
+
+        def grad(g_loss):
+            def bwd(yt, yp, gl):
+                with tf.device(yp.device):
+                    g = tf.zeros(yp.shape, yp.dtype)
+                    gl1 = tf.reshape(tf.cast(gl, tf.float32), [1])
+                ws = state["ws"]
+                rt, rp, rg, rgl, rw = _ref(yt), _ref(yp), _ref(g), _ref(gl1), _ref(ws)
+                _cabi.check(lib.btslpg_silog_backward(rp.ptr, rt.ptr, 1.0, GT_TH[dataset], rgl.ptr, ctypes.c_void_p(rw.struct.data),
+                                                      int(ws.shape[0]), 0, rg.ptr, ctypes.c_void_p(0)))
+                return g
+            g = tf.py_function(bwd, [y_true, y_pred, g_loss], y_pred.dtype)
+            g.set_shape(y_pred.shape)
+            return None, g
+
+        return loss, grad
+
+    return si_log_loss
+
+
+def metrics_list_factory(args):  # pragma: no cover
+    """Drop-in for reference custom_eval_metrics.py:21-88: nine named callables, ONE fused pass per (y_true, y_pred)."""
+    _require_tf()
+    names = ("silog", "abs_rel", "log10", "rmse", "sq_rel", "rmse_log", "d1", "d2", "d3")
+    cache = {}
+
+    def all_metrics(y_true, y_pred):
+        key = (id(y_true), id(y_pred))
+        if key not in cache:
+            cache.clear()
+
+            def run(yt, yp):
+                lib = _cabi.load()
+                ws = _tail_workspace(yp.device)
+                with tf.device(yp.device):
+                    out = tf.zeros([10], tf.float32)
+                rt, rp, ro, rw = _ref(yt), _ref(yp), _ref(out), _ref(ws)
+                _cabi.check(lib.btslpg_eval_metrics(rt.ptr, rp.ptr, float(args.min_depth_eval), float(args.max_depth_eval), ro.ptr,
+                                                    ctypes.c_void_p(rw.struct.data), int(ws.shape[0]), ctypes.c_void_p(0)))
+                return out
+            v = tf.py_function(run, [y_true, y_pred], tf.float32)
+            v.set_shape([10])
+            cache[key] = v
+        return cache[key]
+
+    def make(i, name):
+        def metric(y_true, y_pred):
+            return all_metrics(y_true, y_pred)[i]
+        metric.__name__ = name
+        return metric
+
+    return [make(i, n) for i, n in enumerate(names)]
+
+
+def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
+    """bts_decoder.py:98-99 fused: ELU of upconv1 (built with activation=None) + Concatenate([upconv1, d2, d4, d8])."""
+    _require_tf()
+
+    @tf.custom_gradient
+    def op(a, p0, p1, p2):
+        lib = _cabi.load()
+
+        def fwd(a_, p0_, p1_, p2_):
+            with tf.device(a_.device):
+                out = tf.zeros(a_.shape[:3] + [a_.shape[3] + 3], a_.dtype)
+            ra, ro = _ref(a_), _ref(out)
+            rp = [_ref(t) for t in (p0_, p1_, p2_)]
+            arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
+            _cabi.check(lib.btslpg_concat_forward(ra.ptr, 1, None, arr, 3, ro.ptr, ctypes.c_void_p(0)))
+            return out
+
+        y = tf.py_function(fwd, [a, p0, p1, p2], a.dtype)
+        y.set_shape(a.shape[:3] + [a.shape[3] + 3])
+
+        def grad(g_out):
+            def bwd(g_, y_):
+                with tf.device(g_.device):
+                    g_a = tf.zeros(a.shape, a.dtype)
+                    g_p = [tf.zeros(p0.shape, a.dtype) for _ in range(3)]
+                rg, ry, rga = _ref(g_), _ref(y_), _ref(g_a)
+                rp = [_ref(t) for t in g_p]
+                arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
+                _cabi.check(lib.btslpg_concat_backward(rg.ptr, ry.ptr, 1, rga.ptr, None, arr, 3, ctypes.c_void_p(0)))
+                return [g_a] + g_p
+            outs = tf.py_function(bwd, [g_out, y], [a.dtype] * 4)
+            outs[0].set_shape(a.shape)
+            for o in outs[1:]:
+                o.set_shape(p0.shape)
+            return tuple(outs)
+
+        return y, grad
+
+    return op(upconv1_linear, d2, d4, d8)
