@@ -15,6 +15,8 @@ Files written
   lpg_pole_r8.npz     U(0,1) coefficients that reach the theta->pi/3 pole (den <= 0)
   decoder_small.npz   bts_decoder.py:26-105 whole, num_filters=32, float64 run on
                       float32-representable inputs/weights, inference BN and training BN
+  lpg_full_size_samples.npz   the layer at FULL size (2 x 480 x 640, r = 8/4/2, seeded numpy inputs): 4096 sampled
+                      outputs per scale instead of the 2.4 MB maps (the "full-size" pin of SURVEY 8(c))
   tail_silog.npz      bts.py:27-41 si_log_loss (nyu and kitti thresholds) on depth_est =
                       sigmoid(logit)*max_depth (bts_decoder.py:102-103): loss and autograd gradients
                       with respect to depth_est and to the logit, fp32 and float64 runs
@@ -128,6 +130,30 @@ def golden_decoder():
     print("decoder_small: %d convs, depth %s" % (out["n_convs"], out["infer_depth_est"].shape))
 
 
+def full_size_inputs(r, B=2, H=480, W=640):
+    """Seeded inputs of the full-size pin (numpy Generator streams are stable across platforms)."""
+    rng = np.random.default_rng(4000 + r)
+    z = rng.standard_normal((B, H // r, W // r, 3)).astype(np.float32)
+    coef = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+    idx = np.sort(rng.choice(B * H * W, size=4096, replace=False))
+    return coef, idx
+
+
+def golden_full_size():
+    out = {}
+    for r in (8, 4, 2):
+        coef, idx = full_size_inputs(r)
+        layer = custom_layers.LocalPlanarGuidance(upratio=r)
+        y = layer(torch.from_numpy(coef)).numpy().reshape(-1)
+        y64 = custom_layers.LocalPlanarGuidance(upratio=r)(torch.from_numpy(coef).double()).numpy().reshape(-1)
+        out["r%d_idx" % r] = idx
+        out["r%d_out" % r] = y[idx]
+        out["r%d_out64" % r] = y64[idx]
+        out["r%d_n_negative" % r] = int((y64 < 0).sum())
+        print("lpg_full_size r=%d: sample mean %.6f, negatives %d" % (r, float(y64[idx].mean()), int((y64 < 0).sum())))
+    np.savez_compressed(os.path.join(HERE, "lpg_full_size_samples.npz"), **out)
+
+
 def golden_tail():
     g = torch.Generator().manual_seed(2024)
     out = {}
@@ -176,6 +202,7 @@ def golden_tail():
 
 
 if __name__ == "__main__":
+    golden_full_size()
     golden_tail()
     golden_lpg()
     golden_pole()

@@ -303,6 +303,23 @@ def test_full_size_properties(r, d):
     torch.testing.assert_close(g1[..., 2][tame], patch_sum[tame], rtol=2e-5, atol=0)
 
 
+@pytest.mark.parametrize("r,d", RS)
+def test_full_size_pin(golden_dir, r, d):
+    """Full-size run (2 x 480 x 640) against 4096 sampled outputs of the UNMODIFIED reference layer."""
+    from test_oracle import full_size_inputs
+    z = np.load(os.path.join(golden_dir, "lpg_full_size_samples.npz"))
+    coef, idx = full_size_inputs(r)
+    full, _ = ops.lpg_forward(torch.from_numpy(coef).to(DEV), r, d)
+    assert ops.last_kernel().startswith("lpg_fwd_vec<f32,r%d" % r)
+    _, den = c_oracle.lpg_forward_f64(coef, r, return_den=True)
+    good = den.reshape(-1)[idx] >= parity.DEN_OK
+    got = npf(full).reshape(-1)[idx]
+    np.testing.assert_allclose(got[good], z["r%d_out64" % r][good], rtol=1e-5)
+    np.testing.assert_allclose(got[good], z["r%d_out" % r][good], rtol=1e-5)     # the reference's own float32 run
+    assert int((full < 0).sum()) == int(z["r%d_n_negative" % r])
+    parity.check_forward(npf(full), coef, r, what="full-size pin r=%d" % r)
+
+
 # ------------------------------------------------------------------------------------------------
 # errors and edge cases through the ABI
 # ------------------------------------------------------------------------------------------------

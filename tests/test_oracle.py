@@ -163,3 +163,29 @@ def test_decoder_fixture_wiring(golden_dir):
         np.testing.assert_allclose(coef, z["infer_head%d_out" % r], rtol=1e-12)
         depth = c_oracle.lpg_forward_f64(coef, r)
         np.testing.assert_allclose(depth, z["infer_depth_%dx%d_scaled" % (r, r)][..., 0], rtol=5e-7)
+
+
+def full_size_inputs(r, B=2, H=480, W=640):
+    """Same seeded inputs as tests/golden/make_golden.py:full_size_inputs (numpy Generator streams are stable)."""
+    rng = np.random.default_rng(4000 + r)
+    z = rng.standard_normal((B, H // r, W // r, 3)).astype(np.float32)
+    coef = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+    idx = np.sort(rng.choice(B * H * W, size=4096, replace=False))
+    return coef, idx
+
+
+@pytest.mark.parametrize("r", [8, 4, 2])
+def test_full_size_pin(golden_dir, r):
+    """The layer at full size (2 x 480 x 640): the oracle against 4096 sampled outputs of the UNMODIFIED
+    reference layer (SURVEY 8(c) pin 4: a full-size fixture without committing the 2.4 MB maps)."""
+    z = np.load(os.path.join(golden_dir, "lpg_full_size_samples.npz"))
+    coef, idx = full_size_inputs(r)
+    assert np.array_equal(idx, z["r%d_idx" % r])                       # same inputs, same sample
+    out64, den = c_oracle.lpg_forward_f64(coef, r, return_den=True)
+    good = den.reshape(-1)[idx] >= 0.05
+    assert good.sum() > 4000
+    np.testing.assert_allclose(out64.reshape(-1)[idx][good], z["r%d_out64" % r][good], rtol=5e-7)
+    np.testing.assert_allclose(out64.reshape(-1)[idx][good], z["r%d_out" % r][good], rtol=3e-6)
+    out32 = c_oracle.lpg_forward_f32(coef, r)
+    np.testing.assert_allclose(out32.reshape(-1)[idx][good], z["r%d_out" % r][good], rtol=2e-6)
+    assert int((out64 < 0).sum()) == int(z["r%d_n_negative" % r])      # the pole is crossed in the same places
