@@ -13,6 +13,7 @@
 #include "lpg_kernels.cuh"
 #include "tail_kernels.cuh"
 #include "concat_kernels.cuh"
+#include "upsample_kernels.cuh"
 
 using namespace btslpg;
 
@@ -561,3 +562,4 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 #include "head_api.inl"
 #include "tail_api.inl"
 #include "concat_api.inl"
+#include "upsample_api.inl"

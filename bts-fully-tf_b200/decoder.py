@@ -38,6 +38,13 @@ def _nhwc_view(x):
     return x.permute(0, 2, 3, 1)
 
 
+def _upsample2x(x):
+    """UpSampling2D(size=2, 'nearest') (bts_decoder.py:31, :38, :97) on an NCHW / channels_last tensor through
+    the hand-written kernel (ops.upsample2x_nhwc); the result is again NCHW in channels_last memory."""
+    x_nhwc = _nhwc_view(x.contiguous(memory_format=torch.channels_last))
+    return _to_nchw(ops.upsample2x_nhwc(x_nhwc))
+
+
 def _to_nchw(x_nhwc):
     """NHWC tensor -> NCHW view in channels_last memory format (no copy when x is contiguous)."""
     return x_nhwc.permute(0, 3, 1, 2)
@@ -53,7 +60,7 @@ class _ConvBlock(nn.Module):
         self.iconv = _conv(nf + cskip + clpg, nf)
 
     def forward(self, x, skip, lpg=None):
-        up = F.interpolate(x, scale_factor=2, mode="nearest")
+        up = _upsample2x(x)
         up = self.bn(F.elu(self.upconv(up)))
         parts = [up, skip] + ([lpg] if lpg is not None else [])        # order is load-bearing (bts_decoder.py:42)
         return F.elu(self.iconv(torch.cat(parts, dim=1)))
@@ -169,7 +176,7 @@ class BtsDecoder(nn.Module):
 
         # bts_decoder.py:98-99: upconv1's ELU and concat1 = [upconv1, d2, d4, d8] as ONE pass (ops.concat_nhwc):
         # the raw conv output is read once and the F/16+3 channel NHWC pixel written once, LPG planes in their slots
-        up1_raw = self.upconv1(F.interpolate(iconv2, scale_factor=2, mode="nearest"))
+        up1_raw = self.upconv1(_upsample2x(iconv2))
         up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
         concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True))
         iconv1 = F.elu(self.iconv1(concat1))

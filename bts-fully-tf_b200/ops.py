@@ -11,6 +11,7 @@ Reference lines replaced:
   depth_silog / si_log_loss      bts_decoder.py:102-103 + bts.py:27-41
   eval_metrics                   custom_eval_metrics.py:24-88
   concat_nhwc                    bts_decoder.py:98-99 (ELU of upconv1 + concat1) and :42
+  upsample2x_nhwc                bts_decoder.py:31, :38, :97 UpSampling2D(size=2, 'nearest')
 """
 import ctypes
 
@@ -420,6 +421,46 @@ class ConcatFunction(torch.autograd.Function):
 def concat_nhwc(a, planes=(), b=None, act=False):
     """Fused `Concatenate(axis=3)([act(a), b, *planes])` with autograd (bts_decoder.py:98-99, :42)."""
     return ConcatFunction.apply(a, b, bool(act), *planes)
+
+
+# ---------------------------------------------------------------------------------------------
+# nearest x2 up-sampling (UpSampling2D in front of every upconv)
+# ---------------------------------------------------------------------------------------------
+def upsample2x_forward(x, out=None):
+    """x (B,h,w,C) NHWC contiguous -> (B,2h,2w,C), out[b,y,x] = in[b,y//2,x//2]."""
+    lib = load()
+    B, h, w, C = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * h, 2 * w, C), dtype=x.dtype, device=x.device)
+    ri, ro = as_ref(x), as_ref(out)
+    check(lib.btslpg_upsample2x_forward(ri.ptr, ro.ptr, current_stream_ptr(x.device)))
+    return out
+
+
+def upsample2x_backward(g_out, g_in=None):
+    lib = load()
+    B, H, W, C = g_out.shape
+    if g_in is None:
+        g_in = torch.empty((B, H // 2, W // 2, C), dtype=g_out.dtype, device=g_out.device)
+    rg, ri = as_ref(g_out), as_ref(g_in)
+    check(lib.btslpg_upsample2x_backward(rg.ptr, ri.ptr, current_stream_ptr(g_out.device)))
+    return g_in
+
+
+class Upsample2xFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return upsample2x_forward(x.contiguous())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        return upsample2x_backward(g_out.contiguous())
+
+
+def upsample2x_nhwc(x):
+    """`UpSampling2D(size=2, interpolation='nearest')` on an NHWC tensor, with autograd."""
+    return Upsample2xFunction.apply(x)
 
 
 def launch_count():

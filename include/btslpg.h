@@ -227,6 +227,17 @@ BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y
                                       BtsTensor *const *g_planes, int n_planes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the
+ * `layers.UpSampling2D(size=2, interpolation='nearest')` in front of every upconv of the decoder
+ * (bts_decoder.py:31, :38, :97): out[b, y, x, :] = in[b, y/2, x/2, :].
+ *   in  (B,h,w,C) ; out (B,2h,2w,C) ; contiguous, one dtype (float32 / bfloat16).  16-byte aligned tensors whose
+ *   pixels are a multiple of 16 bytes take the vectorised kernels, anything else a scalar one.
+ * Backward: g_in[b,y,x,:] = sum of the four g_out pixels it was copied to, added in a fixed order.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_upsample2x_forward(const BtsTensor *in, BtsTensor *out, void *stream);
+BTSLPG_API int btslpg_upsample2x_backward(const BtsTensor *g_out, BtsTensor *g_in, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").

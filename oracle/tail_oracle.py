@@ -97,3 +97,15 @@ def concat_elu_grad(g_out, a, ca, cb, n_planes, act=False):
     g_b = g[..., ca:ca + cb] if cb else None
     g_p = [g[..., ca + cb + k:ca + cb + k + 1] for k in range(n_planes)]
     return g_a, g_b, g_p
+
+
+def upsample2x(x):
+    """layers.UpSampling2D(size=2, interpolation='nearest') (bts_decoder.py:31, :38, :97) on NHWC:
+    out[b, y, x] = in[b, y // 2, x // 2] (Keras implements it as repeat_elements along H then W)."""
+    return np.repeat(np.repeat(np.asarray(x), 2, axis=1), 2, axis=2)
+
+
+def upsample2x_grad(g_out):
+    g = np.asarray(g_out, np.float64)
+    B, H, W, C = g.shape
+    return g.reshape(B, H // 2, 2, W // 2, 2, C).sum(axis=(2, 4))

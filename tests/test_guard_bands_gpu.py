@@ -195,3 +195,20 @@ def test_concat_guard_bands(B, H, W, ca, cb, n_planes, act, dtype):
     assert np.abs(npf(g_a) - ga).max() <= (2e-6 if dtype == torch.float32 else 2 ** -6) * max(np.abs(ga).max(), 1e-30)
     for k in range(n_planes):
         np.testing.assert_array_equal(npf(g_p[k]), gp[k])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,h,w,C", [(1, 1, 1, 4), (2, 3, 5, 64), (1, 5, 3, 6), (1, 7, 9, 136)])
+def test_upsample_guard_bands(B, h, w, C, dtype):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, h, w, C, generator=g).to(dtype)
+    A = Arena()
+    out = A.output((B, 2 * h, 2 * w, C), dtype)
+    ops.upsample2x_forward(A.input(x), out=out)
+    A.check()
+    assert np.array_equal(npf(out), tail_oracle.upsample2x(npf(x)))
+    B2 = Arena()
+    g_in = B2.output((B, h, w, C), dtype)
+    ops.upsample2x_backward(B2.input(out), g_in=g_in)
+    B2.check()
+    assert np.array_equal(npf(g_in), npf((x.float() * 4).to(dtype)))
