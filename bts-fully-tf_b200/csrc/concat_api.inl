@@ -58,11 +58,19 @@ int parse_concat(const BtsTensor *a, const BtsTensor *b, const BtsTensor *const 
     return 0;
 }
 
-template <typename T> int concat_tile_px(int64_t ct) {
+constexpr int kConcatMaxSmemBytes = 160 * 1024;
+
+// pixels per tile: as many as fit the per-image budget, at least 8 (wide concats: 896 channels -> 8 pixels = 28 KB)
+template <typename T> int concat_tile_px(int64_t ct, int images) {
     int64_t p = kConcatSmemBytes / (ct * (int64_t)sizeof(T));
     p = p / 8 * 8;
     if (p > 512) p = 512;
+    if (p < 8 && 8 * ct * (int64_t)sizeof(T) * images <= kConcatMaxSmemBytes) p = 8;     // opt-in shared memory beyond 48 KB
     return (int)p;
+}
+
+template <typename KernelT> void concat_allow_smem(KernelT kernel, int smem) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 template <typename KernelT> int concat_blocks(KernelT kernel, int smem, uint64_t ntiles) {
@@ -81,23 +89,30 @@ template <typename KernelT> int concat_blocks(KernelT kernel, int smem, uint64_t
 
 extern "C" {
 
-int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *b, const BtsTensor *const *planes, int n_planes, BtsTensor *out,
-                          void *stream) {
+int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, const BtsTensor *shift, const BtsTensor *b,
+                          const BtsTensor *const *planes, int n_planes, int pad_channels, BtsTensor *out, void *stream) {
     if (!a) return fail(BTSLPG_EINVAL, "a: tensor is NULL");
     if (act != 0 && act != 1) return fail(BTSLPG_EINVAL, "act must be 0 (none) or 1 (elu)");
+    if (pad_channels < 0 || pad_channels > 7) return fail(BTSLPG_EINVAL, "pad_channels must be in [0, 7]");
+    if ((scale == nullptr) != (shift == nullptr)) return fail(BTSLPG_EINVAL, "scale and shift must be given together");
     ConcatGeom g;
     if (int e = parse_concat(a, b, planes, n_planes, out, "a", "b", "planes", "out", g)) return e;
     for (int k = 0; k < n_planes; ++k)
         if (!planes[k]) return fail(BTSLPG_EINVAL, "planes[%d]: tensor is NULL", k);
-    const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes;
-    if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "out: last dimension must be %lld (= CA + CB + n_planes), got %lld", (long long)ct, (long long)g.out.C);
+    const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes + pad_channels;
+    if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "out: last dimension must be %lld (= CA + CB + n_planes + pad_channels), got %lld", (long long)ct, (long long)g.out.C);
+    float *scale_ptr = nullptr, *shift_ptr = nullptr;
+    if (scale) {
+        if (int e = parse_f32_vec(scale, "scale", g.a.C, g.out.dev, scale_ptr)) return e;
+        if (int e = parse_f32_vec(shift, "shift", g.a.C, g.out.dev, shift_ptr)) return e;
+    }
     if (g.npix == 0) return 0;
     DeviceGuard guard(g.out.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g.out.dev, cudaGetErrorString(guard.err));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
-        const int P = concat_tile_px<T>(ct);
+        const int P = concat_tile_px<T>(ct, 1);
         if (P < 8) return fail(BTSLPG_ESHAPE, "concat: %lld channels do not fit the staging buffer", (long long)ct);
         ConcatParams<T> p;
         memset(&p, 0, sizeof(p));
@@ -106,29 +121,33 @@ int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *b, const
         for (int k = 0; k < n_planes; ++k) p.plane[k] = reinterpret_cast<const T *>(g.plane[k].ptr);
         p.out = reinterpret_cast<T *>(g.out.ptr);
         p.npix = (uint64_t)g.npix;
-        p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.ct = (uint32_t)ct;
+        p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.pad = (uint32_t)pad_channels; p.ct = (uint32_t)ct;
+        p.scale = scale_ptr; p.shift = shift_ptr;
         p.tile_px = (uint32_t)P;
         p.div_ca = FastDiv(p.ca);
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
         p.act = act;
         p.vec = (p.ca % (16 / sizeof(T)) == 0) && (p.cb % (16 / sizeof(T)) == 0);
-        const int smem = P * (int)ct * (int)sizeof(T);
+        const int smem = (P * (int)ct * (int)sizeof(T) + 15) / 16 * 16 + (scale_ptr ? 2 * (int)p.ca * (int)sizeof(float) : 0);
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
+        concat_allow_smem(concat_fwd_kernel<T>, smem);
         concat_fwd_kernel<T><<<concat_blocks(concat_fwd_kernel<T>, smem, ntiles), kConcatThreads, smem, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "concat_fwd<%s,%s,C%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.ca, p.cb, p.np);
+        snprintf(tl_kernel, sizeof(tl_kernel), "concat_fwd<%s,%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", scale_ptr ? "+affine" : "", p.ca,
+                 p.cb, p.np, p.pad);
         return check_launch("btslpg_concat_forward");
     };
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
 }
 
 int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, BtsTensor *g_b, BtsTensor *const *g_planes,
-                           int n_planes, void *stream) {
+                           int n_planes, int pad_channels, void *stream) {
     if (!g_a) return fail(BTSLPG_EINVAL, "g_a: tensor is NULL");
     if (act != 0 && act != 1) return fail(BTSLPG_EINVAL, "act must be 0 (none) or 1 (elu)");
+    if (pad_channels < 0 || pad_channels > 7) return fail(BTSLPG_EINVAL, "pad_channels must be in [0, 7]");
     ConcatGeom g;
     if (int e = parse_concat(g_a, g_b, g_planes, n_planes, g_out, "g_a", "g_b", "g_planes", "g_out", g)) return e;
-    const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes;
-    if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "g_out: last dimension must be %lld (= CA + CB + n_planes), got %lld", (long long)ct, (long long)g.out.C);
+    const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes + pad_channels;
+    if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "g_out: last dimension must be %lld (= CA + CB + n_planes + pad_channels), got %lld", (long long)ct, (long long)g.out.C);
     View yv;
     if (act) {
         if (!y) return fail(BTSLPG_EINVAL, "y: the saved forward output is required when act != 0");
@@ -144,7 +163,7 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
-        const int P = concat_tile_px<T>(ct);
+        const int P = concat_tile_px<T>(ct, act ? 2 : 1);
         if (P < 8) return fail(BTSLPG_ESHAPE, "concat: %lld channels do not fit the staging buffer", (long long)ct);
         ConcatParams<T> p;
         memset(&p, 0, sizeof(p));
@@ -154,7 +173,7 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         p.g_b = g.has_b ? reinterpret_cast<T *>(g.b.ptr) : nullptr;
         for (int k = 0; k < n_planes; ++k) p.g_plane[k] = g_planes[k] ? reinterpret_cast<T *>(g.plane[k].ptr) : nullptr;
         p.npix = (uint64_t)g.npix;
-        p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.ct = (uint32_t)ct;
+        p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.pad = (uint32_t)pad_channels; p.ct = (uint32_t)ct;
         p.tile_px = (uint32_t)P;
         p.div_ca = FastDiv(p.ca);
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
@@ -162,8 +181,9 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         p.vec = (p.ca % (16 / sizeof(T)) == 0) && (p.cb % (16 / sizeof(T)) == 0);
         const int smem = (act ? 2 : 1) * P * (int)ct * (int)sizeof(T);
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
+        concat_allow_smem(concat_bwd_kernel<T>, smem);
         concat_bwd_kernel<T><<<concat_blocks(concat_bwd_kernel<T>, smem, ntiles), kConcatThreads, smem, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s,C%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.ca, p.cb, p.np);
+        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.ca, p.cb, p.np, p.pad);
         return check_launch("btslpg_concat_backward");
     };
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});

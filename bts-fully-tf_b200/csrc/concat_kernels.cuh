@@ -39,8 +39,12 @@ template <typename T> struct ConcatParams {
     T *g_a;
     T *g_b;
     T *g_plane[kConcatMaxPlanes];
+    // forward only, optional: per-channel affine applied to source a AFTER the activation -- an inference-mode
+    // BatchNormalization folded in: scale = gamma / sqrt(var + eps), shift = beta - mean * scale (bts_decoder.py:33-34, :41)
+    const float *scale;
+    const float *shift;
     uint64_t npix;
-    uint32_t ca, cb, np, ct;
+    uint32_t ca, cb, np, pad, ct;       // ct = ca + cb + np + pad; the pad channels are written as zeros (and ignored backward)
     uint32_t tile_px;                   // P: pixels per CTA iteration (multiple of 8)
     FastDiv div_ca, div_cb;
     int act;                            // 1: ELU(alpha = 1) on source a (Keras activation='elu')
@@ -94,7 +98,7 @@ template <typename T> __device__ __forceinline__ void flat_s2g(const T *s, T *g,
 
 // scatter a dense source tile (npx pixels x C channels, contiguous) into image rows at channel offset c0
 template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(const T *src, T *img, uint32_t npx, uint32_t C, const FastDiv &divC,
-                                                                              uint32_t ct, uint32_t c0) {
+                                                                              uint32_t ct, uint32_t c0, const float *aff = nullptr) {
     constexpr int V = 16 / (int)sizeof(T);
     const uint32_t n = npx * C;
     for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
@@ -103,7 +107,11 @@ template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(co
         uint32_t p, c;
         divC.divmod(i, p, c);                          // C is a multiple of V: the V elements belong to one pixel
 #pragma unroll
-        for (int e = 0; e < V; ++e) smem_put<T>(img, p * ct + c0 + c + e, ACT ? elu_fwd(v[e]) : v[e]);
+        for (int e = 0; e < V; ++e) {
+            float x = ACT ? elu_fwd(v[e]) : v[e];
+            if (aff) x = fmaf(x, aff[c + e], aff[C + c + e]);      // shared-memory copy of (scale, shift)
+            smem_put<T>(img, p * ct + c0 + c + e, x);
+        }
     }
 }
 
@@ -111,6 +119,16 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_f
     extern __shared__ __align__(16) unsigned char concat_smem[];
     T *img = reinterpret_cast<T *>(concat_smem);
     const uint32_t P = prm.tile_px, ct = prm.ct;
+    // (scale, shift) of the folded BatchNormalization live behind the staged image
+    float *aff = nullptr;
+    if (prm.scale) {
+        aff = reinterpret_cast<float *>(concat_smem + (((size_t)P * ct * sizeof(T) + 15) / 16) * 16);
+        for (uint32_t c = threadIdx.x; c < prm.ca; c += kConcatThreads) {
+            aff[c] = prm.scale[c];
+            aff[prm.ca + c] = prm.shift[c];
+        }
+        __syncthreads();
+    }
     const uint64_t ntiles = (prm.npix + P - 1) / P;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint64_t p0 = t * P;
@@ -118,15 +136,17 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_f
         const bool full_out = (npx % 8) == 0;          // vector paths need 16-byte granular runs
         const bool full = full_out && prm.vec;
         if (full) {
-            if (prm.act) scatter_dense<T, true>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0);
-            else scatter_dense<T, false>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0);
+            if (prm.act) scatter_dense<T, true>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0, aff);
+            else scatter_dense<T, false>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0, aff);
             if (prm.b) scatter_dense<T, false>(prm.b + p0 * prm.cb, img, npx, prm.cb, prm.div_cb, ct, prm.ca);
         } else {
             for (uint32_t i = threadIdx.x; i < npx * prm.ca; i += kConcatThreads) {
                 uint32_t p, c;
                 prm.div_ca.divmod(i, p, c);
-                const float v = load1(prm.a + p0 * prm.ca + i);
-                smem_put<T>(img, p * ct + c, prm.act ? elu_fwd(v) : v);
+                float v = load1(prm.a + p0 * prm.ca + i);
+                if (prm.act) v = elu_fwd(v);
+                if (aff) v = fmaf(v, aff[c], aff[prm.ca + c]);
+                smem_put<T>(img, p * ct + c, v);
             }
             if (prm.b)
                 for (uint32_t i = threadIdx.x; i < npx * prm.cb; i += kConcatThreads) {
@@ -137,6 +157,8 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_f
         }
         for (uint32_t k = 0; k < prm.np; ++k)
             for (uint32_t p = threadIdx.x; p < npx; p += kConcatThreads) smem_put<T>(img, p * ct + prm.ca + prm.cb + k, load1(prm.plane[k] + p0 + p));
+        for (uint32_t i = threadIdx.x; i < npx * prm.pad; i += kConcatThreads)      // zero channels that align CT (cuDNN would pad otherwise)
+            smem_put<T>(img, (i / prm.pad) * ct + prm.ca + prm.cb + prm.np + (i % prm.pad), 0.0f);
         __syncthreads();
         if (full_out) {
             flat_s2g<T>(img, prm.out + p0 * ct, npx * ct);

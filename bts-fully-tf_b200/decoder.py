@@ -50,20 +50,45 @@ def _to_nchw(x_nhwc):
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+def _conv_padded_input(conv, x_nchw, pad):
+    """conv(x) for an input that carries `pad` extra zero channels: the kernel gets matching zero input channels
+    (identical result; the gradient of the padding is dropped by autograd's slice)."""
+    w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad)) if pad else conv.weight
+    return F.conv2d(x_nchw, w, None, conv.stride, conv.padding, conv.dilation)
+
+
+def _bn_affine(bn):
+    """Inference-mode BatchNormalization as y = x * scale + shift (float32 [C] each)."""
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return scale.contiguous(), (bn.bias - bn.running_mean * scale).contiguous()
+
+
 class _ConvBlock(nn.Module):
-    """conv_block / conv_block_no_lpg (bts_decoder.py:30-44): upsample x2, 3x3 conv + ELU, BN, concat, 3x3 conv + ELU."""
+    """conv_block / conv_block_no_lpg (bts_decoder.py:30-44): upsample x2, 3x3 conv + ELU, BN, concat, 3x3 conv + ELU.
+
+    The memory-bound glue between the two convolutions runs on the hand-written kernels: the up-sampling
+    (ops.upsample2x_nhwc) and ONE pass that writes the concat [up, skip, lpg_ds] (ops.concat_*), padded with zero
+    channels to a multiple of 4 so that cuDNN does not re-copy the tensor; in inference mode that pass also applies
+    the ELU of the upconv and the folded BatchNormalization."""
 
     def __init__(self, cin, cskip, clpg, nf):
         super().__init__()
         self.upconv = _conv(cin, nf)
         self.bn = _bn(nf)
         self.iconv = _conv(nf + cskip + clpg, nf)
+        self.pad = ops.pad_to(nf + cskip + clpg)
 
-    def forward(self, x, skip, lpg=None):
-        up = _upsample2x(x)
-        up = self.bn(F.elu(self.upconv(up)))
-        parts = [up, skip] + ([lpg] if lpg is not None else [])        # order is load-bearing (bts_decoder.py:42)
-        return F.elu(self.iconv(torch.cat(parts, dim=1)))
+    def forward(self, x, skip_nhwc, lpg_nhwc=None):
+        up = self.upconv(_upsample2x(x))                                # linear output of the upconv
+        planes = [lpg_nhwc] if lpg_nhwc is not None else []            # order is load-bearing (bts_decoder.py:42)
+        if not self.training and not torch.is_grad_enabled():
+            scale, shift = _bn_affine(self.bn)
+            cat = ops.concat_forward(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, skip_nhwc.contiguous(), act=True,
+                                     pad=self.pad, scale=scale, shift=shift)
+        else:
+            up = self.bn(F.elu(up))
+            cat = ops.concat_nhwc(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, b=skip_nhwc, act=False, pad=self.pad)
+        return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
 
 
 class _DenseAspp(nn.Module):
@@ -152,7 +177,8 @@ class BtsDecoder(nn.Module):
     def forward(self, decoder_inputs, return_logit=False):
         """decoder_inputs: NHWC [dense_features, skip_2, skip_4, skip_8, skip_16] -> depth_est NHWC (B,H,W,1)
         (return_logit: the pre-activation of the last Conv2D instead, for the fused loss)."""
-        dense, s2, s4, s8, s16 = [_to_nchw(t) for t in decoder_inputs]
+        dense = _to_nchw(decoder_inputs[0])
+        s2, s4, s8, s16 = decoder_inputs[1:]                               # skips stay NHWC: the concat kernel reads them as they are
         iconv5 = self.block5(dense, s16)
         iconv4 = self.block4(iconv5, s8)
         iconv4_bn = self.bn4(iconv4)
@@ -169,17 +195,18 @@ class BtsDecoder(nn.Module):
 
         # bts_decoder.py:79-81: reduction_8x8 -> depth_8x8_scaled -> ds  (one kernel)
         red8, d8, d8_ds = self.reduction_8x8(_nhwc_view(daspp_feat.contiguous(memory_format=torch.channels_last)))
-        iconv3 = self.block3(daspp_feat, s4, _to_nchw(d8_ds))
+        iconv3 = self.block3(daspp_feat, s4, d8_ds)
         red4, d4, d4_ds = self.reduction_4x4(_nhwc_view(iconv3.contiguous(memory_format=torch.channels_last)))
-        iconv2 = self.block2(iconv3, s2, _to_nchw(d4_ds))
+        iconv2 = self.block2(iconv3, s2, d4_ds)
         red2, d2 = self.reduction_2x2(_nhwc_view(iconv2.contiguous(memory_format=torch.channels_last)))
 
         # bts_decoder.py:98-99: upconv1's ELU and concat1 = [upconv1, d2, d4, d8] as ONE pass (ops.concat_nhwc):
         # the raw conv output is read once and the F/16+3 channel NHWC pixel written once, LPG planes in their slots
         up1_raw = self.upconv1(_upsample2x(iconv2))
         up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
-        concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True))
-        iconv1 = F.elu(self.iconv1(concat1))
+        pad1 = ops.pad_to(up1_nhwc.shape[-1] + 3)                          # 35 -> 36 channels
+        concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
+        iconv1 = F.elu(_conv_padded_input(self.iconv1, concat1, pad1))
         logit = self.depth_conv(iconv1)                                                # (B,1,H,W): same memory as NHWC (B,H,W,1)
         self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
                               "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}

@@ -365,21 +365,22 @@ def _tensor_ptr_array(refs):
     return arr
 
 
-def concat_forward(a, planes=(), b=None, act=False, out=None):
-    """out[..., :CA] = elu(a) if act else a ; out[..., CA:CA+CB] = b ; then one channel per plane.  One kernel."""
+def concat_forward(a, planes=(), b=None, act=False, out=None, pad=0, scale=None, shift=None):
+    """out[..., :CA] = affine(elu(a) if act else a) ; out[..., CA:CA+CB] = b ; one channel per plane ; `pad` zero
+    channels.  affine (scale, shift: float32 [CA], optional) is an inference-mode BatchNormalization folded in.  One kernel."""
     lib = load()
     B, H, W, ca = a.shape
     cb = b.shape[-1] if b is not None else 0
     if out is None:
-        out = torch.empty((B, H, W, ca + cb + len(planes)), dtype=a.dtype, device=a.device)
-    ra, rb, ro = as_ref(a), as_ref(b), as_ref(out)
+        out = torch.empty((B, H, W, ca + cb + len(planes) + pad), dtype=a.dtype, device=a.device)
+    ra, rb, ro, rs, rt = as_ref(a), as_ref(b), as_ref(out), as_ref(scale), as_ref(shift)
     rp = [as_ref(p) for p in planes]
-    check(lib.btslpg_concat_forward(ra.ptr, 1 if act else 0, ptr_or_null(rb), _tensor_ptr_array(rp), len(rp), ro.ptr,
-                                    current_stream_ptr(a.device)))
+    check(lib.btslpg_concat_forward(ra.ptr, 1 if act else 0, ptr_or_null(rs), ptr_or_null(rt), ptr_or_null(rb), _tensor_ptr_array(rp), len(rp),
+                                    int(pad), ro.ptr, current_stream_ptr(a.device)))
     return out
 
 
-def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=None):
+def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=None, pad=0):
     """Split d concat into (g_a [* elu'(y)], g_b, [g_plane ...]); entries not needed come back as None."""
     lib = load()
     B, H, W, _ = g_out.shape
@@ -391,20 +392,20 @@ def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=No
         raise ValueError("concat_backward: the kernel needs g_b's geometry; pass need_b=True when CB > 0")
     rg, ry, ra, rb = as_ref(g_out), as_ref(y if act else None), as_ref(g_a), as_ref(g_b)
     rp = [as_ref(p) for p in g_p]
-    check(lib.btslpg_concat_backward(rg.ptr, ptr_or_null(ry), 1 if act else 0, ra.ptr, ptr_or_null(rb), _tensor_ptr_array(rp), n_planes,
+    check(lib.btslpg_concat_backward(rg.ptr, ptr_or_null(ry), 1 if act else 0, ra.ptr, ptr_or_null(rb), _tensor_ptr_array(rp), n_planes, int(pad),
                                      current_stream_ptr(g_out.device)))
     return g_a, g_b, g_p
 
 
 class ConcatFunction(torch.autograd.Function):
-    """(a, b-or-None, planes...) -> NHWC concat with the activation of `a` fused."""
+    """(a, b-or-None, planes...) -> NHWC concat with the activation of `a` fused and `pad` zero channels appended."""
 
     @staticmethod
-    def forward(ctx, a, b, act, *planes):
+    def forward(ctx, a, b, act, pad, *planes):
         a_c = a.contiguous()
         b_c = b.contiguous() if b is not None else None
-        out = concat_forward(a_c, [p.contiguous() for p in planes], b_c, act)
-        ctx.act, ctx.ca, ctx.cb, ctx.np = act, a_c.shape[-1], (b_c.shape[-1] if b_c is not None else 0), len(planes)
+        out = concat_forward(a_c, [p.contiguous() for p in planes], b_c, act, pad=pad)
+        ctx.act, ctx.pad, ctx.ca, ctx.cb, ctx.np = act, pad, a_c.shape[-1], (b_c.shape[-1] if b_c is not None else 0), len(planes)
         if act:
             ctx.save_for_backward(out)          # elu' is taken from the output: nothing else is kept alive
         return out
@@ -413,14 +414,19 @@ class ConcatFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
         y = ctx.saved_tensors[0] if ctx.act else None
-        need_planes = [ctx.needs_input_grad[3 + k] for k in range(ctx.np)]
-        g_a, g_b, g_p = concat_backward(g_out.contiguous(), y, ctx.act, ctx.ca, ctx.cb, ctx.np, need_b=True, need_planes=need_planes)
-        return (g_a, g_b, None) + tuple(g_p)
+        need_planes = [ctx.needs_input_grad[4 + k] for k in range(ctx.np)]
+        g_a, g_b, g_p = concat_backward(g_out.contiguous(), y, ctx.act, ctx.ca, ctx.cb, ctx.np, need_b=True, need_planes=need_planes, pad=ctx.pad)
+        return (g_a, g_b, None, None) + tuple(g_p)
 
 
-def concat_nhwc(a, planes=(), b=None, act=False):
-    """Fused `Concatenate(axis=3)([act(a), b, *planes])` with autograd (bts_decoder.py:98-99, :42)."""
-    return ConcatFunction.apply(a, b, bool(act), *planes)
+def concat_nhwc(a, planes=(), b=None, act=False, pad=0):
+    """Fused `Concatenate(axis=3)([act(a), b, *planes])` (+ `pad` zero channels) with autograd (bts_decoder.py:98-99, :42)."""
+    return ConcatFunction.apply(a, b, bool(act), int(pad), *planes)
+
+
+def pad_to(channels, multiple=4):
+    """Zero channels to append so that a concat is a multiple of `multiple` channels wide."""
+    return (-channels) % multiple
 
 
 # ---------------------------------------------------------------------------------------------

@@ -211,20 +211,26 @@ BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_p
  * and, with act = 0, the conv_block concat [upconv, skip, lpg_ds] of bts_decoder.py:42 -- one pass
  * instead of a separate ELU pass plus a re-copy of every input.  Channel order = argument order.
  *   a       (B,H,W,CA)  dense source; act = 1 applies ELU(alpha=1) to it on the way (0 = identity)
+ *   scale, shift  float32 [CA], nullable (together): per-channel affine on `a` AFTER the activation -- an
+ *           inference-mode BatchNormalization folded in (bts_decoder.py:33-34 / :40-41: upconv -> elu -> BN -> concat);
+ *           forward only (the backward entry point differentiates the un-affined form)
  *   b       (B,H,W,CB)  second dense source, nullable
  *   planes  n_planes (<= 3) single-channel maps (B,H,W[,1]), e.g. the LPG outputs
- *   out     (B,H,W,CA+CB+n_planes)
+ *   pad_channels  0..7 zero channels appended so that the total is a multiple of 4: the consumer convolution gets
+ *           matching zero input channels in its kernel and cuDNN skips its own padding copy of the whole tensor
+ *   out     (B,H,W,CA+CB+n_planes+pad_channels)
  * All tensors contiguous, 16-byte aligned, one dtype (float32 / bfloat16).  CA, CB multiples of 4 (8 for
  * bfloat16) take the vectorised path; other channel counts are accepted and run with scalar accesses.
  *
  * Backward (TF autodiff of the above): g_a = g_out[..., :CA] * elu'(.) with elu' taken from the saved
  * output y (required iff act = 1: y > 0 ? 1 : y + 1), g_b and g_planes[k] are slices of g_out.
- * g_b / g_planes[k] may be NULL to skip them.
+ * g_b / g_planes[k] may be NULL to skip them; the pad channels' gradient is dropped.
  * ------------------------------------------------------------------------------------------- */
-BTSLPG_API int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *b, const BtsTensor *const *planes,
-                                     int n_planes, BtsTensor *out, void *stream);
+BTSLPG_API int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, const BtsTensor *shift,
+                                     const BtsTensor *b, const BtsTensor *const *planes, int n_planes,
+                                     int pad_channels, BtsTensor *out, void *stream);
 BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, BtsTensor *g_b,
-                                      BtsTensor *const *g_planes, int n_planes, void *stream);
+                                      BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the

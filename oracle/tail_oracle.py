@@ -78,14 +78,20 @@ def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, dtype=np.float6
     return out
 
 
-def concat_elu(a, planes=(), b=None, act=False, dtype=np.float64):
+def concat_elu(a, planes=(), b=None, act=False, dtype=np.float64, pad=0, scale=None, shift=None):
     """bts_decoder.py:98-99 (activation='elu' of upconv1, then Concatenate(axis=3)) and :42 (act=False):
-    channel order = [a, b, *planes].  Keras elu: x > 0 ? x : exp(x) - 1."""
+    channel order = [a, b, *planes] (+ `pad` zero channels).  Keras elu: x > 0 ? x : exp(x) - 1.
+    scale/shift: an inference-mode BatchNormalization after the activation (bts_decoder.py:33-34, :40-41)."""
     a = np.asarray(a, dtype)
-    parts = [np.where(a > 0, a, np.expm1(np.minimum(a, 0))) if act else a]
+    first = np.where(a > 0, a, np.expm1(np.minimum(a, 0))) if act else a
+    if scale is not None:
+        first = first * np.asarray(scale, dtype) + np.asarray(shift, dtype)
+    parts = [first]
     if b is not None:
         parts.append(np.asarray(b, dtype))
     parts += [np.asarray(p, dtype).reshape(a.shape[:3] + (1,)) for p in planes]
+    if pad:
+        parts.append(np.zeros(a.shape[:3] + (pad,), dtype))
     return np.concatenate(parts, axis=3)
 
 

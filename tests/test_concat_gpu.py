@@ -71,6 +71,40 @@ def test_concat_matches_oracle_and_torch(B, H, W, ca, cb, n_planes, act, dtype):
     assert np.abs(npf(ad.grad) - npf(a2.grad)).max() <= gtol * max(np.abs(npf(a2.grad)).max(), 1e-30)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,ca,cb,n_planes,pad", [
+    (2, 16, 24, 32, 0, 3, 1),       # concat1: 35 -> 36
+    (2, 7, 9, 64, 96, 1, 3),        # block2 concat: 161 -> 164
+    (1, 6, 10, 128, 96, 1, 3),      # block3 concat: 225 -> 228
+    (1, 3, 5, 512, 384, 0, 0),      # block5 concat [up, skip]: 896 channels, 8-pixel tiles
+    (1, 5, 7, 6, 3, 2, 1),          # scalar path with padding
+])
+def test_concat_pad_and_folded_batchnorm(B, H, W, ca, cb, n_planes, pad, dtype):
+    a, b, planes, g_out = make(B, H, W, ca, cb, n_planes, seed=ca + pad, dtype=dtype)
+    g = torch.Generator().manual_seed(7)
+    scale = torch.rand(ca, generator=g) + 0.5
+    shift = torch.randn(ca, generator=g)
+    bd = b.to(DEV) if b is not None else None
+    out = ops.concat_forward(a.to(DEV), [p.to(DEV) for p in planes], bd, act=True, pad=pad, scale=scale.to(DEV), shift=shift.to(DEV))
+    assert "elu+affine" in ops.last_kernel() and ops.last_kernel().endswith("+%d>" % pad), ops.last_kernel()
+    ref = T.concat_elu(npf(a), [npf(p) for p in planes], None if b is None else npf(b), True, pad=pad, scale=scale.numpy(), shift=shift.numpy())
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7
+    np.testing.assert_allclose(npf(out), ref, rtol=tol, atol=tol)
+    if pad:
+        assert (out[..., ca + cb + n_planes:] == 0).all()
+    # autograd form with padding: the gradient of the pad channels is dropped, everything else as before
+    ad = a.to(DEV).requires_grad_(True)
+    pd = [p.to(DEV).requires_grad_(True) for p in planes]
+    out2 = ops.concat_nhwc(ad, pd, b=bd, act=True, pad=pad)
+    g_pad = torch.randn(B, H, W, ca + cb + n_planes + pad, generator=g).to(dtype)
+    out2.backward(g_pad.to(DEV))
+    ga, _, gp = T.concat_elu_grad(npf(g_pad), npf(a), ca, cb, n_planes, True)
+    gtol = 2e-6 if dtype == torch.float32 else 2 ** -6
+    assert np.abs(npf(ad.grad) - ga).max() <= gtol * max(np.abs(ga).max(), 1e-30)
+    for k in range(n_planes):
+        np.testing.assert_array_equal(npf(pd[k].grad), gp[k])
+
+
 def test_concat_full_size_properties():
     """B=8 480x640 (1/4 of BASELINE config 2): channel-slot identities at a size the CPU oracle does not need to see."""
     B, H, W, ca = 8, 480, 640, 32

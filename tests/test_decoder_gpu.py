@@ -96,3 +96,23 @@ def test_forward_loss_equals_unfused_training_step(dataset, max_depth):
     for ga, p in zip(grads_a, dec.parameters()):
         scale = float(p.grad.abs().max())
         assert float((ga - p.grad).abs().max()) <= 2e-4 * scale + 1e-9
+
+
+def test_inference_fast_path_equals_eval_path():
+    """Under torch.no_grad() in eval mode the conv blocks fold ELU + BatchNormalization into the concat pass;
+    the result must equal the autograd-capable eval path (torch ELU + BatchNorm + the plain concat kernel)."""
+    torch.manual_seed(3)
+    B, H, W, F = 2, 64, 96, 64
+    chans = [24, 8, 8, 12, 16]
+    feats = [torch.randn(B, H // s, W // s, c, device=DEV) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    dec = BtsDecoder(chans, 10.0, num_filters=F).to(DEV)
+    dec.train()
+    for _ in range(2):                                   # give the BatchNorm running statistics non-trivial values
+        dec(feats)
+    dec.eval()
+    ops.reset_launch_count()
+    with torch.no_grad():
+        fast = dec(feats)
+    assert ops.launch_count() >= 3 + 5 + 5               # heads, up-samplings, concats
+    slow = dec(feats)                                    # grad enabled: unfused BatchNorm path
+    np.testing.assert_allclose(fast.cpu().numpy(), slow.detach().cpu().numpy(), rtol=2e-4, atol=2e-5)
