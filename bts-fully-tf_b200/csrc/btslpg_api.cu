@@ -14,6 +14,7 @@
 #include "tail_kernels.cuh"
 #include "concat_kernels.cuh"
 #include "upsample_kernels.cuh"
+#include "slice_kernels.cuh"
 
 using namespace btslpg;
 
@@ -563,3 +564,4 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 #include "tail_api.inl"
 #include "concat_api.inl"
 #include "upsample_api.inl"
+#include "slice_api.inl"

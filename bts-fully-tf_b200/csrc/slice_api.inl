@@ -1,0 +1,67 @@
+// slice_api.inl -- C ABI for the strided affine + activation copy (DenseASPP glue, bts_decoder.py:46-76); included by btslpg_api.cu.
+
+namespace {
+
+// (B,H,W,C) NHWC view whose pixels are uniformly strided (e.g. a channel slice of a wider NHWC buffer)
+int parse_pixel_strided(const BtsTensor *t, const char *name, View &v) {
+    if (int e = parse_nhwc(t, name, v)) return e;
+    const int64_t npix = v.B * v.H * v.W;
+    if (npix * v.C == 0) return 0;
+    if (v.C > 1 && v.sC != 1) return fail(BTSLPG_ELAYOUT, "%s: channel stride must be 1", name);
+    const bool uniform = (v.H == 1 || v.sH == v.W * v.sW) && (v.B == 1 || v.sB == v.H * v.sH);
+    if (!uniform) return fail(BTSLPG_ELAYOUT, "%s: pixels must be uniformly strided (a channel slice of a contiguous NHWC tensor)", name);
+    if (v.sW < v.C) return fail(BTSLPG_ELAYOUT, "%s: pixel stride %lld is smaller than the channel count %lld", name, (long long)v.sW, (long long)v.C);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, const BtsTensor *shift, int act, BtsTensor *dst, void *stream) {
+    if (act < 0 || act > 2) return fail(BTSLPG_EINVAL, "act must be 0 (none), 1 (elu) or 2 (relu)");
+    if ((scale == nullptr) != (shift == nullptr)) return fail(BTSLPG_EINVAL, "scale and shift must be given together");
+    View s, d;
+    if (int e = parse_pixel_strided(src, "src", s)) return e;
+    if (int e = parse_pixel_strided(dst, "dst", d)) return e;
+    if (d.B != s.B || d.H != s.H || d.W != s.W || d.C != s.C) return fail(BTSLPG_ESHAPE, "dst: shape differs from src");
+    if (d.dtype != s.dtype) return fail(BTSLPG_EDTYPE, "dst: dtype differs from src");
+    if (d.dev != s.dev) return fail(BTSLPG_EDEVICE, "dst: on a different device than src");
+    float *sc = nullptr, *sh = nullptr;
+    if (scale) {
+        if (int e = parse_f32_vec(scale, "scale", s.C, s.dev, sc)) return e;
+        if (int e = parse_f32_vec(shift, "shift", s.C, s.dev, sh)) return e;
+    }
+    const int64_t npix = s.B * s.H * s.W;
+    if (npix * s.C == 0) return 0;
+    if (npix * s.C >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "src: more than 2^31 elements");
+    DeviceGuard guard(s.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", s.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // a single pixel row: the pixel stride of a (1,1,1,C) tensor carries no information
+    const int64_t s_src = npix == 1 ? s.C : s.sW, s_dst = npix == 1 ? d.C : d.sW;
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        constexpr int N = 16 / (int)sizeof(T);
+        const bool vec = s.C % N == 0 && s_src % N == 0 && s_dst % N == 0 && s.aligned(16) && d.aligned(16);
+        SliceParams<T> p;
+        p.src = reinterpret_cast<const T *>(s.ptr);
+        p.dst = reinterpret_cast<T *>(d.ptr);
+        p.scale = sc; p.shift = sh;
+        p.C = (uint32_t)s.C;
+        p.per_px = (uint32_t)(vec ? s.C / N : s.C);
+        p.n = (uint64_t)npix * p.per_px;
+        p.s_src = s_src; p.s_dst = s_dst;
+        p.div_pp = FastDiv(p.per_px);
+        p.act = act;
+        const unsigned blocks = (unsigned)((p.n + kSliceThreads - 1) / kSliceThreads);
+        if (vec) slice_affine_act_vec_kernel<T><<<blocks, kSliceThreads, 0, st>>>(p);
+        else slice_affine_act_scalar_kernel<T><<<blocks, kSliceThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "affine_act_%s<%s,%s%s,C%u>", vec ? "vec" : "scalar", ElemTraits<T>::kName, sc ? "affine+" : "",
+                 act == 1 ? "elu" : act == 2 ? "relu" : "id", p.C);
+        return check_launch("btslpg_affine_act");
+    };
+    return s.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+}  // extern "C"

@@ -107,6 +107,13 @@ class _DenseAspp(nn.Module):
         x = self.conv1(F.relu(x))
         return self.conv2(F.relu(self.bn2(x)))
 
+    def tail_inference(self, x_relu_nchw):
+        """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode:
+        the second BatchNormalization is folded into the 1x1 kernel (w * scale[o]) and a bias (shift)."""
+        scale, shift = _bn_affine(self.bn2)
+        x = F.conv2d(x_relu_nchw, self.conv1.weight * scale.view(-1, 1, 1, 1), shift)
+        return self.conv2(F.relu_(x))
+
 
 class BtsDecoder(nn.Module):
     """The decoder graph of bts_decoder.py with the three LPG heads fused.  Sub-modules are created in
@@ -181,6 +188,34 @@ class BtsDecoder(nn.Module):
         s2, s4, s8, s16 = decoder_inputs[1:]                               # skips stay NHWC: the concat kernel reads them as they are
         iconv5 = self.block5(dense, s16)
         iconv4 = self.block4(iconv5, s8)
+        if not self.training and not torch.is_grad_enabled():
+            daspp_feat = self._daspp_inference(iconv4)
+        else:
+            daspp_feat = self._daspp(iconv4)
+        return self._tail(daspp_feat, s2, s4, return_logit)
+
+    def _daspp_inference(self, iconv4):
+        """DenseASPP (bts_decoder.py:46-77) in inference mode on ONE (B,h,w,896) buffer that the blocks append to:
+        the reference's Concatenate + BatchNormalization + ReLU in front of every 1x1 conv (three passes over a
+        growing map) are one ops.affine_act pass over a channel slice; see csrc/slice_kernels.cuh."""
+        B, nf, h, w = iconv4.shape
+        half = nf // 2
+        buf = torch.empty((B, h, w, nf + 5 * half), dtype=iconv4.dtype, device=iconv4.device)       # [iconv4 | d3 | d6 | d12 | d18 | d24]
+        ops.affine_act(_nhwc_view(iconv4.contiguous(memory_format=torch.channels_last)), dst=buf[..., :nf])
+        s4_, t4_ = _bn_affine(self.bn4)
+        x = ops.affine_act(buf[..., :nf], scale=s4_, shift=t4_, act=ops.ACT_RELU)                    # relu(iconv4_bn)
+        ops.affine_act(_nhwc_view(self.daspp_3.tail_inference(_to_nchw(x)).contiguous(memory_format=torch.channels_last)),
+                       dst=buf[..., nf:nf + half])
+        for k, blk in enumerate((self.daspp_6, self.daspp_12, self.daspp_18, self.daspp_24)):
+            ck = nf + half * (k + 1)
+            sc, sh = _bn_affine(blk.bn_first)
+            x = ops.affine_act(buf[..., :ck], scale=sc, shift=sh, act=ops.ACT_RELU)                  # relu(BN(concat4_k)), contiguous
+            d = blk.tail_inference(_to_nchw(x))
+            ops.affine_act(_nhwc_view(d.contiguous(memory_format=torch.channels_last)), dst=buf[..., ck:ck + half])
+        ops.affine_act(buf[..., :nf], dst=buf[..., :nf], scale=s4_, shift=t4_)                       # concat4_daspp starts with iconv4_bn (:75)
+        return F.elu(self.daspp_feat(_to_nchw(buf)))
+
+    def _daspp(self, iconv4):
         iconv4_bn = self.bn4(iconv4)
         d3 = self.daspp_3(iconv4_bn)
         c2 = torch.cat([iconv4, d3], 1)
@@ -191,8 +226,9 @@ class BtsDecoder(nn.Module):
         d18 = self.daspp_18(c4)
         c5 = torch.cat([c4, d18], 1)
         d24 = self.daspp_24(c5)
-        daspp_feat = F.elu(self.daspp_feat(torch.cat([iconv4_bn, d3, d6, d12, d18, d24], 1)))
+        return F.elu(self.daspp_feat(torch.cat([iconv4_bn, d3, d6, d12, d18, d24], 1)))
 
+    def _tail(self, daspp_feat, s2, s4, return_logit):
         # bts_decoder.py:79-81: reduction_8x8 -> depth_8x8_scaled -> ds  (one kernel)
         red8, d8, d8_ds = self.reduction_8x8(_nhwc_view(daspp_feat.contiguous(memory_format=torch.channels_last)))
         iconv3 = self.block3(daspp_feat, s4, d8_ds)
@@ -212,6 +248,10 @@ class BtsDecoder(nn.Module):
                               "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
         if return_logit:
             return _nhwc_view(logit)
+        if not torch.is_grad_enabled():                                                # bts_decoder.py:102-103 in one pass
+            depth, _, _ = ops.silog_forward(_nhwc_view(logit.contiguous(memory_format=torch.channels_last)).contiguous(), None,
+                                            self.max_depth, 0.0)
+            return depth
         depth = torch.sigmoid(logit) * self.max_depth                                  # bts_decoder.py:102-103
         return _nhwc_view(depth)
 

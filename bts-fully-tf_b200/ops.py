@@ -12,6 +12,7 @@ Reference lines replaced:
   eval_metrics                   custom_eval_metrics.py:24-88
   concat_nhwc                    bts_decoder.py:98-99 (ELU of upconv1 + concat1) and :42
   upsample2x_nhwc                bts_decoder.py:31, :38, :97 UpSampling2D(size=2, 'nearest')
+  affine_act                     bts_decoder.py:46-76 DenseASPP glue: BN affine + ReLU over channel slices
 """
 import ctypes
 
@@ -467,6 +468,23 @@ class Upsample2xFunction(torch.autograd.Function):
 def upsample2x_nhwc(x):
     """`UpSampling2D(size=2, interpolation='nearest')` on an NHWC tensor, with autograd."""
     return Upsample2xFunction.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# strided per-channel affine + activation copy (DenseASPP glue, inference)
+# ---------------------------------------------------------------------------------------------
+ACT_NONE, ACT_ELU, ACT_RELU = 0, 1, 2
+
+
+def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
+    """dst[..., c] = act(src[..., c] * scale[c] + shift[c]); src / dst are (B,H,W,C) views with channel stride 1 and
+    uniformly strided pixels (channel slices of wider NHWC buffers), may alias.  No autograd (inference glue)."""
+    lib = load()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=src.dtype, device=src.device)
+    rs, rd, rsc, rsh = as_ref(src), as_ref(dst), as_ref(scale), as_ref(shift)
+    check(lib.btslpg_affine_act(rs.ptr, ptr_or_null(rsc), ptr_or_null(rsh), int(act), rd.ptr, current_stream_ptr(src.device)))
+    return dst
 
 
 def launch_count():

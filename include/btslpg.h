@@ -244,6 +244,18 @@ BTSLPG_API int btslpg_upsample2x_forward(const BtsTensor *in, BtsTensor *out, vo
 BTSLPG_API int btslpg_upsample2x_backward(const BtsTensor *g_out, BtsTensor *g_in, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-channel affine + activation copy between channel slices of NHWC tensors -- the glue of
+ * the DenseASPP block (bts_decoder.py:46-54, :61-76): with one (B,h,w,896) buffer that the blocks append to,
+ * the reference's Concatenate + BatchNormalization + ReLU in front of every 1x1 conv (three passes over a growing
+ * map) become one:  dst[b,y,x,c] = act(src[b,y,x,c] * scale[c] + shift[c]).
+ *   src, dst  (B,H,W,C), channel stride 1, uniformly strided pixels (e.g. buffer[..., c0:c0+C]); may alias (in place)
+ *   scale, shift  float32 [C], nullable together (an inference-mode BatchNormalization folded to an affine)
+ *   act  0 none, 1 ELU(alpha=1), 2 ReLU
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, const BtsTensor *shift, int act,
+                                 BtsTensor *dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").

@@ -115,3 +115,15 @@ def upsample2x_grad(g_out):
     g = np.asarray(g_out, np.float64)
     B, H, W, C = g.shape
     return g.reshape(B, H // 2, 2, W // 2, 2, C).sum(axis=(2, 4))
+
+
+def affine_act(x, scale=None, shift=None, act=0):
+    """DenseASPP glue (bts_decoder.py:47-49, :51-52): inference BatchNormalization as an affine, then 0 none / 1 ELU / 2 ReLU."""
+    x = np.asarray(x, np.float64)
+    if scale is not None:
+        x = x * np.asarray(scale, np.float64) + np.asarray(shift, np.float64)
+    if act == 1:
+        return np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    if act == 2:
+        return np.maximum(x, 0)
+    return x

@@ -212,3 +212,17 @@ def test_upsample_guard_bands(B, h, w, C, dtype):
     ops.upsample2x_backward(B2.input(out), g_in=g_in)
     B2.check()
     assert np.array_equal(npf(g_in), npf((x.float() * 4).to(dtype)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,h,w,C", [(1, 1, 1, 8), (2, 3, 5, 384), (1, 5, 3, 10)])
+def test_affine_act_guard_bands(B, h, w, C, dtype):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, h, w, C, generator=g).to(dtype)
+    scale, shift = (torch.rand(C, generator=g) + 0.5), torch.randn(C, generator=g)
+    A = Arena()
+    out = A.output((B, h, w, C), dtype)
+    ops.affine_act(A.input(x), dst=out, scale=A.input(scale), shift=A.input(shift), act=ops.ACT_RELU)
+    A.check()
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7
+    np.testing.assert_allclose(npf(out), tail_oracle.affine_act(npf(x), npf(scale), npf(shift), 2), rtol=tol, atol=tol)
