@@ -141,7 +141,7 @@ def run(cfg_id, a, rank, local_rank, world):
             "unit": "images/s", "n_gpus": world, "per_gpu_batch": b, "global_batch": gb, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms / a.steps, 3), "scaling": "strong" if a.per_gpu_batch is None else "weak",
             "lpg_path": a.lpg, "fused_heads_forward_ms": None if lpg_ms is None else round(lpg_ms, 3),
-            "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32",
+            "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32", "cudnn_autotune": bool(torch.backends.cudnn.benchmark),
             "grad_bucket_bytes": None if bucket is None else bucket.nbytes(), "result_mean": result,
             "data": "synthetic encoder taps, random-init decoder"}))
 
@@ -153,7 +153,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-gpu-batch", type=int, default=None, help="fix the per-GPU batch (weak scaling) instead of the global batch")
     ap.add_argument("--lpg", default="fused", choices=["fused", "literal"])
+    ap.add_argument("--no-cudnn-autotune", action="store_true",
+                    help="keep cuDNN's heuristic algorithm choice (default: autotune, as TensorFlow does with TF_CUDNN_USE_AUTOTUNE=1)")
     a = ap.parse_args()
+    torch.backends.cudnn.benchmark = not a.no_cudnn_autotune
     rank, local_rank, world = parallel.init_distributed()
     torch.cuda.set_device(local_rank)
     for c in a.config:
