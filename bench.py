@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--skip-decoder", action="store_true", help="skip the decoder images/s context line (extras.decoder_config3)")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -228,6 +229,43 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # the B200 arm
 # --------------------------------------------------------------------------------------------
+def decoder_context(device, rank, world, barrier, global_batch=64, H=480, W=640, steps=5, warmup=3):
+    """BASELINE config 3: BTS-NYU DenseNet-161 decoder, batched inference at 480x640, global batch 64 sharded over the
+    ranks (strong scaling), synthetic encoder taps of the reference's shapes (bts.py:72,80), random-init decoder."""
+    import torch
+    import torch.distributed as dist
+    from bts_fully_tf_b200 import ops, parallel
+    from bts_fully_tf_b200.decoder import BtsDecoder
+    chans, filters = [2208, 96, 96, 192, 384], 512
+    lo, hi = parallel.shard_range(global_batch, world, rank)
+    b = hi - lo
+    torch.backends.cudnn.benchmark = True            # TensorFlow autotunes cuDNN by default as well
+    torch.manual_seed(rank)
+    feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=device)) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    dec = BtsDecoder(chans, 10.0, num_filters=filters).to(device).eval()
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = dec(feats)
+        barrier()
+        ops.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = dec(feats)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"workload": "BTS-NYU DenseNet-161 decoder inference 480x640, global batch %d (BASELINE config 3; encoder out of scope: "
+                        "synthetic taps)" % global_batch,
+            "images_per_s": round(global_batch * steps / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 3), "per_gpu_batch": b,
+            "scaling": "strong", "steps": steps, "warmup": warmup, "own_kernel_launches_per_step": ops.launch_count() // steps,
+            "conv_math": "TF32 on cuDNN (autotuned)", "result_mean": float(out.float().mean())}
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
@@ -438,6 +476,18 @@ def main():
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # ---- context for the second half of BASELINE.json's metric ("BTS decoder images/s at 1/2/4/8 B200"): config 3,
+    # the decoder with this repo's kernels around cuDNN's convolutions; a failure here never touches the headline line
+    if not a.skip_decoder:
+        try:
+            del all_sets, sets
+            if not a.skip_e2e:
+                del pipe, host
+            torch.cuda.empty_cache()
+            extras["decoder_config3"] = decoder_context(device, rank, world, barrier)
+        except Exception as exc:  # noqa: BLE001
+            extras["decoder_config3"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu:

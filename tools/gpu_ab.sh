@@ -6,8 +6,8 @@ LIBDIR=$PWD/bts-fully-tf_b200/lib
 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/ab/pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/ab/pytest.log
 for tag in default $TAGS; do
   if [ $tag = default ]; then unset BTSLPG_LIB; else export BTSLPG_LIB=$LIBDIR/libbtslpg_$tag.so; fi
-  timeout 300 python bench.py --skip-cpu --skip-e2e > gpurun_out/ab/bench_${tag}_f32.json 2> gpurun_out/ab/bench_${tag}_f32.err; echo "$tag f32 exit $?"
-  timeout 300 python bench.py --skip-cpu --skip-e2e --dtype bf16 > gpurun_out/ab/bench_${tag}_bf16.json 2> gpurun_out/ab/bench_${tag}_bf16.err; echo "$tag bf16 exit $?"
+  timeout 300 python bench.py --skip-cpu --skip-e2e --skip-decoder > gpurun_out/ab/bench_${tag}_f32.json 2> gpurun_out/ab/bench_${tag}_f32.err; echo "$tag f32 exit $?"
+  timeout 300 python bench.py --skip-cpu --skip-e2e --skip-decoder --dtype bf16 > gpurun_out/ab/bench_${tag}_bf16.json 2> gpurun_out/ab/bench_${tag}_bf16.err; echo "$tag bf16 exit $?"
 done
 python - <<'PY'
 import json,glob

@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1;
 for tag in default $TAGS; do
   if [ $tag = default ]; then unset BTSLPG_LIB; else export BTSLPG_LIB=$LIBDIR/libbtslpg_$tag.so; fi
   for i in 1 2; do
-    timeout 300 python bench.py --skip-cpu --skip-e2e --dtype bf16 > gpurun_out/ab/bench_${tag}_bf16_$i.json 2>/dev/null
+    timeout 300 python bench.py --skip-cpu --skip-e2e --skip-decoder --dtype bf16 > gpurun_out/ab/bench_${tag}_bf16_$i.json 2>/dev/null
   done
   python tools/sweep_head.py > gpurun_out/ab/sweep_head_$tag.json 2>/dev/null
 done

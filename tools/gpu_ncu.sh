@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>
 [ $rc -ne 0 ] && exit $rc
 timeout 600 python bench.py > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err; echo "bench f32 exit $?"
 timeout 300 python bench.py --dtype bf16 --skip-cpu > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench bf16 exit $?"
-CMD="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu --skip-extras --no-graph --mode multi"
+CMD="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu --skip-extras --skip-decoder --no-graph --mode multi"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?"

@@ -16,7 +16,7 @@ timeout 300 python bench.py --dtype bf16 --skip-cpu > gpurun_out/bench_bf16.json
 timeout 600 python tools/sweep.py > gpurun_out/sweep.json 2> gpurun_out/sweep.err; echo "sweep exit $?"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"
 if [ $rc -eq 0 ]; then
-  CMD="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu --skip-extras --no-graph --mode multi"
+  CMD="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu --skip-extras --skip-decoder --no-graph --mode multi"
   $CMD > gpurun_out/plain.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
   echo "ncu launches exit $?"
