@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbtslpg.so")
 
 SOURCES = ["btslpg_api.cu"]
-DEPS = ["btslpg_api.cu", "head_api.inl", "head_kernels.cuh", "lpg_kernels.cuh", "common.cuh", "tma_pipe.cuh", "lpg_dir_tables.h", "tail_kernels.cuh", "tail_api.inl", "concat_kernels.cuh", "concat_api.inl", "upsample_kernels.cuh", "upsample_api.inl", "slice_kernels.cuh", "slice_api.inl",
+DEPS = ["btslpg_api.cu", "head_api.inl", "head_kernels.cuh", "lpg_kernels.cuh", "common.cuh", "tma_pipe.cuh", "lpg_dir_tables.h", "tail_kernels.cuh", "tail_api.inl", "concat_kernels.cuh", "concat_api.inl", "upsample_kernels.cuh", "upsample_api.inl", "slice_kernels.cuh", "slice_api.inl", "depthconv_kernels.cuh", "depthconv_api.inl",
         os.path.join("..", "..", "include", "btslpg.h")]
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 #include "concat_kernels.cuh"
 #include "upsample_kernels.cuh"
 #include "slice_kernels.cuh"
+#include "depthconv_kernels.cuh"
 
 using namespace btslpg;
 
@@ -565,3 +566,4 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 #include "concat_api.inl"
 #include "upsample_api.inl"
 #include "slice_api.inl"
+#include "depthconv_api.inl"

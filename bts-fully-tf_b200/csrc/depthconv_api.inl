@@ -1,0 +1,76 @@
+// depthconv_api.inl -- C ABI for the backward of the last convolution (bts_decoder.py:102); included by btslpg_api.cu.
+
+extern "C" {
+
+size_t btslpg_depthconv_backward_workspace_bytes(int channels) {
+    if (channels < 1) channels = 1;
+    return (size_t)kDcHeaderBytes + (size_t)kDcMaxBlocks * 9 * channels * sizeof(float);
+}
+
+int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, BtsTensor *g_x, BtsTensor *g_kernel,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    View xv, gv, gxv;
+    if (int e = parse_nhwc(x, "x", xv)) return e;
+    const int C = (int)xv.C;
+    if (C != 16 && C != 32) return fail(BTSLPG_ESHAPE, "x: %d channels; the fused backward is built for C = 16 and C = 32 (F/16 of the reference's encoders)", C);
+    if (!is_contig_nhwc(xv) || !xv.aligned(16)) return fail(BTSLPG_ELAYOUT, "x: must be a contiguous, 16-byte aligned NHWC tensor");
+    int64_t ng = 0;
+    if (int e = parse_flat(g_out, "g_out", gv, ng)) return e;
+    if (gv.B != xv.B || gv.H != xv.H || gv.W != xv.W) return fail(BTSLPG_ESHAPE, "g_out: (B,H,W) differs from x");
+    if (gv.dtype != xv.dtype) return fail(BTSLPG_EDTYPE, "g_out: dtype differs from x");
+    if (gv.dev != xv.dev) return fail(BTSLPG_EDEVICE, "g_out: on a different device than x");
+    float *w = nullptr, *gw = nullptr;
+    if (!kernel) return fail(BTSLPG_EINVAL, "kernel: tensor is NULL");
+    if (int e = parse_f32_vec(kernel, "kernel", 9 * C, xv.dev, w)) return e;
+    if (!g_x && !g_kernel) return fail(BTSLPG_EINVAL, "depthconv_backward: both outputs are NULL");
+    if (g_x) {
+        if (int e = parse_nhwc(g_x, "g_x", gxv)) return e;
+        if (gxv.B != xv.B || gxv.H != xv.H || gxv.W != xv.W || gxv.C != xv.C) return fail(BTSLPG_ESHAPE, "g_x: shape differs from x");
+        if (gxv.dtype != xv.dtype) return fail(BTSLPG_EDTYPE, "g_x: dtype differs from x");
+        if (gxv.dev != xv.dev) return fail(BTSLPG_EDEVICE, "g_x: on a different device than x");
+        if (!is_contig_nhwc(gxv) || !gxv.aligned(16)) return fail(BTSLPG_ELAYOUT, "g_x: must be a contiguous, 16-byte aligned NHWC tensor");
+    }
+    if (g_kernel) {
+        if (int e = parse_f32_vec(g_kernel, "g_kernel", 9 * C, xv.dev, gw)) return e;
+        if (!workspace) return fail(BTSLPG_EWORKSPACE, "depthconv_backward: workspace is NULL");
+        if (workspace_bytes < (size_t)kDcHeaderBytes + (size_t)9 * C * sizeof(float)) return fail(BTSLPG_EWORKSPACE, "depthconv_backward: workspace too small");
+        if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(BTSLPG_EWORKSPACE, "depthconv_backward: workspace must be 16-byte aligned");
+    }
+    const int64_t npix = xv.B * xv.H * xv.W;
+    if (npix == 0) return 0;
+    if (npix * C >= ((int64_t)1 << 31) * 4) return fail(BTSLPG_ESHAPE, "x: too large");
+    DeviceGuard guard(xv.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", xv.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag, auto ctag) -> int {
+        using T = decltype(tag);
+        constexpr int CC = decltype(ctag)::value;
+        DepthConvBwdParams<T> p;
+        p.x = reinterpret_cast<const T *>(xv.ptr);
+        p.g = reinterpret_cast<const T *>(gv.ptr);
+        p.w = w;
+        p.g_x = g_x ? reinterpret_cast<T *>(gxv.ptr) : nullptr;
+        p.g_w = gw;
+        p.counter = reinterpret_cast<unsigned int *>(workspace);
+        p.partial = workspace ? reinterpret_cast<float *>(static_cast<char *>(workspace) + kDcHeaderBytes) : nullptr;
+        p.B = (uint32_t)xv.B; p.H = (uint32_t)xv.H; p.W = (uint32_t)xv.W;
+        p.col_blocks = (uint32_t)((xv.W + kDcTileW - 1) / kDcTileW);
+        p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
+        p.div_cb = FastDiv(p.col_blocks);
+        p.div_h = FastDiv(p.H);
+        static const int resident = occupancy_blocks(depthconv_bwd_kernel<T, CC>, kDcThreads);
+        uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
+        if (blocks > (uint32_t)kDcMaxBlocks) blocks = kDcMaxBlocks;
+        if (gw) {
+            const size_t fit = (workspace_bytes - kDcHeaderBytes) / ((size_t)9 * CC * sizeof(float));
+            if (fit < blocks) blocks = (uint32_t)fit;
+        }
+        depthconv_bwd_kernel<T, CC><<<blocks, kDcThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_bwd<%s,C%d>", ElemTraits<T>::kName, CC);
+        return check_launch("btslpg_depthconv_backward");
+    };
+    if (xv.dtype == kF32) return C == 32 ? go(float{}, IntC<32>{}) : go(float{}, IntC<16>{});
+    return C == 32 ? go(__nv_bfloat16{}, IntC<32>{}) : go(__nv_bfloat16{}, IntC<16>{});
+}
+
+}  // extern "C"

@@ -243,7 +243,11 @@ class BtsDecoder(nn.Module):
         pad1 = ops.pad_to(up1_nhwc.shape[-1] + 3)                          # 35 -> 36 channels
         concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
         iconv1 = F.elu(_conv_padded_input(self.iconv1, concat1, pad1))
-        logit = self.depth_conv(iconv1)                                                # (B,1,H,W): same memory as NHWC (B,H,W,1)
+        if torch.is_grad_enabled() and iconv1.shape[1] in (16, 32):
+            # bts_decoder.py:102: library forward, ONE hand-written pass for both gradients (ops.depth_conv)
+            logit = _to_nchw(ops.depth_conv(_nhwc_view(iconv1.contiguous(memory_format=torch.channels_last)), self.depth_conv.weight))
+        else:
+            logit = self.depth_conv(iconv1)                                            # (B,1,H,W): same memory as NHWC (B,H,W,1)
         self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
                               "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
         if return_logit:

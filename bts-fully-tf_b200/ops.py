@@ -13,6 +13,7 @@ Reference lines replaced:
   concat_nhwc                    bts_decoder.py:98-99 (ELU of upconv1 + concat1) and :42
   upsample2x_nhwc                bts_decoder.py:31, :38, :97 UpSampling2D(size=2, 'nearest')
   affine_act                     bts_decoder.py:46-76 DenseASPP glue: BN affine + ReLU over channel slices
+  depth_conv                     bts_decoder.py:102 last Conv2D(1, 3x3): fused data + weight gradient
 """
 import ctypes
 
@@ -485,6 +486,52 @@ def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
     rs, rd, rsc, rsh = as_ref(src), as_ref(dst), as_ref(scale), as_ref(shift)
     check(lib.btslpg_affine_act(rs.ptr, ptr_or_null(rsc), ptr_or_null(rsh), int(act), rd.ptr, current_stream_ptr(src.device)))
     return dst
+
+
+# ---------------------------------------------------------------------------------------------
+# last convolution Conv2D(1, 3x3, 'same'): library forward, fused hand-written backward
+# ---------------------------------------------------------------------------------------------
+def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True):
+    """x (B,H,W,C) NHWC, kernel9c float32 [9*C] ([tap][c] == Keras HWIO (3,3,C,1)), g_out (B,H,W,1).
+    Returns (g_x-or-None, g_kernel [9*C] float32-or-None), both from one pass."""
+    lib = load()
+    C = x.shape[-1]
+    g_x = torch.empty_like(x, memory_format=torch.contiguous_format) if need_g_x else None
+    g_k = torch.empty(9 * C, dtype=torch.float32, device=x.device) if need_g_kernel else None
+    ws = _workspace(x.device, int(lib.btslpg_depthconv_backward_workspace_bytes(C))) if need_g_kernel else None
+    rx, rk, rg, rgx, rgk = as_ref(x), as_ref(kernel9c), as_ref(g_out), as_ref(g_x), as_ref(g_k)
+    check(lib.btslpg_depthconv_backward(rx.ptr, rk.ptr, rg.ptr, ptr_or_null(rgx), ptr_or_null(rgk),
+                                        ctypes.c_void_p(ws.data_ptr() if ws is not None else 0), ws.numel() if ws is not None else 0,
+                                        current_stream_ptr(x.device)))
+    return g_x, g_k
+
+
+class DepthConvFunction(torch.autograd.Function):
+    """x NHWC (B,H,W,C), weight torch OIHW (1,C,3,3) -> (B,H,W,1).  Forward: the library convolution (at its HBM floor
+    already); backward: one hand-written pass for both gradients."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, weight):
+        y = torch.nn.functional.conv2d(x_nhwc.permute(0, 3, 1, 2), weight, padding=1)          # (B,1,H,W): NHWC memory as well
+        ctx.save_for_backward(x_nhwc, weight)
+        return y.permute(0, 2, 3, 1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        x, weight = ctx.saved_tensors
+        k9c = weight.detach().permute(2, 3, 1, 0).reshape(-1).float().contiguous()              # OIHW -> [ky][kx][c] == HWIO flattened
+        g_x, g_k = depthconv_backward(x.contiguous(), k9c, g_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g_w = None
+        if g_k is not None:
+            C = x.shape[-1]
+            g_w = g_k.view(3, 3, C, 1).permute(3, 2, 0, 1).to(weight.dtype)                      # back to OIHW
+        return g_x, g_w
+
+
+def depth_conv(x_nhwc, weight):
+    """The decoder's last convolution with autograd; C in (16, 32) takes the fused backward."""
+    return DepthConvFunction.apply(x_nhwc, weight)
 
 
 def launch_count():

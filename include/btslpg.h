@@ -256,6 +256,23 @@ BTSLPG_API int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, c
                                  BtsTensor *dst, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Backward of the decoder's last convolution -- bts_decoder.py:102
+ *     Conv2D(1, kernel_size=3, strides=1, padding='same', use_bias=False)(iconv1)
+ * both gradients in ONE pass (library convolutions need 3.7 ms for it at B = 32, 480x640: a tensor-core weight
+ * gradient with a 288-element output plus two layout conversions; the traffic floor is 0.4 ms):
+ *   x        (B,H,W,C)  the layer input, C = 16 or 32 (F/16), contiguous NHWC
+ *   kernel   float32, 9*C elements: the Keras HWIO kernel (3,3,C,1) as it lies in memory ([tap][c])
+ *   g_out    (B,H,W[,1]) gradient of the layer's (pre-activation) output
+ *   g_x      (B,H,W,C)  d loss / d x, nullable
+ *   g_kernel float32 [9*C] d loss / d kernel in the same layout, nullable; reduced deterministically through
+ *            `workspace` (btslpg_depthconv_backward_workspace_bytes(C) bytes, first 256 zeroed once)
+ * Exact float32 arithmetic.  The forward of this layer stays on the library convolution (already at its floor).
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API size_t btslpg_depthconv_backward_workspace_bytes(int channels);
+BTSLPG_API int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, BtsTensor *g_x,
+                                         BtsTensor *g_kernel, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").

@@ -127,3 +127,33 @@ def affine_act(x, scale=None, shift=None, act=0):
     if act == 2:
         return np.maximum(x, 0)
     return x
+
+
+def depthconv_forward(x, w9c):
+    """bts_decoder.py:102 Conv2D(1, 3, padding='same', use_bias=False): y[p] = sum_{t,c} x[p + t][c] * w[t][c], float64.
+    w9c: the HWIO kernel (3,3,C,1) flattened to (9, C)."""
+    x = np.asarray(x, np.float64)
+    B, H, W, C = x.shape
+    w = np.asarray(w9c, np.float64).reshape(3, 3, C)
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    y = np.zeros((B, H, W))
+    for ky in range(3):
+        for kx in range(3):
+            y += (xp[:, ky:ky + H, kx:kx + W, :] * w[ky, kx]).sum(-1)
+    return y[..., None]
+
+
+def depthconv_backward(x, w9c, g_out):
+    """Gradients of depthconv_forward: (g_x (B,H,W,C), g_w (9, C)), float64."""
+    x = np.asarray(x, np.float64)
+    B, H, W, C = x.shape
+    w = np.asarray(w9c, np.float64).reshape(3, 3, C)
+    g = np.asarray(g_out, np.float64).reshape(B, H, W)
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    gxp = np.zeros_like(xp)
+    gw = np.zeros((3, 3, C))
+    for ky in range(3):
+        for kx in range(3):
+            gw[ky, kx] = (g[..., None] * xp[:, ky:ky + H, kx:kx + W, :]).sum(axis=(0, 1, 2))
+            gxp[:, ky:ky + H, kx:kx + W, :] += g[..., None] * w[ky, kx]
+    return gxp[:, 1:-1, 1:-1, :], gw.reshape(9, C)

@@ -226,3 +226,19 @@ def test_affine_act_guard_bands(B, h, w, C, dtype):
     A.check()
     tol = 2e-6 if dtype == torch.float32 else 2 ** -7
     np.testing.assert_allclose(npf(out), tail_oracle.affine_act(npf(x), npf(scale), npf(shift), 2), rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,C", [(1, 1, 1, 16), (2, 3, 5, 32), (1, 2, 131, 32), (1, 5, 7, 16)])
+def test_depthconv_guard_bands(B, H, W, C, dtype):
+    g = torch.Generator().manual_seed(W)
+    x = torch.randn(B, H, W, C, generator=g).to(dtype)
+    w = torch.randn(9 * C, generator=g) * 0.2
+    go = torch.randn(B, H, W, 1, generator=g).to(dtype)
+    A = Arena()
+    g_x, g_k = ops.depthconv_backward(A.input(x), A.input(w), A.input(go))
+    A.check()
+    ref_gx, ref_gw = tail_oracle.depthconv_backward(npf(x), w.numpy(), npf(go))
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7
+    assert np.abs(npf(g_x) - ref_gx).max() <= tol * max(np.abs(ref_gx).max(), 1e-30)
+    assert np.abs(npf(g_k).reshape(9, C) - ref_gw).max() <= 1e-5 * max(np.abs(ref_gw).max(), 1e-30)
