@@ -18,7 +18,7 @@ from bts_fully_tf_b200.decoder import BtsDecoder  # noqa: E402
 TAPS = ([2208, 96, 96, 192, 384], 512)
 
 
-def top_kernels(prof, n=14):
+def top_kernels(prof, n=24):
     rows = []
     for e in prof.key_averages():
         t = getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0)
