@@ -243,15 +243,33 @@ def decoder_context(device, rank, world, barrier, global_batch=64, H=480, W=640,
     torch.manual_seed(rank)
     feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=device)) for s, c in zip((32, 2, 4, 8, 16), chans)]
     dec = BtsDecoder(chans, 10.0, num_filters=filters).to(device).eval()
+    graph = None
     with torch.no_grad():
         for _ in range(warmup):
             out = dec(feats)
-        barrier()
         ops.reset_launch_count()
+        out = dec(feats)
+        launches = ops.launch_count()
+        try:        # the whole step as one CUDA graph: it is launch-bound at small per-GPU batches
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    out = dec(feats)
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            graph = g
+        except Exception:  # noqa: BLE001
+            graph = None
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            out = dec(feats)
+            if graph is not None:
+                graph.replay()
+            else:
+                out = dec(feats)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -262,7 +280,7 @@ def decoder_context(device, rank, world, barrier, global_batch=64, H=480, W=640,
     return {"workload": "BTS-NYU DenseNet-161 decoder inference 480x640, global batch %d (BASELINE config 3; encoder out of scope: "
                         "synthetic taps)" % global_batch,
             "images_per_s": round(global_batch * steps / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 3), "per_gpu_batch": b,
-            "scaling": "strong", "steps": steps, "warmup": warmup, "own_kernel_launches_per_step": ops.launch_count() // steps,
+            "scaling": "strong", "steps": steps, "warmup": warmup, "own_kernel_launches_per_step": launches, "cuda_graph": graph is not None,
             "conv_math": "TF32 on cuDNN (autotuned)", "result_mean": float(out.float().mean())}
 
 

@@ -2,7 +2,9 @@
 hot path behind the reference's Keras-layer surface.
 
 Only what the path needs lives here:
-  csrc/        hand-written CUDA kernels + the C ABI (include/btslpg.h) -> lib/libbtslpg.so
+  csrc/        hand-written CUDA kernels + the C ABI (include/btslpg.h) -> lib/libbtslpg.so:
+               lpg_* (LPG fwd/bwd), head_* (fused reduction heads), tail_* (sigmoid*max_depth + si_log_loss, eval metrics),
+               concat_* (ELU/BatchNorm + concat), upsample_* (nearest x2), slice_* (DenseASPP glue), depthconv_* (last conv backward)
   _cabi.py     ctypes binding (BtsTensor == DLTensor, zero copy)
   ops.py       functional ops + autograd glue
   layers.py    LocalPlanarGuidance / ReductionLPG with the reference's layer protocol

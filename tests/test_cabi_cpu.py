@@ -95,6 +95,39 @@ def test_argument_validation_without_gpu(lib):
     assert lib.btslpg_reduce_backward_workspace_bytes(2457600, 64) >= 256 + 64 * 3 * 4
 
 
+def test_argument_validation_of_the_decoder_glue_entry_points(lib):
+    """tail / concat / up-sampling / slice / depth-conv entry points: validation errors without any launch."""
+    def fake_cuda(t):
+        ref = _cabi.from_torch(t)
+        ref.struct.device.device_type = 2
+        return ref
+    x = fake_cuda(torch.rand(1, 4, 4, 8))
+    out = fake_cuda(torch.rand(1, 4, 4, 9))
+    plane = fake_cuda(torch.rand(1, 4, 4, 1))
+    arr = (_cabi._TP * 1)(plane.ptr)
+    assert lib.btslpg_concat_forward(x.ptr, 2, None, None, None, arr, 1, 0, out.ptr, None) == -1            # act out of range
+    assert lib.btslpg_concat_forward(x.ptr, 0, None, None, None, arr, 1, 9, out.ptr, None) == -1            # pad out of range
+    assert lib.btslpg_concat_forward(x.ptr, 0, x.ptr, None, None, arr, 1, 0, out.ptr, None) == -1           # scale without shift
+    wide = fake_cuda(torch.rand(1, 4, 4, 12))
+    assert lib.btslpg_concat_forward(x.ptr, 0, None, None, None, arr, 1, 0, wide.ptr, None) == -3           # out must be CA + planes + pad wide
+    big = fake_cuda(torch.rand(1, 8, 9, 8))
+    assert lib.btslpg_upsample2x_forward(x.ptr, big.ptr, None) == -3                                         # (B, 2h, 2w, C)
+    assert lib.btslpg_affine_act(x.ptr, None, None, 3, x.ptr, None) == -1                                    # act out of range
+    assert lib.btslpg_affine_act(x.ptr, None, None, 0, out.ptr, None) == -3                                  # shape differs
+    g = fake_cuda(torch.rand(1, 4, 4, 1))
+    k = fake_cuda(torch.rand(72))
+    assert lib.btslpg_depthconv_backward(x.ptr, k.ptr, g.ptr, x.ptr, None, None, 0, None) == -3              # C must be 16 or 32
+    assert b"C = 16 and C = 32" in lib.btslpg_last_error()
+    yt = fake_cuda(torch.rand(1, 4, 4, 1))
+    assert lib.btslpg_silog_forward(None, None, 10.0, 0.1, yt.ptr, None, None, 0, None) == -1                # nothing to compute
+    assert lib.btslpg_silog_forward(yt.ptr, yt.ptr, 10.0, 0.1, yt.ptr, None, None, 0, None) == -1            # loss tensor missing
+    m = fake_cuda(torch.rand(4))
+    ws = ctypes.c_void_p(256)
+    assert lib.btslpg_eval_metrics(yt.ptr, yt.ptr, 1e-3, 10.0, m.ptr, ws, 1 << 20, None) == -3               # metrics needs 10 floats
+    assert lib.btslpg_tail_workspace_bytes() >= 256 + 148 * 10 * 8
+    assert lib.btslpg_depthconv_backward_workspace_bytes(32) >= 256 + 9 * 32 * 4
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_cabi, "_lib", None)
     monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libbtslpg.so")

@@ -98,8 +98,31 @@ def run(cfg_id, a, rank, local_rank, world):
         with torch.no_grad():
             return dec(feats)
 
+    graph = None
     for _ in range(a.warmup):
         out = step()
+    if not cfg["train"] and not a.no_graph:
+        # inference: the whole decoder step as ONE CUDA graph (≈130 launches, launch-bound at small per-GPU batches);
+        # every op of this repo is capture-safe (no synchronisation, no host-side data dependence)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    out = step()
+            torch.cuda.current_stream().wait_stream(side)
+            inner = step
+
+            def step():                     # noqa: F811
+                graph.replay()
+                return out
+            step()
+        except Exception as exc:  # noqa: BLE001
+            graph = None
+            step = inner if "inner" in dir() else step
+            print("CUDA graph capture failed, running eagerly: %s" % exc, file=sys.stderr)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -141,7 +164,7 @@ def run(cfg_id, a, rank, local_rank, world):
             "unit": "images/s", "n_gpus": world, "per_gpu_batch": b, "global_batch": gb, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms / a.steps, 3), "scaling": "strong" if a.per_gpu_batch is None else "weak",
             "lpg_path": a.lpg, "fused_heads_forward_ms": None if lpg_ms is None else round(lpg_ms, 3),
-            "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32", "cudnn_autotune": bool(torch.backends.cudnn.benchmark),
+            "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32", "cudnn_autotune": bool(torch.backends.cudnn.benchmark), "cuda_graph": graph is not None,
             "grad_bucket_bytes": None if bucket is None else bucket.nbytes(), "result_mean": result,
             "data": "synthetic encoder taps, random-init decoder"}))
 
@@ -153,6 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-gpu-batch", type=int, default=None, help="fix the per-GPU batch (weak scaling) instead of the global batch")
     ap.add_argument("--lpg", default="fused", choices=["fused", "literal"])
+    ap.add_argument("--no-graph", action="store_true", help="inference configs: run eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--no-cudnn-autotune", action="store_true",
                     help="keep cuDNN's heuristic algorithm choice (default: autotune, as TensorFlow does with TF_CUDNN_USE_AUTOTUNE=1)")
     a = ap.parse_args()
