@@ -69,10 +69,10 @@ SYMBOLS = {
                                              ctypes.c_int, _TP, ctypes.c_void_p]),
     "btslpg_eval_metrics": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p, ctypes.c_size_t,
                                            ctypes.c_void_p]),
-    "btslpg_concat_forward": (ctypes.c_int, [_TP, ctypes.c_int, _TP, _TP, _TP, ctypes.POINTER(_TP), ctypes.c_int, ctypes.c_int, _TP,
-                                             ctypes.c_void_p]),
-    "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, _TP, ctypes.POINTER(_TP), ctypes.c_int, ctypes.c_int,
-                                              ctypes.c_void_p]),
+    "btslpg_concat_forward": (ctypes.c_int, [_TP, ctypes.c_int, ctypes.c_int, _TP, _TP, _TP, ctypes.POINTER(_TP), ctypes.c_int, ctypes.c_int,
+                                             _TP, ctypes.c_void_p]),
+    "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p]),
     "btslpg_upsample2x_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_upsample2x_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_affine_act": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_void_p]),

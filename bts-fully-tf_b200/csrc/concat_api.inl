@@ -20,7 +20,7 @@ int check_dense_nhwc(const View &v, const char *name, int vec) {
 
 // parse (dense a, optional dense b, planes, concatenated tensor); `cat_name` names the (B,H,W,CT) tensor
 int parse_concat(const BtsTensor *a, const BtsTensor *b, const BtsTensor *const *planes, int n_planes, const BtsTensor *cat, const char *a_name,
-                 const char *b_name, const char *p_name, const char *cat_name, ConcatGeom &g) {
+                 const char *b_name, const char *p_name, const char *cat_name, ConcatGeom &g, bool a_subpixel = false) {
     if (n_planes < 0 || n_planes > kConcatMaxPlanes) return fail(BTSLPG_EINVAL, "concat: n_planes must be in [0, %d]", kConcatMaxPlanes);
     if (n_planes > 0 && !planes) return fail(BTSLPG_EINVAL, "%s: array is NULL", p_name);
     if (int e = parse_nhwc(cat, cat_name, g.out)) return e;
@@ -37,7 +37,17 @@ int parse_concat(const BtsTensor *a, const BtsTensor *b, const BtsTensor *const 
     if (a) {
         if (int e = parse_nhwc(a, a_name, g.a)) return e;
         if (int e = check_dense_nhwc(g.a, a_name, vec)) return e;
-        if (int e = same(g.a, a_name)) return e;
+        if (a_subpixel) {
+            // (B, h, w, 4*CA) with (2h, 2w) = the concat's (H, W): fold it into the logical (B, H, W, CA) geometry
+            if (g.a.B != g.out.B || 2 * g.a.H != g.out.H || 2 * g.a.W != g.out.W || g.a.C % 4)
+                return fail(BTSLPG_ESHAPE, "%s: sub-pixel source must be (B, H/2, W/2, 4*CA) of %s (B,H,W,CT)", a_name, cat_name);
+            if ((g.a.C / 4) % vec) return fail(BTSLPG_ESHAPE, "%s: sub-pixel source needs CA %% %d == 0", a_name, vec);
+            if (g.a.dtype != g.out.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", a_name, cat_name);
+            if (g.a.dev != g.out.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", a_name, cat_name);
+            g.a.C /= 4; g.a.H *= 2; g.a.W *= 2;
+        } else {
+            if (int e = same(g.a, a_name)) return e;
+        }
         ct += g.a.C;
     }
     g.has_b = b != nullptr;
@@ -89,14 +99,14 @@ template <typename KernelT> int concat_blocks(KernelT kernel, int smem, uint64_t
 
 extern "C" {
 
-int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, const BtsTensor *shift, const BtsTensor *b,
+int btslpg_concat_forward(const BtsTensor *a, int a_subpixel, int act, const BtsTensor *scale, const BtsTensor *shift, const BtsTensor *b,
                           const BtsTensor *const *planes, int n_planes, int pad_channels, BtsTensor *out, void *stream) {
     if (!a) return fail(BTSLPG_EINVAL, "a: tensor is NULL");
     if (act != 0 && act != 1) return fail(BTSLPG_EINVAL, "act must be 0 (none) or 1 (elu)");
     if (pad_channels < 0 || pad_channels > 7) return fail(BTSLPG_EINVAL, "pad_channels must be in [0, 7]");
     if ((scale == nullptr) != (shift == nullptr)) return fail(BTSLPG_EINVAL, "scale and shift must be given together");
     ConcatGeom g;
-    if (int e = parse_concat(a, b, planes, n_planes, out, "a", "b", "planes", "out", g)) return e;
+    if (int e = parse_concat(a, b, planes, n_planes, out, "a", "b", "planes", "out", g, a_subpixel != 0)) return e;
     for (int k = 0; k < n_planes; ++k)
         if (!planes[k]) return fail(BTSLPG_EINVAL, "planes[%d]: tensor is NULL", k);
     const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes + pad_channels;
@@ -107,6 +117,7 @@ int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, c
         if (int e = parse_f32_vec(shift, "shift", g.a.C, g.out.dev, shift_ptr)) return e;
     }
     if (g.npix == 0) return 0;
+    if (a_subpixel && g.npix >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "sub-pixel source: more than 2^31 pixels");
     DeviceGuard guard(g.out.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g.out.dev, cudaGetErrorString(guard.err));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -123,6 +134,8 @@ int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, c
         p.npix = (uint64_t)g.npix;
         p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.pad = (uint32_t)pad_channels; p.ct = (uint32_t)ct;
         p.scale = scale_ptr; p.shift = shift_ptr;
+        p.sub_w = a_subpixel ? (uint32_t)(g.out.W / 2) : 0;
+        p.div_w2 = FastDiv((uint32_t)(g.out.W ? g.out.W : 1));
         p.tile_px = (uint32_t)P;
         p.div_ca = FastDiv(p.ca);
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
@@ -132,20 +145,20 @@ int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, c
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
         concat_allow_smem(concat_fwd_kernel<T>, smem);
         concat_fwd_kernel<T><<<concat_blocks(concat_fwd_kernel<T>, smem, ntiles), kConcatThreads, smem, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "concat_fwd<%s,%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", scale_ptr ? "+affine" : "", p.ca,
-                 p.cb, p.np, p.pad);
+        snprintf(tl_kernel, sizeof(tl_kernel), "concat_fwd<%s,%s%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", scale_ptr ? "+affine" : "",
+                 p.sub_w ? "+subpixel" : "", p.ca, p.cb, p.np, p.pad);
         return check_launch("btslpg_concat_forward");
     };
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
 }
 
-int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, BtsTensor *g_b, BtsTensor *const *g_planes,
-                           int n_planes, int pad_channels, void *stream) {
+int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, int a_subpixel, BtsTensor *g_b,
+                           BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream) {
     if (!g_a) return fail(BTSLPG_EINVAL, "g_a: tensor is NULL");
     if (act != 0 && act != 1) return fail(BTSLPG_EINVAL, "act must be 0 (none) or 1 (elu)");
     if (pad_channels < 0 || pad_channels > 7) return fail(BTSLPG_EINVAL, "pad_channels must be in [0, 7]");
     ConcatGeom g;
-    if (int e = parse_concat(g_a, g_b, g_planes, n_planes, g_out, "g_a", "g_b", "g_planes", "g_out", g)) return e;
+    if (int e = parse_concat(g_a, g_b, g_planes, n_planes, g_out, "g_a", "g_b", "g_planes", "g_out", g, a_subpixel != 0)) return e;
     const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes + pad_channels;
     if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "g_out: last dimension must be %lld (= CA + CB + n_planes + pad_channels), got %lld", (long long)ct, (long long)g.out.C);
     View yv;
@@ -158,6 +171,7 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         if (!is_contig_nhwc(yv) || !yv.aligned(16)) return fail(BTSLPG_ELAYOUT, "y: must be contiguous and 16-byte aligned");
     }
     if (g.npix == 0) return 0;
+    if (a_subpixel && g.npix >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "sub-pixel source: more than 2^31 pixels");
     DeviceGuard guard(g.out.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", g.out.dev, cudaGetErrorString(guard.err));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -174,6 +188,8 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         for (int k = 0; k < n_planes; ++k) p.g_plane[k] = g_planes[k] ? reinterpret_cast<T *>(g.plane[k].ptr) : nullptr;
         p.npix = (uint64_t)g.npix;
         p.ca = (uint32_t)g.a.C; p.cb = g.has_b ? (uint32_t)g.b.C : 0; p.np = (uint32_t)n_planes; p.pad = (uint32_t)pad_channels; p.ct = (uint32_t)ct;
+        p.sub_w = a_subpixel ? (uint32_t)(g.out.W / 2) : 0;
+        p.div_w2 = FastDiv((uint32_t)(g.out.W ? g.out.W : 1));
         p.tile_px = (uint32_t)P;
         p.div_ca = FastDiv(p.ca);
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
@@ -183,7 +199,7 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
         concat_allow_smem(concat_bwd_kernel<T>, smem);
         concat_bwd_kernel<T><<<concat_blocks(concat_bwd_kernel<T>, smem, ntiles), kConcatThreads, smem, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.ca, p.cb, p.np, p.pad);
+        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.sub_w ? "+subpixel" : "", p.ca, p.cb, p.np, p.pad);
         return check_launch("btslpg_concat_backward");
     };
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});

@@ -49,6 +49,12 @@ template <typename T> struct ConcatParams {
     FastDiv div_ca, div_cb;
     int act;                            // 1: ELU(alpha = 1) on source a (Keras activation='elu')
     int vec;                            // CA and CB are multiples of the 16-byte vector width: dense sources use vector accesses
+    // Sub-pixel source (sub_w > 0): `a` (and g_a) is the output of a 3x3 convolution run on the LOW-RES input with 4*CA
+    // output channels ordered (row parity, column parity, channel) -- algebraically the nearest-x2 up-sampling followed by
+    // the 3x3 upconv (bts_decoder.py:97-98), without the up-sampled tensor ever existing.  Its memory is (B, h, w, 2, 2, CA);
+    // the concat's pixel (Y, X) reads [row Y/2][col X/2][Y%2][X%2][:], i.e. the pixel shuffle happens in this kernel's addressing.
+    uint32_t sub_w;                     // low-res width w (output width 2w); 0 = plain NHWC source
+    FastDiv div_w2;                     // 2w
 };
 
 // Keras / TF elu: x > 0 ? x : expm1(x).  expm1 for x <= 0 in ~12 branch-free instructions instead of libm's
@@ -115,6 +121,13 @@ template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(co
     }
 }
 
+// element offset of channel 0 of output pixel q (flat index over B * 2h * 2w) in the un-shuffled (B,h,w,2,2,CA) tensor
+template <typename T> __device__ __forceinline__ size_t subpixel_offset(const ConcatParams<T> &prm, uint64_t q) {
+    uint32_t rowY, X;
+    prm.div_w2.divmod((uint32_t)q, rowY, X);
+    return (((size_t)(rowY >> 1) * prm.sub_w + (X >> 1)) * 4 + ((rowY & 1) << 1 | (X & 1))) * prm.ca;
+}
+
 template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_fwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
     extern __shared__ __align__(16) unsigned char concat_smem[];
     T *img = reinterpret_cast<T *>(concat_smem);
@@ -135,7 +148,30 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_f
         const uint32_t npx = (uint32_t)min((uint64_t)P, prm.npix - p0);
         const bool full_out = (npx % 8) == 0;          // vector paths need 16-byte granular runs
         const bool full = full_out && prm.vec;
-        if (full) {
+        if (prm.sub_w) {                               // source a in the un-shuffled sub-pixel layout (CA % V == 0 checked on the host)
+            constexpr int V = 16 / (int)sizeof(T);
+            for (uint32_t i = threadIdx.x * V; i < npx * prm.ca; i += kConcatThreads * V) {
+                uint32_t p, c;
+                prm.div_ca.divmod(i, p, c);
+                float v[V];
+                load_elems<T, V, 4>(prm.a + subpixel_offset(prm, p0 + p) + c, v);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float x = prm.act ? elu_fwd(v[e]) : v[e];
+                    if (aff) x = fmaf(x, aff[c + e], aff[prm.ca + c + e]);
+                    smem_put<T>(img, p * ct + c + e, x);
+                }
+            }
+            if (prm.b) {
+                if (full) scatter_dense<T, false>(prm.b + p0 * prm.cb, img, npx, prm.cb, prm.div_cb, ct, prm.ca);
+                else
+                    for (uint32_t i = threadIdx.x; i < npx * prm.cb; i += kConcatThreads) {
+                        uint32_t p, c;
+                        prm.div_cb.divmod(i, p, c);
+                        smem_put<T>(img, p * ct + prm.ca + c, load1(prm.b + p0 * prm.cb + i));
+                    }
+            }
+        } else if (full) {
             if (prm.act) scatter_dense<T, true>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0, aff);
             else scatter_dense<T, false>(prm.a + p0 * prm.ca, img, npx, prm.ca, prm.div_ca, ct, 0, aff);
             if (prm.b) scatter_dense<T, false>(prm.b + p0 * prm.cb, img, npx, prm.cb, prm.div_cb, ct, prm.ca);
@@ -191,7 +227,20 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_b
             }
         }
         __syncthreads();
-        if (prm.g_a) {
+        if (prm.g_a && prm.sub_w) {                       // gradient in the un-shuffled sub-pixel layout
+            const uint32_t n = npx * prm.ca;
+            for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
+                uint32_t p, c;
+                prm.div_ca.divmod(i, p, c);
+                float v[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float g = smem_get<T>(gimg, p * ct + c + e);
+                    v[e] = prm.act ? g * elu_grad_from_output(smem_get<T>(yimg, p * ct + c + e)) : g;
+                }
+                store_elems<T, V, 4>(prm.g_a + subpixel_offset(prm, p0 + p) + c, v);
+            }
+        } else if (prm.g_a) {
             if (full) {
                 const uint32_t n = npx * prm.ca;
                 for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {

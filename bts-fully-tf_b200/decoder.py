@@ -238,10 +238,19 @@ class BtsDecoder(nn.Module):
 
         # bts_decoder.py:98-99: upconv1's ELU and concat1 = [upconv1, d2, d4, d8] as ONE pass (ops.concat_nhwc):
         # the raw conv output is read once and the F/16+3 channel NHWC pixel written once, LPG planes in their slots
-        up1_raw = self.upconv1(_upsample2x(iconv2))
-        up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
-        pad1 = ops.pad_to(up1_nhwc.shape[-1] + 3)                          # 35 -> 36 channels
-        concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
+        # bts_decoder.py:97-98 without the up-sampled tensor: UpSampling2D(2) + Conv2D(3x3) == the 3x3 conv on the LOW-RES
+        # iconv2 with 4*Cout combined kernels (ops.subpixel_kernel) + a pixel shuffle, which the concat kernel does in its
+        # addressing.  cuDNN: forward 0.77 -> 0.48 ms, forward+backward 3.0 -> 1.7 ms (B = 16, 352x1216).
+        nf1 = self.upconv1.weight.shape[0]
+        pad1 = ops.pad_to(nf1 + 3)                                         # 35 -> 36 channels
+        if nf1 % 4 == 0:
+            up4 = F.conv2d(iconv2, ops.subpixel_kernel(self.upconv1.weight), padding=1)       # (B, 4*nf1, H/2, W/2)
+            up4_nhwc = _nhwc_view(up4.contiguous(memory_format=torch.channels_last))
+            concat1 = _to_nchw(ops.concat_nhwc(up4_nhwc, [d2, d4, d8], act=True, pad=pad1, a_subpixel=True))
+        else:
+            up1_raw = self.upconv1(_upsample2x(iconv2))
+            up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
+            concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
         iconv1 = F.elu(_conv_padded_input(self.iconv1, concat1, pad1))
         if torch.is_grad_enabled() and iconv1.shape[1] in (16, 32):
             # bts_decoder.py:102: library forward, ONE hand-written pass for both gradients (ops.depth_conv)

@@ -367,35 +367,40 @@ def _tensor_ptr_array(refs):
     return arr
 
 
-def concat_forward(a, planes=(), b=None, act=False, out=None, pad=0, scale=None, shift=None):
+def concat_forward(a, planes=(), b=None, act=False, out=None, pad=0, scale=None, shift=None, a_subpixel=False):
     """out[..., :CA] = affine(elu(a) if act else a) ; out[..., CA:CA+CB] = b ; one channel per plane ; `pad` zero
-    channels.  affine (scale, shift: float32 [CA], optional) is an inference-mode BatchNormalization folded in.  One kernel."""
+    channels.  affine (scale, shift: float32 [CA], optional) is an inference-mode BatchNormalization folded in.
+    a_subpixel: `a` is (B,H/2,W/2,4*CA), the upconv evaluated on the low-res input (see subpixel_kernel).  One kernel."""
     lib = load()
-    B, H, W, ca = a.shape
+    if a_subpixel:
+        B, H, W, ca = a.shape[0], 2 * a.shape[1], 2 * a.shape[2], a.shape[3] // 4
+    else:
+        B, H, W, ca = a.shape
     cb = b.shape[-1] if b is not None else 0
     if out is None:
         out = torch.empty((B, H, W, ca + cb + len(planes) + pad), dtype=a.dtype, device=a.device)
     ra, rb, ro, rs, rt = as_ref(a), as_ref(b), as_ref(out), as_ref(scale), as_ref(shift)
     rp = [as_ref(p) for p in planes]
-    check(lib.btslpg_concat_forward(ra.ptr, 1 if act else 0, ptr_or_null(rs), ptr_or_null(rt), ptr_or_null(rb), _tensor_ptr_array(rp), len(rp),
-                                    int(pad), ro.ptr, current_stream_ptr(a.device)))
+    check(lib.btslpg_concat_forward(ra.ptr, 1 if a_subpixel else 0, 1 if act else 0, ptr_or_null(rs), ptr_or_null(rt), ptr_or_null(rb),
+                                    _tensor_ptr_array(rp), len(rp), int(pad), ro.ptr, current_stream_ptr(a.device)))
     return out
 
 
-def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=None, pad=0):
-    """Split d concat into (g_a [* elu'(y)], g_b, [g_plane ...]); entries not needed come back as None."""
+def concat_backward(g_out, y, act, ca, cb, n_planes, need_b=True, need_planes=None, pad=0, a_subpixel=False):
+    """Split d concat into (g_a [* elu'(y)], g_b, [g_plane ...]); entries not needed come back as None.
+    a_subpixel: g_a comes back as (B,H/2,W/2,4*CA), the layout of the low-res upconv's output."""
     lib = load()
     B, H, W, _ = g_out.shape
     need_planes = [True] * n_planes if need_planes is None else list(need_planes)
-    g_a = torch.empty((B, H, W, ca), dtype=g_out.dtype, device=g_out.device)
+    g_a = torch.empty((B, H // 2, W // 2, 4 * ca) if a_subpixel else (B, H, W, ca), dtype=g_out.dtype, device=g_out.device)
     g_b = torch.empty((B, H, W, cb), dtype=g_out.dtype, device=g_out.device) if (cb and need_b) else None
     g_p = [torch.empty((B, H, W, 1), dtype=g_out.dtype, device=g_out.device) if need_planes[k] else None for k in range(n_planes)]
     if cb and not need_b:
         raise ValueError("concat_backward: the kernel needs g_b's geometry; pass need_b=True when CB > 0")
     rg, ry, ra, rb = as_ref(g_out), as_ref(y if act else None), as_ref(g_a), as_ref(g_b)
     rp = [as_ref(p) for p in g_p]
-    check(lib.btslpg_concat_backward(rg.ptr, ptr_or_null(ry), 1 if act else 0, ra.ptr, ptr_or_null(rb), _tensor_ptr_array(rp), n_planes, int(pad),
-                                     current_stream_ptr(g_out.device)))
+    check(lib.btslpg_concat_backward(rg.ptr, ptr_or_null(ry), 1 if act else 0, ra.ptr, 1 if a_subpixel else 0, ptr_or_null(rb),
+                                     _tensor_ptr_array(rp), n_planes, int(pad), current_stream_ptr(g_out.device)))
     return g_a, g_b, g_p
 
 
@@ -403,11 +408,12 @@ class ConcatFunction(torch.autograd.Function):
     """(a, b-or-None, planes...) -> NHWC concat with the activation of `a` fused and `pad` zero channels appended."""
 
     @staticmethod
-    def forward(ctx, a, b, act, pad, *planes):
+    def forward(ctx, a, b, act, pad, a_subpixel, *planes):
         a_c = a.contiguous()
         b_c = b.contiguous() if b is not None else None
-        out = concat_forward(a_c, [p.contiguous() for p in planes], b_c, act, pad=pad)
-        ctx.act, ctx.pad, ctx.ca, ctx.cb, ctx.np = act, pad, a_c.shape[-1], (b_c.shape[-1] if b_c is not None else 0), len(planes)
+        out = concat_forward(a_c, [p.contiguous() for p in planes], b_c, act, pad=pad, a_subpixel=a_subpixel)
+        ctx.act, ctx.pad, ctx.sub = act, pad, a_subpixel
+        ctx.ca, ctx.cb, ctx.np = a_c.shape[-1] // (4 if a_subpixel else 1), (b_c.shape[-1] if b_c is not None else 0), len(planes)
         if act:
             ctx.save_for_backward(out)          # elu' is taken from the output: nothing else is kept alive
         return out
@@ -416,14 +422,32 @@ class ConcatFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
         y = ctx.saved_tensors[0] if ctx.act else None
-        need_planes = [ctx.needs_input_grad[4 + k] for k in range(ctx.np)]
-        g_a, g_b, g_p = concat_backward(g_out.contiguous(), y, ctx.act, ctx.ca, ctx.cb, ctx.np, need_b=True, need_planes=need_planes, pad=ctx.pad)
-        return (g_a, g_b, None, None) + tuple(g_p)
+        need_planes = [ctx.needs_input_grad[5 + k] for k in range(ctx.np)]
+        g_a, g_b, g_p = concat_backward(g_out.contiguous(), y, ctx.act, ctx.ca, ctx.cb, ctx.np, need_b=True, need_planes=need_planes, pad=ctx.pad,
+                                        a_subpixel=ctx.sub)
+        return (g_a, g_b, None, None, None) + tuple(g_p)
 
 
-def concat_nhwc(a, planes=(), b=None, act=False, pad=0):
+def concat_nhwc(a, planes=(), b=None, act=False, pad=0, a_subpixel=False):
     """Fused `Concatenate(axis=3)([act(a), b, *planes])` (+ `pad` zero channels) with autograd (bts_decoder.py:98-99, :42)."""
-    return ConcatFunction.apply(a, b, bool(act), int(pad), *planes)
+    return ConcatFunction.apply(a, b, bool(act), int(pad), bool(a_subpixel), *planes)
+
+
+_subpixel_R = {}
+
+
+def subpixel_kernel(weight):
+    """Kernel of the 3x3 upconv evaluated on the LOW-RES input: OIHW (Cout,Cin,3,3) -> (4*Cout,Cin,3,3), output channels
+    ordered (row parity, column parity, o).  UpSampling2D(2,'nearest') + Conv2D(3x3,'same') (bts_decoder.py:97-98) equals this
+    convolution followed by a pixel shuffle: an even output row sees low-res rows (y-1: w0), (y: w1+w2), an odd one
+    (y: w0+w1), (y+1: w2); same for columns.  Differentiable (a fixed linear map of the weights)."""
+    key = (weight.device, weight.dtype)
+    R = _subpixel_R.get(key)
+    if R is None:       # built once per device (a host-to-device copy: not allowed while a CUDA graph is being captured)
+        R = torch.tensor([[[1, 0, 0], [0, 1, 1], [0, 0, 0]], [[0, 0, 0], [1, 1, 0], [0, 0, 1]]], dtype=weight.dtype).to(weight.device)
+        _subpixel_R[key] = R
+    cout, cin = weight.shape[:2]
+    return torch.einsum("aik,bjl,ockl->abocij", R, R, weight).reshape(4 * cout, cin, 3, 3)
 
 
 def pad_to(channels, multiple=4):

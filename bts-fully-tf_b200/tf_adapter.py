@@ -207,7 +207,7 @@ def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
             ra, ro = _ref(a_), _ref(out)
             rp = [_ref(t) for t in (p0_, p1_, p2_)]
             arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
-            _cabi.check(lib.btslpg_concat_forward(ra.ptr, 1, None, None, None, arr, 3, 0, ro.ptr, ctypes.c_void_p(0)))
+            _cabi.check(lib.btslpg_concat_forward(ra.ptr, 0, 1, None, None, None, arr, 3, 0, ro.ptr, ctypes.c_void_p(0)))
             return out
 
         y = tf.py_function(fwd, [a, p0, p1, p2], a.dtype)
@@ -221,7 +221,7 @@ def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
                 rg, ry, rga = _ref(g_), _ref(y_), _ref(g_a)
                 rp = [_ref(t) for t in g_p]
                 arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
-                _cabi.check(lib.btslpg_concat_backward(rg.ptr, ry.ptr, 1, rga.ptr, None, arr, 3, 0, ctypes.c_void_p(0)))
+                _cabi.check(lib.btslpg_concat_backward(rg.ptr, ry.ptr, 1, rga.ptr, 0, None, arr, 3, 0, ctypes.c_void_p(0)))
                 return [g_a] + g_p
             outs = tf.py_function(bwd, [g_out, y], [a.dtype] * 4)
             outs[0].set_shape(a.shape)

@@ -211,6 +211,10 @@ BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_p
  * and, with act = 0, the conv_block concat [upconv, skip, lpg_ds] of bts_decoder.py:42 -- one pass
  * instead of a separate ELU pass plus a re-copy of every input.  Channel order = argument order.
  *   a       (B,H,W,CA)  dense source; act = 1 applies ELU(alpha=1) to it on the way (0 = identity)
+ *   a_subpixel  != 0: `a` is instead (B,H/2,W/2,4*CA), the output of the 3x3 upconv evaluated on the LOW-RES input with
+ *           4*CA output channels ordered (row parity, column parity, channel) -- algebraically UpSampling2D(2,'nearest') +
+ *           Conv2D(3x3) (bts_decoder.py:97-98) without the up-sampled tensor; the pixel shuffle is done by this kernel's
+ *           addressing (and g_a of the backward comes back in the same layout)
  *   scale, shift  float32 [CA], nullable (together): per-channel affine on `a` AFTER the activation -- an
  *           inference-mode BatchNormalization folded in (bts_decoder.py:33-34 / :40-41: upconv -> elu -> BN -> concat);
  *           forward only (the backward entry point differentiates the un-affined form)
@@ -226,11 +230,12 @@ BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_p
  * output y (required iff act = 1: y > 0 ? 1 : y + 1), g_b and g_planes[k] are slices of g_out.
  * g_b / g_planes[k] may be NULL to skip them; the pad channels' gradient is dropped.
  * ------------------------------------------------------------------------------------------- */
-BTSLPG_API int btslpg_concat_forward(const BtsTensor *a, int act, const BtsTensor *scale, const BtsTensor *shift,
-                                     const BtsTensor *b, const BtsTensor *const *planes, int n_planes,
-                                     int pad_channels, BtsTensor *out, void *stream);
-BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, BtsTensor *g_b,
-                                      BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream);
+BTSLPG_API int btslpg_concat_forward(const BtsTensor *a, int a_subpixel, int act, const BtsTensor *scale,
+                                     const BtsTensor *shift, const BtsTensor *b, const BtsTensor *const *planes,
+                                     int n_planes, int pad_channels, BtsTensor *out, void *stream);
+BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, int a_subpixel,
+                                      BtsTensor *g_b, BtsTensor *const *g_planes, int n_planes, int pad_channels,
+                                      void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the

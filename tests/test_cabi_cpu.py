@@ -105,11 +105,11 @@ def test_argument_validation_of_the_decoder_glue_entry_points(lib):
     out = fake_cuda(torch.rand(1, 4, 4, 9))
     plane = fake_cuda(torch.rand(1, 4, 4, 1))
     arr = (_cabi._TP * 1)(plane.ptr)
-    assert lib.btslpg_concat_forward(x.ptr, 2, None, None, None, arr, 1, 0, out.ptr, None) == -1            # act out of range
-    assert lib.btslpg_concat_forward(x.ptr, 0, None, None, None, arr, 1, 9, out.ptr, None) == -1            # pad out of range
-    assert lib.btslpg_concat_forward(x.ptr, 0, x.ptr, None, None, arr, 1, 0, out.ptr, None) == -1           # scale without shift
+    assert lib.btslpg_concat_forward(x.ptr, 0, 2, None, None, None, arr, 1, 0, out.ptr, None) == -1            # act out of range
+    assert lib.btslpg_concat_forward(x.ptr, 0, 0, None, None, None, arr, 1, 9, out.ptr, None) == -1            # pad out of range
+    assert lib.btslpg_concat_forward(x.ptr, 0, 0, x.ptr, None, None, arr, 1, 0, out.ptr, None) == -1           # scale without shift
     wide = fake_cuda(torch.rand(1, 4, 4, 12))
-    assert lib.btslpg_concat_forward(x.ptr, 0, None, None, None, arr, 1, 0, wide.ptr, None) == -3           # out must be CA + planes + pad wide
+    assert lib.btslpg_concat_forward(x.ptr, 0, 0, None, None, None, arr, 1, 0, wide.ptr, None) == -3           # out must be CA + planes + pad wide
     big = fake_cuda(torch.rand(1, 8, 9, 8))
     assert lib.btslpg_upsample2x_forward(x.ptr, big.ptr, None) == -3                                         # (B, 2h, 2w, C)
     assert lib.btslpg_affine_act(x.ptr, None, None, 3, x.ptr, None) == -1                                    # act out of range

@@ -105,6 +105,38 @@ def test_concat_pad_and_folded_batchnorm(B, H, W, ca, cb, n_planes, pad, dtype):
         np.testing.assert_array_equal(npf(pd[k].grad), gp[k])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,h,w,cin,cout,pad", [(2, 4, 6, 8, 8, 1), (1, 5, 7, 16, 32, 1), (1, 3, 3, 4, 16, 0)])
+def test_subpixel_source_equals_upsample_then_conv(B, h, w, cin, cout, pad, dtype):
+    """UpSampling2D(2) + Conv2D(3x3) + ELU + concat  ==  low-res conv with ops.subpixel_kernel + concat(a_subpixel=True),
+    forward and every gradient (bts_decoder.py:97-99)."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(cin + cout)
+        x = torch.randn(B, cin, h, w, generator=g).to(DEV)
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.2).to(DEV)
+        planes = [torch.randn(B, 2 * h, 2 * w, 1, generator=g).to(dtype).to(DEV) for _ in range(3)]
+        g_out = torch.randn(B, 2 * h, 2 * w, cout + 3 + pad, generator=g).to(dtype).to(DEV)
+        # reference form (float32 convs, the concat in `dtype`)
+        x1, w1 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        up = F.conv2d(F.interpolate(x1, scale_factor=2, mode="nearest"), w1, padding=1).permute(0, 2, 3, 1).to(dtype)
+        ref = ops.concat_nhwc(up, planes, act=True, pad=pad)
+        ref.backward(g_out)
+        # sub-pixel form
+        x2, w2 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        up4 = F.conv2d(x2, ops.subpixel_kernel(w2), padding=1).permute(0, 2, 3, 1).to(dtype)
+        out = ops.concat_nhwc(up4, planes, act=True, pad=pad, a_subpixel=True)
+        assert "+subpixel" in ops.last_kernel()
+        out.backward(g_out)
+        tol = 2e-5 if dtype == torch.float32 else 2e-2
+        assert float((out - ref).abs().max()) <= tol * float(ref.abs().max())
+        assert float((x2.grad - x1.grad).abs().max()) <= tol * float(x1.grad.abs().max())
+        assert float((w2.grad - w1.grad).abs().max()) <= tol * float(w1.grad.abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 def test_concat_full_size_properties():
     """B=8 480x640 (1/4 of BASELINE config 2): channel-slot identities at a size the CPU oracle does not need to see."""
     B, H, W, ca = 8, 480, 640, 32
