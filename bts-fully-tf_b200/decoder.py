@@ -71,23 +71,28 @@ class _ConvBlock(nn.Module):
     channels to a multiple of 4 so that cuDNN does not re-copy the tensor; in inference mode that pass also applies
     the ELU of the upconv and the folded BatchNormalization."""
 
-    def __init__(self, cin, cskip, clpg, nf):
+    def __init__(self, cin, cskip, clpg, nf, subpixel_inference=False):
         super().__init__()
         self.upconv = _conv(cin, nf)
         self.bn = _bn(nf)
         self.iconv = _conv(nf + cskip + clpg, nf)
         self.pad = ops.pad_to(nf + cskip + clpg)
+        # inference: evaluate the upconv on the low-res input (ops.subpixel_kernel) where cuDNN gains from it (block2: 0.76 -> 0.57 ms)
+        self.subpixel_inference = bool(subpixel_inference) and nf % 4 == 0
 
     def forward(self, x, skip_nhwc, lpg_nhwc=None):
-        up = self.upconv(_upsample2x(x))                                # linear output of the upconv
         planes = [lpg_nhwc] if lpg_nhwc is not None else []            # order is load-bearing (bts_decoder.py:42)
         if not self.training and not torch.is_grad_enabled():
             scale, shift = _bn_affine(self.bn)
+            if self.subpixel_inference:
+                up = F.conv2d(x, ops.subpixel_kernel(self.upconv.weight), padding=1)
+            else:
+                up = self.upconv(_upsample2x(x))
             cat = ops.concat_forward(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, skip_nhwc.contiguous(), act=True,
-                                     pad=self.pad, scale=scale, shift=shift)
-        else:
-            up = self.bn(F.elu(up))
-            cat = ops.concat_nhwc(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, b=skip_nhwc, act=False, pad=self.pad)
+                                     pad=self.pad, scale=scale, shift=shift, a_subpixel=self.subpixel_inference)
+            return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
+        up = self.bn(F.elu(self.upconv(_upsample2x(x))))               # training / autograd: BatchNorm needs its batch statistics
+        cat = ops.concat_nhwc(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, b=skip_nhwc, act=False, pad=self.pad)
         return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
 
 
@@ -141,7 +146,7 @@ class BtsDecoder(nn.Module):
         self.block3 = _ConvBlock(c_daspp, c4, 1, nf)              # iconv3, H/4
         self.reduction_4x4 = ReductionLPG(nf, 4, ds_stride=2, name="reduction_4x4")
         nf //= 2
-        self.block2 = _ConvBlock(nf * 2, c2, 1, nf)               # iconv2, H/2
+        self.block2 = _ConvBlock(nf * 2, c2, 1, nf, subpixel_inference=True)   # iconv2, H/2
         self.reduction_2x2 = ReductionLPG(nf, 2, ds_stride=0, name="reduction_2x2")
         c_iconv2 = nf
         nf //= 2
