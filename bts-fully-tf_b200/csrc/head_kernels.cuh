@@ -266,7 +266,6 @@ template <typename T, int R, int M, bool FWD> struct FeatRing {
 template <typename T, int R, int D, int M>
 __global__ void __launch_bounds__(256) head_lpg_fwd_tma_kernel(const __grid_constant__ HeadFwdParams<T> prm) {
     using Cfg = HeadTmaCfg<T, R, M, true>;
-    constexpr int C = 32 * M;
     constexpr int NDS = D ? R / D : 0;
     extern __shared__ __align__(128) unsigned char head_smem[];
 
