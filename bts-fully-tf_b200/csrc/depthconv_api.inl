@@ -1,4 +1,4 @@
-// depthconv_api.inl -- C ABI for the backward of the last convolution (bts_decoder.py:102); included by btslpg_api.cu.
+// depthconv_api.inl -- C ABI for the forward and the backward of the last convolution (bts_decoder.py:102); included by btslpg_api.cu.
 
 extern "C" {
 
@@ -71,6 +71,57 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
     };
     if (xv.dtype == kF32) return C == 32 ? go(float{}, IntC<32>{}) : go(float{}, IntC<16>{});
     return C == 32 ? go(__nv_bfloat16{}, IntC<32>{}) : go(__nv_bfloat16{}, IntC<16>{});
+}
+
+int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int act_in, int act_out, float out_scale, BtsTensor *y, void *stream) {
+    View xv, yv;
+    if (int e = parse_nhwc(x, "x", xv)) return e;
+    const int C = (int)xv.C;
+    if (C != 16 && C != 32) return fail(BTSLPG_ESHAPE, "x: %d channels; the fused forward is built for C = 16 and C = 32 (F/16 of the reference's encoders)", C);
+    if (!is_contig_nhwc(xv) || !xv.aligned(16)) return fail(BTSLPG_ELAYOUT, "x: must be a contiguous, 16-byte aligned NHWC tensor");
+    if (act_in != 0 && act_in != 1) return fail(BTSLPG_EINVAL, "act_in: %d (0 none, 1 ELU)", act_in);
+    if (act_out != 0 && act_out != 1) return fail(BTSLPG_EINVAL, "act_out: %d (0 none, 1 sigmoid * out_scale)", act_out);
+    int64_t ny = 0;
+    if (!y) return fail(BTSLPG_EINVAL, "y: tensor is NULL");
+    if (int e = parse_flat(y, "y", yv, ny)) return e;
+    if (yv.B != xv.B || yv.H != xv.H || yv.W != xv.W) return fail(BTSLPG_ESHAPE, "y: (B,H,W) differs from x");
+    if (yv.dtype != xv.dtype) return fail(BTSLPG_EDTYPE, "y: dtype differs from x");
+    if (yv.dev != xv.dev) return fail(BTSLPG_EDEVICE, "y: on a different device than x");
+    float *w = nullptr;
+    if (!kernel) return fail(BTSLPG_EINVAL, "kernel: tensor is NULL");
+    if (int e = parse_f32_vec(kernel, "kernel", 9 * C, xv.dev, w)) return e;
+    const int64_t npix = xv.B * xv.H * xv.W;
+    if (npix == 0) return 0;
+    if (npix * C >= ((int64_t)1 << 31) * 4) return fail(BTSLPG_ESHAPE, "x: too large");
+    const int64_t tiles_x = (xv.W + kDfTile - 1) / kDfTile, tiles_y = (xv.H + kDfTile - 1) / kDfTile;
+    if (xv.B * tiles_x * tiles_y >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "x: too many tiles");
+    DeviceGuard guard(xv.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", xv.dev, cudaGetErrorString(guard.err));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto go = [&](auto tag, auto ctag, auto etag) -> int {
+        using T = decltype(tag);
+        constexpr int CC = decltype(ctag)::value;
+        constexpr bool ELU = decltype(etag)::value != 0;
+        DepthConvFwdParams<T> p;
+        p.x = reinterpret_cast<const T *>(xv.ptr);
+        p.w = w;
+        p.y = reinterpret_cast<T *>(yv.ptr);
+        p.H = (uint32_t)xv.H; p.W = (uint32_t)xv.W;
+        p.tiles_x = (uint32_t)tiles_x;
+        p.items = (uint32_t)(xv.B * tiles_x * tiles_y);
+        p.div_tx = FastDiv((uint32_t)tiles_x);
+        p.div_ty = FastDiv((uint32_t)tiles_y);
+        p.act_out = act_out;
+        p.out_scale = out_scale;
+        static const int resident = occupancy_blocks_smem(depthconv_fwd_kernel<T, CC, ELU>, kDfThreads, 0);
+        const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
+        depthconv_fwd_kernel<T, CC, ELU><<<blocks, kDfThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");
+        return check_launch("btslpg_depthconv_forward");
+    };
+    auto by_act = [&](auto tag, auto ctag) -> int { return act_in ? go(tag, ctag, IntC<1>{}) : go(tag, ctag, IntC<0>{}); };
+    if (xv.dtype == kF32) return C == 32 ? by_act(float{}, IntC<32>{}) : by_act(float{}, IntC<16>{});
+    return C == 32 ? by_act(__nv_bfloat16{}, IntC<32>{}) : by_act(__nv_bfloat16{}, IntC<16>{});
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "tail_kernels.cuh"   // tail_sigmoid
 
 namespace btslpg {
 
@@ -169,6 +170,185 @@ template <typename T, int C> __global__ void __launch_bounds__(kDcThreads, 2) de
         __threadfence();
         dc_reduce_partials(prm.partial, gridDim.x, NCOL4, prm.g_w, reinterpret_cast<float4 *>(&red[0][0]));
         if (threadIdx.x == 0) *prm.counter = 0u;      // leave the workspace header zero for the next launch
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward of the same layer with its neighbours folded in (bts_decoder.py:100-103):
+//     iconv1           = Conv2D(F/16, 3, activation='elu')(concat1)      # :100  -- only the ACTIVATION is taken over
+//     depth_est_scaled = Conv2D(1, 3, padding='same', use_bias=False, activation='sigmoid')(iconv1)      # :102
+//     depth_est        = depth_est_scaled * max_depth                                                     # :103
+// The library path is four passes over full-resolution maps: ELU (read + write of the (B,H,W,F/16) map), a layout
+// conversion of that map (cuDNN has no NHWC kernel for ONE output channel), the convolution, and the sigmoid -- about
+// 1.1 ms at B = 32, 480x640 for a layer whose floor is 0.1 ms (the raw conv output read once, one float per pixel written).
+// Here x is read ONCE:
+//   phase 1  every pixel of a 32x32 output tile plus its one-pixel halo gets its nine per-tap dot products
+//            P[t][q] = sum_c elu(x[q][c]) * w[t][c].  Four lanes share a pixel (C/4 channels each: a warp instruction
+//            fetches whole 32-byte sectors), the lane's 9 x C/4 weights stay in registers as packed pairs (FFMA2: two
+//            channels per instruction), the four partial sums are combined by a fixed xor tree (reduce-scatter, so a
+//            lane ends with the taps it stores) and land in shared memory, tap-major.  Pixels outside the image give
+//            P = 0 (padding='same' pads the ACTIVATED map with zeros; elu(0) = 0).
+//   phase 2  y[p] = sum_t P[t][p + t] in tap order, then the optional sigmoid * max_depth, one coalesced store per row.
+// FP32 FMAs on purpose: 2.25 FMA per input byte is under the machine balance, and TF32 would miss the 1e-5 budget.
+// The ELU inside the sum is x > 0 ? x : ex2(x*log2e) - 1 (4 instructions per element instead of the 13 of the
+// expm1 form used where ELU values are an OUTPUT): its absolute error (<= 2.4e-7 per activation) enters a 9*C-term sum
+// of |w| ~ 0.1 products, i.e. < 1e-6 relative to the logit's scale.
+// Algorithmic bytes per pixel: (C + 1) * sizeof(T).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDfTile = 32;                        // output tile edge
+constexpr int kDfHalo = kDfTile + 2;
+constexpr int kDfNQ = kDfHalo * kDfHalo;           // 1156 halo pixels; 1156 % 32 == 4, so the four tap rows a warp stores
+constexpr int kDfThreads = 256;                    //   (taps b, b+2, b+4, b+6 for 8 consecutive pixels) fall on 32 distinct banks
+
+template <typename T> struct DepthConvFwdParams {
+    const T *x;          // (B,H,W,C) contiguous
+    const float *w;      // [9][C]
+    T *y;                // (B,H,W) contiguous
+    uint32_t H, W, tiles_x, items;
+    FastDiv div_tx, div_ty;
+    int act_out;         // 1: sigmoid(y) * out_scale
+    float out_scale;
+};
+
+// channel of element j (0 <= j < C/4) of lane-in-pixel s: float32 lanes interleave 16-byte chunks (chunk k of lane s =
+// channels [16k + 4s, +4): each load instruction covers 64 contiguous bytes of the pixel), bfloat16 lanes own C/4
+// contiguous channels (8 or 16 bytes)
+template <typename T, int C> __device__ __forceinline__ int dcf_channel(int s, int j) {
+    if constexpr (sizeof(T) == 4) return (j >> 2) * 16 + 4 * s + (j & 3);
+    else return (C / 4) * s + j;
+}
+template <typename T, int C> __device__ __forceinline__ void dcf_load(const T *px, int s, float (&v)[C / 4]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+            float t[4];
+            load_elems<T, 4>(px + 16 * k + 4 * s, t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * k + e] = t[e];
+        }
+    } else {
+        load_elems<T, C / 4>(px + (C / 4) * s, v);
+    }
+}
+
+__device__ __forceinline__ float elu_in_sum(float x, float em1) { return x > 0.0f ? x : em1; }
+
+template <typename T, int C, bool ELU>
+__global__ void __launch_bounds__(kDfThreads, 2) depthconv_fwd_kernel(const __grid_constant__ DepthConvFwdParams<T> prm) {
+    constexpr int CPL = C / 4;                 // channels per lane: 8 or 4
+    constexpr int NP2 = CPL / 2;               // packed pairs
+    constexpr int NW = kDfThreads / 32;
+    constexpr int NPASS = (kDfNQ + 7) / 8;     // warp passes of 8 halo pixels
+    __shared__ float P[9 * kDfNQ];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = lane & 3, pl = lane >> 2;
+    const bool h2 = s & 2, h1 = s & 1;
+    const int tap0 = (h2 ? 4 : 0) + (h1 ? 2 : 0);   // after the reduce-scatter the lane holds taps tap0, tap0 + 1
+
+    F2 wr[9][NP2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < NP2; ++j)
+            wr[t][j] = f2(__ldg(prm.w + t * C + dcf_channel<T, C>(s, 2 * j)), __ldg(prm.w + t * C + dcf_channel<T, C>(s, 2 * j + 1)));
+
+    for (uint32_t item = blockIdx.x; item < prm.items; item += gridDim.x) {
+        uint32_t rest, tx, b, ty;
+        prm.div_tx.divmod(item, rest, tx);
+        prm.div_ty.divmod(rest, b, ty);
+        const int y0 = (int)(ty * kDfTile) - 1, x0 = (int)(tx * kDfTile) - 1;      // image coordinates of halo pixel (0, 0)
+        const T *img = prm.x + (size_t)b * prm.H * prm.W * C;
+
+        // One halo pixel per lane group and pass, software-pipelined: the loads of the warp's next pass are issued before the
+        // current one is used (two 32-byte requests per lane in flight; the 72 weight registers leave room for no more).
+        auto fetch = [&](int pass, float (&v)[CPL]) -> int {
+            const int q = pass * 8 + pl;
+            const int hr = q / kDfHalo, hc = q - hr * kDfHalo;
+            const int gy = y0 + hr, gx = x0 + hc;
+            if (q < kDfNQ && gy >= 0 && gy < (int)prm.H && gx >= 0 && gx < (int)prm.W) {
+                dcf_load<T, C>(img + ((size_t)gy * prm.W + gx) * C, s, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) v[j] = 0.0f;      // outside the image: P = 0 (elu(0) = 0); beyond the tile: not stored
+            }
+            return q;
+        };
+        float cur[CPL];
+        int qc = fetch(wid, cur);
+#pragma unroll 2
+        for (int pass = wid; pass < NPASS; pass += NW) {
+            float nxt[CPL];
+            const int qn = fetch(pass + NW, nxt);
+            F2 xe[NP2];
+#pragma unroll
+            for (int j = 0; j < NP2; ++j) {
+                float a0 = cur[2 * j], a1 = cur[2 * j + 1];
+                if constexpr (ELU) {
+                    float t0, t1, e0, e1, m0, m1;
+                    unpack(mul2(f2(a0, a1), f2(1.442695040888963407f)), t0, t1);
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+                    unpack(add2(f2(e0, e1), f2(-1.0f)), m0, m1);
+                    a0 = elu_in_sum(a0, m0);
+                    a1 = elu_in_sum(a1, m1);
+                }
+                xe[j] = f2(a0, a1);
+            }
+            float a[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                F2 acc = mul2(xe[0], wr[t][0]);
+#pragma unroll
+                for (int j = 1; j < NP2; ++j) acc = fma2(xe[j], wr[t][j], acc);
+                a[t] = lo(acc) + hi(acc);
+            }
+            // four lanes -> one: reduce-scatter over xor 2, xor 1 (fixed order), tap 8 by a plain butterfly
+            float b4[4], c2[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float send = h2 ? a[j] : a[j + 4];
+                const float keep = h2 ? a[j + 4] : a[j];
+                b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float send = h1 ? b4[j] : b4[j + 2];
+                const float keep = h1 ? b4[j + 2] : b4[j];
+                c2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            float a8 = a[8];
+            a8 += __shfl_xor_sync(0xffffffffu, a8, 2);
+            a8 += __shfl_xor_sync(0xffffffffu, a8, 1);
+            if (qc < kDfNQ) {
+                P[tap0 * kDfNQ + qc] = c2[0];
+                P[(tap0 + 1) * kDfNQ + qc] = c2[1];
+                if (s == 0) P[8 * kDfNQ + qc] = a8;
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) cur[j] = nxt[j];
+            qc = qn;
+        }
+        __syncthreads();
+        // phase 2: thread -> column (threadIdx & 31), rows (threadIdx >> 5) + 8 k
+        {
+            const int col = threadIdx.x & 31;
+            const int gx = x0 + 1 + col;
+#pragma unroll
+            for (int k = 0; k < kDfTile / NW; ++k) {
+                const int row = (threadIdx.x >> 5) + NW * k;
+                const int gy = y0 + 1 + row;
+                if (gx < (int)prm.W && gy < (int)prm.H) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) acc += P[(dy * 3 + dx) * kDfNQ + (row + dy) * kDfHalo + col + dx];
+                    if (prm.act_out) acc = tail_sigmoid(acc) * prm.out_scale;
+                    store1(prm.y + ((size_t)b * prm.H + gy) * prm.W + gx, acc);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -256,14 +256,22 @@ class BtsDecoder(nn.Module):
             up1_raw = self.upconv1(_upsample2x(iconv2))
             up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
             concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
-        iconv1 = F.elu(_conv_padded_input(self.iconv1, concat1, pad1))
-        if torch.is_grad_enabled() and iconv1.shape[1] in (16, 32):
-            # bts_decoder.py:102: library forward, ONE hand-written pass for both gradients (ops.depth_conv)
+        iconv1_raw = _conv_padded_input(self.iconv1, concat1, pad1)
+        self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
+                              "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
+        fused_tail = iconv1_raw.shape[1] in (16, 32)
+        if fused_tail and not torch.is_grad_enabled():
+            # bts_decoder.py:100-103 in ONE pass over the raw conv output: iconv1's ELU, the last Conv2D(1, 3x3) and,
+            # unless the logit is asked for, sigmoid * max_depth (ops.depthconv_forward)
+            x = _nhwc_view(iconv1_raw.contiguous(memory_format=torch.channels_last))
+            return ops.depthconv_forward(x, ops.kernel9c(self.depth_conv.weight), act_in=True,
+                                         sigmoid_scale=None if return_logit else self.max_depth)
+        iconv1 = F.elu(iconv1_raw)
+        if fused_tail:
+            # bts_decoder.py:102 with autograd: hand-written forward, ONE hand-written pass for both gradients (ops.depth_conv)
             logit = _to_nchw(ops.depth_conv(_nhwc_view(iconv1.contiguous(memory_format=torch.channels_last)), self.depth_conv.weight))
         else:
             logit = self.depth_conv(iconv1)                                            # (B,1,H,W): same memory as NHWC (B,H,W,1)
-        self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
-                              "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
         if return_logit:
             return _nhwc_view(logit)
         if not torch.is_grad_enabled():                                                # bts_decoder.py:102-103 in one pass

@@ -513,7 +513,7 @@ def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
 
 
 # ---------------------------------------------------------------------------------------------
-# last convolution Conv2D(1, 3x3, 'same'): library forward, fused hand-written backward
+# last convolution Conv2D(1, 3x3, 'same'): hand-written forward (with the neighbouring ELU / sigmoid folded in) and backward
 # ---------------------------------------------------------------------------------------------
 def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True):
     """x (B,H,W,C) NHWC, kernel9c float32 [9*C] ([tap][c] == Keras HWIO (3,3,C,1)), g_out (B,H,W,1).
@@ -530,22 +530,38 @@ def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True):
     return g_x, g_k
 
 
+def kernel9c(weight):
+    """torch OIHW (1,C,3,3) conv weight -> float32 [9*C] in Keras HWIO (3,3,C,1) memory order ([ky][kx][c])."""
+    return weight.detach().permute(2, 3, 1, 0).reshape(-1).float().contiguous()
+
+
+def depthconv_forward(x, kernel9c, act_in=False, sigmoid_scale=None, out=None):
+    """bts_decoder.py:100-103 in one pass: y = conv3x3_same(elu(x) if act_in else x) (one output channel), then
+    sigmoid(y) * sigmoid_scale when a scale is given.  x (B,H,W,C) contiguous NHWC, C in (16, 32); kernel9c float32
+    [9*C] ([tap][c] == Keras HWIO (3,3,C,1)).  Returns (B,H,W,1).  No autograd (see depth_conv)."""
+    lib = load()
+    y = out if out is not None else torch.empty(x.shape[:3] + (1,), dtype=x.dtype, device=x.device)
+    rx, rk, ry = as_ref(x), as_ref(kernel9c), as_ref(y)
+    check(lib.btslpg_depthconv_forward(rx.ptr, rk.ptr, int(bool(act_in)), int(sigmoid_scale is not None),
+                                       float(sigmoid_scale if sigmoid_scale is not None else 1.0), ry.ptr, current_stream_ptr(x.device)))
+    return y
+
+
 class DepthConvFunction(torch.autograd.Function):
-    """x NHWC (B,H,W,C), weight torch OIHW (1,C,3,3) -> (B,H,W,1).  Forward: the library convolution (at its HBM floor
-    already); backward: one hand-written pass for both gradients."""
+    """x NHWC (B,H,W,C), weight torch OIHW (1,C,3,3) -> (B,H,W,1): hand-written forward (exact float32) and one
+    hand-written pass for both gradients."""
 
     @staticmethod
     def forward(ctx, x_nhwc, weight):
-        y = torch.nn.functional.conv2d(x_nhwc.permute(0, 3, 1, 2), weight, padding=1)          # (B,1,H,W): NHWC memory as well
+        x_nhwc = x_nhwc.contiguous()
         ctx.save_for_backward(x_nhwc, weight)
-        return y.permute(0, 2, 3, 1)
+        return depthconv_forward(x_nhwc, kernel9c(weight))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
         x, weight = ctx.saved_tensors
-        k9c = weight.detach().permute(2, 3, 1, 0).reshape(-1).float().contiguous()              # OIHW -> [ky][kx][c] == HWIO flattened
-        g_x, g_k = depthconv_backward(x.contiguous(), k9c, g_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g_x, g_k = depthconv_backward(x, kernel9c(weight), g_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         g_w = None
         if g_k is not None:
             C = x.shape[-1]

@@ -271,11 +271,28 @@ BTSLPG_API int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, c
  *   g_x      (B,H,W,C)  d loss / d x, nullable
  *   g_kernel float32 [9*C] d loss / d kernel in the same layout, nullable; reduced deterministically through
  *            `workspace` (btslpg_depthconv_backward_workspace_bytes(C) bytes, first 256 zeroed once)
- * Exact float32 arithmetic.  The forward of this layer stays on the library convolution (already at its floor).
+ * Exact float32 arithmetic.
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API size_t btslpg_depthconv_backward_workspace_bytes(int channels);
 BTSLPG_API int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, BtsTensor *g_x,
                                          BtsTensor *g_kernel, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward of the same layer with its neighbours folded in -- bts_decoder.py:100-103
+ *     iconv1           = Conv2D(F/16, 3, activation='elu')(concat1)          only the ACTIVATION (act_in = 1)
+ *     depth_est_scaled = Conv2D(1, 3, padding='same', use_bias=False, activation='sigmoid')(iconv1)
+ *     depth_est        = depth_est_scaled * max_depth                        (act_out = 1, out_scale = max_depth)
+ * in ONE pass over the raw output of iconv1's convolution (the library path: ELU pass, NHWC->NCHW conversion,
+ * convolution, sigmoid pass -- about 1.1 ms at B = 32, 480x640 against a 0.1 ms traffic floor):
+ *   x        (B,H,W,C)  C = 16 or 32, contiguous NHWC; the PRE-activation map when act_in = 1
+ *   kernel   float32, 9*C elements, Keras HWIO (3,3,C,1) as it lies in memory ([tap][c])
+ *   act_in   0 none, 1 ELU(alpha = 1) applied to x inside the sum (padding='same' pads the activated map with zeros)
+ *   act_out  0: y = the convolution (the logit; training / fused loss), 1: y = sigmoid(conv) * out_scale
+ *   y        (B,H,W[,1]) contiguous, same dtype as x
+ * Exact float32 FMAs in a fixed order (bit-reproducible); see csrc/depthconv_kernels.cuh for the ELU error bound.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int act_in, int act_out, float out_scale,
+                                        BtsTensor *y, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued

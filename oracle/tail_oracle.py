@@ -143,6 +143,21 @@ def depthconv_forward(x, w9c):
     return y[..., None]
 
 
+def depth_tail_forward(x_raw, w9c, act_in=True, max_depth=None):
+    """bts_decoder.py:100-103 downstream of iconv1's convolution, float64:
+        iconv1 = elu(x_raw)                                  (:100 activation='elu'; Keras elu = x > 0 ? x : expm1(x))
+        logit  = Conv2D(1, 3, padding='same', use_bias=False)(iconv1)         (:102, zero padding of the ACTIVATED map)
+        depth  = sigmoid(logit) * max_depth                  (:102 activation='sigmoid', :103) -- when max_depth is given
+    """
+    x = np.asarray(x_raw, np.float64)
+    if act_in:
+        x = np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    y = depthconv_forward(x, w9c)
+    if max_depth is not None:
+        y = max_depth / (1.0 + np.exp(-y))
+    return y
+
+
 def depthconv_backward(x, w9c, g_out):
     """Gradients of depthconv_forward: (g_x (B,H,W,C), g_w (9, C)), float64."""
     x = np.asarray(x, np.float64)

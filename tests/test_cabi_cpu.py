@@ -118,6 +118,16 @@ def test_argument_validation_of_the_decoder_glue_entry_points(lib):
     k = fake_cuda(torch.rand(72))
     assert lib.btslpg_depthconv_backward(x.ptr, k.ptr, g.ptr, x.ptr, None, None, 0, None) == -3              # C must be 16 or 32
     assert b"C = 16 and C = 32" in lib.btslpg_last_error()
+    y1 = fake_cuda(torch.rand(1, 4, 4, 1))
+    assert lib.btslpg_depthconv_forward(x.ptr, k.ptr, 1, 1, 10.0, y1.ptr, None) == -3                        # C must be 16 or 32
+    x32 = fake_cuda(torch.rand(1, 4, 4, 32))
+    k288 = fake_cuda(torch.rand(288))
+    assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 2, 0, 1.0, y1.ptr, None) == -1                    # act_in out of range
+    assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 1, 3, 1.0, y1.ptr, None) == -1                    # act_out out of range
+    assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 1, 1, 1.0, None, None) == -1                      # y missing
+    assert lib.btslpg_depthconv_forward(x32.ptr, k.ptr, 1, 1, 1.0, y1.ptr, None) == -3                       # kernel needs 9*C floats
+    host = _cabi.from_torch(torch.rand(1, 4, 4, 32))
+    assert lib.btslpg_depthconv_forward(host.ptr, k288.ptr, 1, 1, 1.0, y1.ptr, None) < 0                     # host tensor: no CPU fallback
     yt = fake_cuda(torch.rand(1, 4, 4, 1))
     assert lib.btslpg_silog_forward(None, None, 10.0, 0.1, yt.ptr, None, None, 0, None) == -1                # nothing to compute
     assert lib.btslpg_silog_forward(yt.ptr, yt.ptr, 10.0, 0.1, yt.ptr, None, None, 0, None) == -1            # loss tensor missing

@@ -1,4 +1,5 @@
-"""GPU tests of the fused backward of the decoder's last convolution (bts_decoder.py:102) through the C ABI."""
+"""GPU tests of the decoder's last convolution (bts_decoder.py:100-103) through the C ABI: the fused forward
+(ELU of iconv1 + Conv2D(1, 3x3) + sigmoid * max_depth in one pass) and the fused backward (both gradients in one pass)."""
 import numpy as np
 import pytest
 import torch
@@ -58,7 +59,7 @@ def test_depth_conv_autograd_matches_library_convolution(C):
     conv.weight.grad = None
     y2 = conv(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     y2.backward(g)
-    assert torch.equal(y, y2)
+    assert float((y - y2).abs().max()) <= 2e-6 * float(y2.abs().max())                  # both exact float32, different summation order
     assert float((gx - x.grad).abs().max()) <= 2e-6 * float(x.grad.abs().max())
     assert float((gw - conv.weight.grad).abs().max()) <= 1e-5 * float(conv.weight.grad.abs().max())
     # forward against the oracle too (Keras HWIO (3,3,C,1) == [tap][c])
@@ -91,3 +92,91 @@ def test_depthconv_errors():
         ops.depthconv_backward(x, torch.zeros(288, device=DEV), torch.zeros(1, 4, 5, 1, device=DEV))
     with pytest.raises(ValueError, match="at least"):
         ops.depthconv_backward(x, torch.zeros(100, device=DEV), torch.zeros(1, 4, 4, 1, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------
+# forward: bts_decoder.py:100-103 in one pass
+# ---------------------------------------------------------------------------------------------
+FWD_SHAPES = [(1, 1, 1), (2, 3, 5), (1, 7, 37), (2, 33, 65), (1, 32, 32), (1, 31, 34), (1, 64, 96), (3, 40, 130)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [16, 32])
+@pytest.mark.parametrize("B,H,W", FWD_SHAPES)
+def test_depthconv_forward_vs_oracle(B, H, W, C, dtype):
+    g = torch.Generator().manual_seed(H * 1000 + W + C)
+    x = (torch.randn(B, H, W, C, generator=g) * 1.5).to(dtype)
+    w9c = torch.randn(9 * C, generator=g) * 0.2
+    name = "f32" if dtype == torch.float32 else "bf16"
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7          # bfloat16: one rounding of the output
+    for act_in in (False, True):
+        ref = T.depth_tail_forward(npf(x), w9c.numpy(), act_in=act_in)
+        y = ops.depthconv_forward(x.to(DEV), w9c.to(DEV), act_in=act_in)
+        assert ops.last_kernel() == "depthconv_fwd<%s,C%d,%s>" % (name, C, "elu" if act_in else "lin")
+        assert y.shape == (B, H, W, 1)
+        assert np.abs(npf(y) - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), (act_in, np.abs(npf(y) - ref).max())
+        y2 = ops.depthconv_forward(x.to(DEV), w9c.to(DEV), act_in=act_in)
+        assert torch.equal(y, y2)                                                        # fixed summation order
+    ref = T.depth_tail_forward(npf(x), w9c.numpy(), act_in=True, max_depth=10.0)         # sigmoid * max_depth (NYU)
+    d = ops.depthconv_forward(x.to(DEV), w9c.to(DEV), act_in=True, sigmoid_scale=10.0)
+    np.testing.assert_allclose(npf(d), ref, rtol=1e-5 if dtype == torch.float32 else 2 ** -7, atol=1e-6)
+
+
+def test_depthconv_forward_elu_extremes():
+    """ELU inside the sum at its corners: 0, tiny negatives (expm1 regime), large negatives (-> -1), large positives."""
+    C = 32
+    vals = torch.tensor([0.0, -0.0, -1e-8, -1e-4, -0.3, -0.35, -1.0, -20.0, -200.0, 1e-8, 3.0, 50.0])
+    x = vals.repeat(C * 9 * 4)[:4 * 9 * C].view(1, 4, 9, C).contiguous()
+    w9c = torch.linspace(-0.3, 0.3, 9 * C)
+    ref = T.depth_tail_forward(npf(x), w9c.numpy(), act_in=True)
+    y = ops.depthconv_forward(x.to(DEV), w9c.to(DEV), act_in=True)
+    assert np.abs(npf(y) - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("C", [16, 32])
+def test_depthconv_forward_matches_library_path(C):
+    """The op-by-op library path the kernel replaces: F.elu -> conv2d (TF32 off) -> sigmoid * max_depth."""
+    torch.manual_seed(C)
+    B, H, W = 2, 96, 160
+    x = torch.randn(B, H, W, C, device=DEV)
+    conv = torch.nn.Conv2d(C, 1, 3, padding=1, bias=False).to(DEV)
+    with torch.no_grad():
+        ref = torch.sigmoid(conv(F.elu(x.permute(0, 3, 1, 2)))).permute(0, 2, 3, 1) * 80.0
+        d = ops.depthconv_forward(x, ops.kernel9c(conv.weight), act_in=True, sigmoid_scale=80.0)
+    assert float((d - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_depthconv_forward_full_size_properties():
+    """B=8 480x640 C=32 (the oracle takes minutes there): linear in the kernel and in x without activations, exact tap
+    selection with one-hot kernels, deterministic, and equal to the library convolution."""
+    B, H, W, C = 8, 480, 640, 32
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(B, H, W, C, device=DEV, generator=g)
+    w = torch.randn(9 * C, device=DEV, generator=g) * 0.1
+    y1 = ops.depthconv_forward(x, w)
+    assert torch.equal(ops.depthconv_forward(x, w * 2), y1 * 2) and torch.equal(ops.depthconv_forward(x * 2, w), y1 * 2)
+    assert torch.equal(ops.depthconv_forward(x, w), y1)
+    for tap, c in ((0, 0), (4, 17), (8, 31), (2, 5), (6, 30)):
+        onehot = torch.zeros(9 * C, device=DEV)
+        onehot[tap * C + c] = 1.0
+        dy, dx = tap // 3 - 1, tap % 3 - 1
+        ref = torch.zeros(B, H, W, device=DEV)
+        ys, xs = slice(max(0, -dy), H - max(0, dy)), slice(max(0, -dx), W - max(0, dx))
+        yd, xd = slice(max(0, dy), H - max(0, -dy)), slice(max(0, dx), W - max(0, -dx))
+        ref[:, ys, xs] = x[:, yd, xd, c]
+        assert torch.equal(ops.depthconv_forward(x, onehot)[..., 0], ref), (tap, c)
+    lib = F.conv2d(F.elu(x.permute(0, 3, 1, 2)), w.view(3, 3, C, 1).permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    y2 = ops.depthconv_forward(x, w, act_in=True)
+    assert float((y2 - lib).abs().max()) <= 1e-5 * float(lib.abs().max())
+
+
+def test_depthconv_forward_errors():
+    x = torch.zeros(1, 4, 4, 32, device=DEV)
+    with pytest.raises(ValueError, match="built for C = 16 and C = 32"):
+        ops.depthconv_forward(torch.zeros(1, 4, 4, 8, device=DEV), torch.zeros(72, device=DEV))
+    with pytest.raises(ValueError, match="at least"):
+        ops.depthconv_forward(x, torch.zeros(100, device=DEV))
+    with pytest.raises(ValueError, match="differs from x"):
+        ops.depthconv_forward(x, torch.zeros(288, device=DEV), out=torch.zeros(1, 4, 5, 1, device=DEV))
+    with pytest.raises(ValueError, match="contiguous"):
+        ops.depthconv_forward(torch.zeros(1, 4, 4, 64, device=DEV)[..., :32], torch.zeros(288, device=DEV))

@@ -242,3 +242,17 @@ def test_depthconv_guard_bands(B, H, W, C, dtype):
     tol = 2e-6 if dtype == torch.float32 else 2 ** -7
     assert np.abs(npf(g_x) - ref_gx).max() <= tol * max(np.abs(ref_gx).max(), 1e-30)
     assert np.abs(npf(g_k).reshape(9, C) - ref_gw).max() <= 1e-5 * max(np.abs(ref_gw).max(), 1e-30)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,C", [(1, 1, 1, 16), (2, 3, 5, 32), (1, 2, 131, 32), (1, 33, 35, 16), (2, 31, 65, 32)])
+def test_depthconv_forward_guard_bands(B, H, W, C, dtype):
+    g = torch.Generator().manual_seed(W + C)
+    x = torch.randn(B, H, W, C, generator=g).to(dtype)
+    w = torch.randn(9 * C, generator=g) * 0.2
+    A = Arena()
+    out = A.output((B, H, W, 1), dtype)
+    ops.depthconv_forward(A.input(x), A.input(w), act_in=True, sigmoid_scale=10.0, out=out)
+    A.check()
+    ref = tail_oracle.depth_tail_forward(npf(x), w.numpy(), act_in=True, max_depth=10.0)
+    np.testing.assert_allclose(npf(out), ref, rtol=1e-5 if dtype == torch.float32 else 2 ** -7, atol=1e-6)

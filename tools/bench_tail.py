@@ -106,6 +106,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="plain launches (for ncu)")
     ap.add_argument("--skip-literal", action="store_true")
     ap.add_argument("--skip-concat", action="store_true")
+    ap.add_argument("--skip-depthconv", action="store_true")
+    ap.add_argument("--only-depthconv", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     dtype = torch.float32 if a.dtype == "f32" else torch.bfloat16
@@ -139,7 +141,9 @@ def main():
     for i in range(a.sets):
         fwd(i)
     ops.reset_launch_count()
-    for name, fn, maps in (("silog_fwd", fwd, 3), ("silog_bwd", bwd, 3), ("eval_metrics", met, 2)):
+    if a.only_depthconv:
+        a.skip_concat = a.skip_cpu = True
+    for name, fn, maps in (() if a.only_depthconv else (("silog_fwd", fwd, 3), ("silog_bwd", bwd, 3), ("eval_metrics", met, 2))):
         us = time_gpu(fn, a.sets, a.steps, a.warmup, graph=not a.no_graph)
         nbytes = maps * n * es
         res[name] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
@@ -176,10 +180,38 @@ def main():
             res["concat1_speedup"] = round(us_l / (res["concat1_fwd"]["us"] + res["concat1_bwd"]["us"]), 2)
         del csets, g_cat
         torch.cuda.empty_cache()
+    # last convolution forward with iconv1's ELU and sigmoid * max_depth folded in (bts_decoder.py:100-103), C = F/16
+    if not a.skip_depthconv:
+        for cdc in (32, 16):
+            dsets = [dict(x=torch.randn(a.batch, a.height, a.width, cdc, generator=g, device=dev).to(dtype),
+                          y=torch.empty(shape, device=dev, dtype=dtype)) for _ in range(2 if cdc == 32 else 4)]
+            w9c = (torch.rand(9 * cdc, generator=g, device=dev) - 0.5) * 0.28
+            us = time_gpu(lambda i: ops.depthconv_forward(dsets[i]["x"], w9c, act_in=True, sigmoid_scale=md, out=dsets[i]["y"]), len(dsets),
+                          max(8, a.steps // 4), 2, graph=not a.no_graph)
+            nbytes = (cdc + 1) * n * es
+            key = "depthconv_fwd_C%d" % cdc
+            res[key] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
+                        "kernel": ops.last_kernel()}
+            if a.dtype == "f32" and not a.skip_literal:
+                wt = w9c.view(3, 3, cdc, 1).permute(3, 2, 0, 1).contiguous()
+                xs = [d["x"].permute(0, 3, 1, 2) for d in dsets]              # NCHW views of channels_last memory, as in the decoder
+
+                def lib_path(i):
+                    with torch.no_grad():
+                        return torch.sigmoid(torch.nn.functional.conv2d(torch.nn.functional.elu(xs[i]), wt, padding=1)) * md
+                torch.backends.cudnn.benchmark = True
+                us_l = time_gpu(lib_path, len(dsets), 8, 3, graph=False)
+                res[key]["library_path_us"] = round(us_l, 1)
+                res[key]["speedup"] = round(us_l / us, 2)
+                ref = lib_path(0).permute(0, 2, 3, 1)
+                ops.depthconv_forward(dsets[0]["x"], w9c, act_in=True, sigmoid_scale=md, out=dsets[0]["y"])
+                res[key]["max_abs_diff_vs_library_tf32"] = float((dsets[0]["y"] - ref).abs().max())
+            del dsets
+            torch.cuda.empty_cache()
     launches = ops.launch_count()
 
     # the same work as torch ops on the GPU (a port without custom kernels)
-    if a.dtype == "f32" and not a.skip_literal:
+    if a.dtype == "f32" and not a.skip_literal and not a.only_depthconv:
         lit_f = time_gpu(lambda i: literal_silog(sets[i]["logit"], sets[i]["y_true"], md, th), a.sets, max(3, a.steps // 5), 2, graph=False)
         lit_m = time_gpu(lambda i: literal_metrics(sets[i]["y_true"], sets[i]["depth"], lo, hi), a.sets, max(3, a.steps // 5), 2, graph=False)
         res["torch_gpu_literal"] = {"silog_fwd_bwd_us": round(lit_f, 1), "eval_metrics_us": round(lit_m, 1),

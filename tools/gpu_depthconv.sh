@@ -1,0 +1,10 @@
+#!/bin/bash
+# GPU session for the fused last-convolution forward: parity tests, micro-benchmark, one ncu capture, decoder config 3
+mkdir -p gpurun_out
+python -m pytest tests/test_depthconv_gpu.py tests/test_decoder_gpu.py "tests/test_guard_bands_gpu.py" -k "depthconv or decoder" -m gpu -q -x --timeout 600 > gpurun_out/pytest_dcf.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/pytest_dcf.log
+python tools/bench_tail.py --only-depthconv > gpurun_out/dcf_f32.json 2> gpurun_out/dcf_f32.err; rc=$?; echo "dcf f32 exit $rc"; cat gpurun_out/dcf_f32.json; tail -3 gpurun_out/dcf_f32.err
+python tools/bench_tail.py --only-depthconv --dtype bf16 > gpurun_out/dcf_bf16.json 2> gpurun_out/dcf_bf16.err; echo "dcf bf16 exit $?"; cat gpurun_out/dcf_bf16.json
+if [ $rc -eq 0 ]; then
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:depthconv_fwd -c 1 -f -o gpurun_out/dcf_f32 python tools/bench_tail.py --only-depthconv --no-graph --skip-literal --steps 8 > gpurun_out/ncu_dcf.log 2>&1; echo "ncu exit $?"
+fi
+timeout 600 python tools/bench_decoder.py --config 3 --steps 5 --warmup 3 > gpurun_out/decoder_cfg3.jsonl 2> gpurun_out/decoder_cfg3.err; echo "decoder exit $?"; cat gpurun_out/decoder_cfg3.jsonl | cut -c1-600
