@@ -113,10 +113,18 @@ int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int ac
         p.div_ty = FastDiv((uint32_t)tiles_y);
         p.act_out = act_out;
         p.out_scale = out_scale;
-        static const int resident = occupancy_blocks_smem(depthconv_fwd_kernel<T, CC, ELU>, kDfThreads, 0);
-        const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
-        depthconv_fwd_kernel<T, CC, ELU><<<blocks, kDfThreads, 0, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");
+        if (g_tune_depthconv_impl.load() == 1) {
+            static const int resident = occupancy_blocks_smem(depthconv_fwd_kernel<T, CC, ELU>, kDfThreads, 0);
+            const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
+            depthconv_fwd_kernel<T, CC, ELU><<<blocks, kDfThreads, 0, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd_fp32pipe<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");
+        } else {
+            constexpr int smem = DcfMmaCfg<T, CC>::kSmemBytes;
+            static const int resident = occupancy_blocks_smem(depthconv_fwd_mma_kernel<T, CC, ELU>, kDfThreads, smem);
+            const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
+            depthconv_fwd_mma_kernel<T, CC, ELU><<<blocks, kDfThreads, smem, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");
+        }
         return check_launch("btslpg_depthconv_forward");
     };
     auto by_act = [&](auto tag, auto ctag) -> int { return act_in ? go(tag, ctag, IntC<1>{}) : go(tag, ctag, IntC<0>{}); };

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "tail_kernels.cuh"   // tail_sigmoid
+#include "tma_pipe.cuh"       // smem_u32
 
 namespace btslpg {
 
@@ -233,6 +234,27 @@ template <typename T, int C> __device__ __forceinline__ void dcf_load(const T *p
 
 __device__ __forceinline__ float elu_in_sum(float x, float em1) { return x > 0.0f ? x : em1; }
 
+// phase 2: thread -> column (threadIdx & 31), rows (threadIdx >> 5) + 8 k;  y[p] = sum_t P[t][p + t] in tap order
+template <typename T> __device__ __forceinline__ void dcf_phase2(const DepthConvFwdParams<T> &prm, const float *P, uint32_t b, int y0, int x0) {
+    constexpr int NW = kDfThreads / 32;
+    const int col = threadIdx.x & 31;
+    const int gx = x0 + 1 + col;
+#pragma unroll
+    for (int k = 0; k < kDfTile / NW; ++k) {
+        const int row = (threadIdx.x >> 5) + NW * k;
+        const int gy = y0 + 1 + row;
+        if (gx < (int)prm.W && gy < (int)prm.H) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) acc += P[(dy * 3 + dx) * kDfNQ + (row + dy) * kDfHalo + col + dx];
+            if (prm.act_out) acc = tail_sigmoid(acc) * prm.out_scale;
+            store1(prm.y + ((size_t)b * prm.H + gy) * prm.W + gx, acc);
+        }
+    }
+}
+
 template <typename T, int C, bool ELU>
 __global__ void __launch_bounds__(kDfThreads, 2) depthconv_fwd_kernel(const __grid_constant__ DepthConvFwdParams<T> prm) {
     constexpr int CPL = C / 4;                 // channels per lane: 8 or 4
@@ -329,25 +351,239 @@ __global__ void __launch_bounds__(kDfThreads, 2) depthconv_fwd_kernel(const __gr
             qc = qn;
         }
         __syncthreads();
-        // phase 2: thread -> column (threadIdx & 31), rows (threadIdx >> 5) + 8 k
-        {
-            const int col = threadIdx.x & 31;
-            const int gx = x0 + 1 + col;
+        dcf_phase2<T>(prm, P, b, y0, x0);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 1 on the tensor cores.  ncu on the FP32-pipe kernel above (profiles/r01_depthconv_fwd_f32pipe.md): 24.5 warp
+// instructions per pixel, issue slots 52 % busy, FMA 37 % + ALU 36 %, DRAM 46 % -- the per-tap dot products are bound by
+// instruction issue (the C -> 9 contraction plus its cross-lane reduction), not by HBM: the case where the contraction
+// belongs on the tensor cores.  P[16 pixels x 8 taps] = X[16 x C] * W[C x 8] is one mma.sync.m16n8k8 per 8 channels;
+// float32 accuracy is kept by the 3xTF32 split (x = x_hi + x_lo, w = w_hi + w_lo, P = x_lo w_hi + x_hi w_lo + x_hi w_hi;
+// the dropped x_lo w_lo term and the truncation of the low parts are <= 2^-20 relative per product; accumulation is
+// float32).  bfloat16 inputs are exact TF32 values and need no x_lo term.  The ninth tap stays on the FP32 pipe (a
+// second n-tile would spend 12 more MMAs on one column).  The contraction index is order-free, so k-slot (j, tig) /
+// (j, tig + 4) of the fragments is mapped to the lane's OWN channels: a quad reads the pixel's 128 bytes with whole-sector
+// loads and no shuffle is needed anywhere -- the D fragment already has lane (g, tig) holding taps 2 tig, 2 tig + 1 of
+// pixels g and g + 8.  Fixed order, bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Asynchronous global -> shared copies (LDGSTS): a lane copies ITS OWN 8 / 16 bytes of a pixel into a lane-private slot
+// and reads the same slot back later, so no barrier is involved (cp.async.wait_group is per thread) and the LDS is
+// conflict-free by construction; src_bytes = 0 zero-fills the slot (padding='same').
+template <int BYTES> __device__ __forceinline__ void cp_async(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int V> struct IntC1 {
+    static constexpr int value = V;
+};
+
+#ifndef BTSLPG_DCF_MMA_MINB
+#define BTSLPG_DCF_MMA_MINB 2
+#endif
+#ifndef BTSLPG_DCF_STAGES
+#define BTSLPG_DCF_STAGES 4            // passes in the per-thread copy ring (STAGES - 1 in flight while one is consumed)
+#endif
+template <typename T, int C> struct DcfMmaCfg {
+    static constexpr int kLaneBytes = (C / 4) * (int)sizeof(T);          // bytes of a pixel one lane owns: 32, 16 or 8
+    static constexpr int kChunks = kLaneBytes > 16 ? kLaneBytes / 16 : 1;
+    static constexpr int kCopyBytes = kLaneBytes >= 16 ? 16 : 8;
+    static constexpr int kStageBytes = 2 * kChunks * kDfThreads * 16;    // two pixels per lane and pass, 16-byte slots
+    static constexpr int kPBytes = 9 * kDfNQ * 4;
+    static constexpr int kSmemBytes = kPBytes + BTSLPG_DCF_STAGES * kStageBytes;
+    static_assert(kPBytes % 16 == 0, "the copy ring must stay 16-byte aligned");
+};
+
+template <typename T, int C, bool ELU>
+__global__ void __launch_bounds__(kDfThreads, BTSLPG_DCF_MMA_MINB) depthconv_fwd_mma_kernel(const __grid_constant__ DepthConvFwdParams<T> prm) {
+    using Cfg = DcfMmaCfg<T, C>;
+    constexpr int CPL = C / 4;                 // channels per lane: a quad covers the pixel
+    constexpr int NJ = CPL / 2;                // k-steps of 8 channels (2 per lane)
+    constexpr bool SPLIT_X = sizeof(T) == 4;
+    constexpr int NW = kDfThreads / 32;
+    constexpr int NPASS = (kDfNQ + 15) / 16;   // warp passes of 16 halo pixels
+    constexpr int D = BTSLPG_DCF_STAGES;
+    extern __shared__ __align__(16) unsigned char dcf_smem[];
+    float *const P = reinterpret_cast<float *>(dcf_smem);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    float *const Pl = P + (2 * tig) * kDfNQ;   // the lane's tap rows 2 tig, 2 tig + 1
+    const uint32_t ring = smem_u32(dcf_smem + Cfg::kPBytes) + threadIdx.x * 16;       // this thread's slot 0 of stage 0
+    const unsigned char *const ring_g = dcf_smem + Cfg::kPBytes + threadIdx.x * 16;
+
+    // B fragments of taps 0..7 (n = g): k rows tig and tig + 4 of k-step j <-> channels dcf_channel(tig, 2j), (tig, 2j + 1)
+    uint32_t bh[NJ][2], bl[NJ][2];
+    F2 w8[NJ];
 #pragma unroll
-            for (int k = 0; k < kDfTile / NW; ++k) {
-                const int row = (threadIdx.x >> 5) + NW * k;
-                const int gy = y0 + 1 + row;
-                if (gx < (int)prm.W && gy < (int)prm.H) {
-                    float acc = 0.0f;
+    for (int j = 0; j < NJ; ++j) {
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
+        for (int h = 0; h < 2; ++h) {
+            const float w = __ldg(prm.w + g * C + dcf_channel<T, C>(tig, 2 * j + h));
+            bh[j][h] = to_tf32(w);
+            bl[j][h] = __float_as_uint(w - __uint_as_float(bh[j][h]));
+        }
+        w8[j] = f2(__ldg(prm.w + 8 * C + dcf_channel<T, C>(tig, 2 * j)), __ldg(prm.w + 8 * C + dcf_channel<T, C>(tig, 2 * j + 1)));
+    }
+    const int rowC = (int)prm.W * C;           // elements per image row
+    // byte offset of the lane's first chunk inside a pixel: float32 lanes interleave 16-byte chunks (see dcf_channel)
+    const int lane_off = sizeof(T) == 4 ? 16 * tig : Cfg::kLaneBytes * tig;
+
+    for (uint32_t item = blockIdx.x; item < prm.items; item += gridDim.x) {
+        uint32_t rest, tx, b, ty;
+        prm.div_tx.divmod(item, rest, tx);
+        prm.div_ty.divmod(rest, b, ty);
+        const int y0 = (int)(ty * kDfTile) - 1, x0 = (int)(tx * kDfTile) - 1;      // image coordinates of halo pixel (0, 0)
+        // a tile whose halo lies inside the image (most of them) runs the loop without any bounds logic
+        const bool interior = y0 >= 0 && x0 >= 0 && y0 + kDfHalo <= (int)prm.H && x0 + kDfHalo <= (int)prm.W;     // CTA-uniform
+        const unsigned char *img = reinterpret_cast<const unsigned char *>(prm.x + (size_t)b * prm.H * prm.W * C) + lane_off;
+
+        // copy the lane's share of halo pixel q (row-major in the 34 x 34 halo) into slot `sel` (0: D rows g, 1: rows g + 8)
+        // of stage `st`.  The address is clamped into the image (always legal); padding pixels are zero-filled by the
+        // copy itself (padding='same' pads the ACTIVATED map; elu(0) = 0).  q >= kDfNQ: past the tile, copied, never stored.
+        auto issue = [&](auto interior_tag, int st, int sel, int q) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value != 0;
+            const int hr = min(q / kDfHalo, kDfHalo - 1), hc = q - (q / kDfHalo) * kDfHalo;
+            int gy = y0 + hr, gx = x0 + hc;
+            uint32_t nbytes = Cfg::kCopyBytes;
+            if constexpr (!INTERIOR) {
+                if (gy < 0 || gy >= (int)prm.H || gx < 0 || gx >= (int)prm.W) nbytes = 0;
+                gy = max(0, min(gy, (int)prm.H - 1));
+                gx = max(0, min(gx, (int)prm.W - 1));
+            }
+            const unsigned char *src = img + (size_t)(gy * rowC + gx * C) * sizeof(T);
+            const uint32_t dst = ring + st * Cfg::kStageBytes + sel * (Cfg::kChunks * kDfThreads * 16);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) acc += P[(dy * 3 + dx) * kDfNQ + (row + dy) * kDfHalo + col + dx];
-                    if (prm.act_out) acc = tail_sigmoid(acc) * prm.out_scale;
-                    store1(prm.y + ((size_t)b * prm.H + gy) * prm.W + gx, acc);
+            for (int k = 0; k < Cfg::kChunks; ++k) cp_async<Cfg::kCopyBytes>(dst + k * (kDfThreads * 16), src + 64 * k, nbytes);
+        };
+        auto take = [&](int st, int sel, float (&v)[CPL]) {
+            const unsigned char *src = ring_g + st * Cfg::kStageBytes + sel * (Cfg::kChunks * kDfThreads * 16);
+            if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                for (int k = 0; k < Cfg::kChunks; ++k) {
+                    const float4 f = *reinterpret_cast<const float4 *>(src + k * (kDfThreads * 16));
+                    v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+                }
+            } else if constexpr (CPL == 8) {
+                const uint4 u = *reinterpret_cast<const uint4 *>(src);
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+            } else {
+                const uint2 u = *reinterpret_cast<const uint2 *>(src);
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+            }
+        };
+        auto activate = [&](float (&v)[CPL]) {
+            if constexpr (ELU) {
+#pragma unroll
+                for (int j = 0; j < CPL; j += 2) {
+                    float t0, t1, e0, e1, m0, m1;
+                    unpack(mul2(f2(v[j], v[j + 1]), f2(1.442695040888963407f)), t0, t1);
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+                    unpack(add2(f2(e0, e1), f2(-1.0f)), m0, m1);
+                    v[j] = elu_in_sum(v[j], m0);
+                    v[j + 1] = elu_in_sum(v[j + 1], m1);
                 }
             }
-        }
+        };
+        // one pass: halo pixel qa -> D rows g, qa + 8 -> D rows g + 8
+        auto process = [&](float (&ca)[CPL], float (&cb)[CPL], int qa) {
+            activate(ca);
+            activate(cb);
+            // three independent accumulator chains (x_hi w_hi, x_lo w_hi, x_hi w_lo): NJ dependent MMAs each
+            float big[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sx[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            F2 t8a, t8b;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                uint32_t ah[4], al[4];
+                const float xs[4] = {ca[2 * j], cb[2 * j], ca[2 * j + 1], cb[2 * j + 1]};   // a0 (g, tig), a1 (g+8, tig), a2 (g, tig+4), a3 (g+8, tig+4)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if constexpr (SPLIT_X) {
+                        ah[e] = __float_as_uint(xs[e]) & 0xffffe000u;          // truncation: x_lo < 2^-10 |x|, itself cut to TF32 by the MMA
+                        al[e] = __float_as_uint(xs[e] - __uint_as_float(ah[e]));
+                    } else {
+                        ah[e] = __float_as_uint(xs[e]);
+                    }
+                }
+                if constexpr (SPLIT_X) mma_tf32(sx, al, bh[j][0], bh[j][1]);
+                mma_tf32(sw, ah, bl[j][0], bl[j][1]);
+                mma_tf32(big, ah, bh[j][0], bh[j][1]);
+                const F2 xa = f2(ca[2 * j], ca[2 * j + 1]), xb = f2(cb[2 * j], cb[2 * j + 1]);
+                t8a = j == 0 ? mul2(xa, w8[0]) : fma2(xa, w8[j], t8a);
+                t8b = j == 0 ? mul2(xb, w8[0]) : fma2(xb, w8[j], t8b);
+            }
+            float s8a = lo(t8a) + hi(t8a), s8b = lo(t8b) + hi(t8b);
+            s8a += __shfl_xor_sync(0xffffffffu, s8a, 1);
+            s8b += __shfl_xor_sync(0xffffffffu, s8b, 1);
+            s8a += __shfl_xor_sync(0xffffffffu, s8a, 2);
+            s8b += __shfl_xor_sync(0xffffffffu, s8b, 2);
+            float d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] = SPLIT_X ? big[e] + (sx[e] + sw[e]) : big[e] + sw[e];
+            const int qb = qa + 8;
+            if (qa < kDfNQ) {
+                Pl[qa] = d[0];
+                Pl[kDfNQ + qa] = d[1];
+                if (tig == 0) P[8 * kDfNQ + qa] = s8a;
+            }
+            if (qb < kDfNQ) {
+                Pl[qb] = d[2];
+                Pl[kDfNQ + qb] = d[3];
+                if (tig == 0) P[8 * kDfNQ + qb] = s8b;
+            }
+        };
+
+        // per-thread copy ring: D - 1 passes in flight while one is consumed; nothing is held in registers meanwhile
+        auto run = [&](auto interior_tag) {
+            int qi = wid * 16 + g;                    // next pass to issue (pixel of D row g; row g + 8 is qi + 8)
+            int qc = qi;                              // next pass to consume
+#pragma unroll
+            for (int st = 0; st < D - 1; ++st) {
+                issue(interior_tag, st, 0, qi);
+                issue(interior_tag, st, 1, qi + 8);
+                cp_async_commit();
+                qi += NW * 16;
+            }
+            int st_in = D - 1, st_out = 0;
+#pragma unroll 1
+            for (int pass = wid; pass < NPASS; pass += NW) {
+                issue(interior_tag, st_in, 0, qi);    // unconditional: past the warp's last pass it re-reads a clamped address
+                issue(interior_tag, st_in, 1, qi + 8);
+                cp_async_commit();
+                qi += NW * 16;
+                st_in = st_in + 1 == D ? 0 : st_in + 1;
+                cp_async_wait<D - 1>();               // the copies of the pass consumed now have landed
+                float ca[CPL], cb[CPL];
+                take(st_out, 0, ca);
+                take(st_out, 1, cb);
+                st_out = st_out + 1 == D ? 0 : st_out + 1;
+                process(ca, cb, qc);
+                qc += NW * 16;
+            }
+        };
+        if (interior) run(IntC1<1>{}); else run(IntC1<0>{});
+        cp_async_wait<0>();                       // drain before the ring is reused by the next tile
+        __syncthreads();
+        dcf_phase2<T>(prm, P, b, y0, x0);
         __syncthreads();
     }
 }

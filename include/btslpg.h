@@ -289,7 +289,8 @@ BTSLPG_API int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *ke
  *   act_in   0 none, 1 ELU(alpha = 1) applied to x inside the sum (padding='same' pads the activated map with zeros)
  *   act_out  0: y = the convolution (the logit; training / fused loss), 1: y = sigmoid(conv) * out_scale
  *   y        (B,H,W[,1]) contiguous, same dtype as x
- * Exact float32 FMAs in a fixed order (bit-reproducible); see csrc/depthconv_kernels.cuh for the ELU error bound.
+ * float32-accurate (3xTF32 split on the tensor cores, float32 accumulation; csrc/depthconv_kernels.cuh has the error
+ * bounds), fixed order, bit-reproducible.
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int act_in, int act_out, float out_scale,
                                         BtsTensor *y, void *stream);
@@ -305,7 +306,8 @@ BTSLPG_API const char *btslpg_last_kernel(void);
 
 /* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default).
  * btslpg_set_tuning keys: 0 forward block threads, 1 backward block threads, 2 float32 r=8 patch rows
- * per lane (2/4/8), 3 float32 r=4 coarse pixels per thread (1/2).  Results do not depend on them,
+ * per lane (2/4/8), 3 float32 r=4 coarse pixels per thread (1/2), 9 last-convolution forward (0 tensor-core
+ * phase 1 with the 3xTF32 split, 1 FP32 pipe).  Results do not depend on them beyond float32 rounding,
  * except that the r=8 backward sum is associated per lane group (still deterministic). */
 BTSLPG_API void btslpg_set_block_threads(int fwd_threads, int bwd_threads);
 BTSLPG_API void btslpg_set_tuning(int key, int value);

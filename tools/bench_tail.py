@@ -192,6 +192,11 @@ def main():
             key = "depthconv_fwd_C%d" % cdc
             res[key] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "GBps": round(nbytes / us * 1e-3, 1), "frac_of_peak": round(nbytes / us * 1e-3 / pk, 4),
                         "kernel": ops.last_kernel()}
+            ops.set_tuning(9, 1)
+            us1 = time_gpu(lambda i: ops.depthconv_forward(dsets[i]["x"], w9c, act_in=True, sigmoid_scale=md, out=dsets[i]["y"]), len(dsets),
+                           max(8, a.steps // 4), 2, graph=not a.no_graph)
+            res[key]["fp32pipe_us"] = round(us1, 2)
+            ops.set_tuning(9, 0)
             if a.dtype == "f32" and not a.skip_literal:
                 wt = w9c.view(3, 3, cdc, 1).permute(3, 2, 0, 1).contiguous()
                 xs = [d["x"].permute(0, 3, 1, 2) for d in dsets]              # NCHW views of channels_last memory, as in the decoder
