@@ -26,6 +26,7 @@ thread_local char tl_kernel[128] = "";
 std::atomic<uint64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
 std::atomic<int> g_fwd_threads{0}, g_bwd_threads{0};
 extern std::atomic<int> g_tune_head_impl;
+std::atomic<int> g_tune_concat_impl{0};      // concat forward: 0 = staged kernel (default), 1 = chunked kernel where it applies (experiment)
 std::atomic<int> g_tune_depthconv_impl{0};   // last-convolution forward: 0 = tensor-core phase 1 (default), 1 = FP32-pipe phase 1
 
 int fail(int code, const char *fmt, ...) {
@@ -440,6 +441,7 @@ void btslpg_set_tuning(int key, int value) {
         case 2: g_tune_r8_rows.store(value); break;   // float32 r=8: patch rows per lane (2, 4 or 8)
         case 3: g_tune_r4_px.store(value); break;     // float32 r=4: coarse pixels per thread (1 or 2)
         case 7: g_tune_head_impl.store(value); break; // fused head forward: 0 TMA-staged, 1 register-staged
+        case 10: g_tune_concat_impl.store(value); break;     // concat forward: 0 staged (default), 1 chunked where it applies
         case 9: g_tune_depthconv_impl.store(value); break;   // last-convolution forward: 0 tensor-core phase 1 (3xTF32), 1 FP32 pipe
         case 6: g_tune_r2_px.store(value); break;     // float32 r=2: coarse pixels per thread (2 or 4)
         default: break;

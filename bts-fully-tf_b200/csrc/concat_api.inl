@@ -141,6 +141,22 @@ int btslpg_concat_forward(const BtsTensor *a, int a_subpixel, int act, const Bts
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
         p.act = act;
         p.vec = (p.ca % (16 / sizeof(T)) == 0) && (p.cb % (16 / sizeof(T)) == 0);
+        // every 16-byte chunk of the output from exactly one source: the chunked kernel (no staging) CAN run; it is an
+        // experiment behind tuning key 10 -- measured slower than the staged kernel on the decoder's five concats
+        // (1954 us vs 1709 us per inference step at B = 32, 480x640; profiles/experiments/README.md)
+        constexpr uint32_t V = 16 / sizeof(T);
+        const bool chunked = g_tune_concat_impl.load() == 1 && p.ca % V == 0 && p.cb % V == 0 && (p.np + p.pad == 0 || p.np + p.pad == V) &&
+                             g.a.aligned(16) && (!g.has_b || g.b.aligned(16)) && (!scale_ptr || p.ca % 4 == 0) &&
+                             (!scale_ptr || (reinterpret_cast<uintptr_t>(scale_ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(shift_ptr) % 16 == 0));
+        if (chunked) {
+            p.div_cpp = FastDiv(p.ct / V);
+            const uint64_t nt = ((uint64_t)g.npix + kConcatChunkTilePx - 1) / kConcatChunkTilePx;
+            if (act) concat_fwd_chunk_kernel<T, true><<<concat_blocks(concat_fwd_chunk_kernel<T, true>, 0, nt), kConcatThreads, 0, st>>>(p);
+            else concat_fwd_chunk_kernel<T, false><<<concat_blocks(concat_fwd_chunk_kernel<T, false>, 0, nt), kConcatThreads, 0, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "concat_fwd_chunk<%s,%s%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", scale_ptr ? "+affine" : "",
+                     p.sub_w ? "+subpixel" : "", p.ca, p.cb, p.np, p.pad);
+            return check_launch("btslpg_concat_forward");
+        }
         const int smem = (P * (int)ct * (int)sizeof(T) + 15) / 16 * 16 + (scale_ptr ? 2 * (int)p.ca * (int)sizeof(float) : 0);
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
         concat_allow_smem(concat_fwd_kernel<T>, smem);

@@ -307,7 +307,8 @@ BTSLPG_API const char *btslpg_last_kernel(void);
 /* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default).
  * btslpg_set_tuning keys: 0 forward block threads, 1 backward block threads, 2 float32 r=8 patch rows
  * per lane (2/4/8), 3 float32 r=4 coarse pixels per thread (1/2), 9 last-convolution forward (0 tensor-core
- * phase 1 with the 3xTF32 split, 1 FP32 pipe).  Results do not depend on them beyond float32 rounding,
+ * phase 1 with the 3xTF32 split, 1 FP32 pipe), 10 concat forward (0 shared-memory-staged kernel, 1 the
+ * chunked kernel where every 16-byte output chunk has one source: an experiment, measured slower).  Results do not depend on them beyond float32 rounding,
  * except that the r=8 backward sum is associated per lane group (still deterministic). */
 BTSLPG_API void btslpg_set_block_threads(int fwd_threads, int bwd_threads);
 BTSLPG_API void btslpg_set_tuning(int key, int value);

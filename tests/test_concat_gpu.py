@@ -17,6 +17,15 @@ def npf(t):
     return t.detach().float().cpu().numpy().astype(np.float64)
 
 
+@pytest.fixture(autouse=True, params=["chunked", "staged"])
+def concat_impl(request):
+    """Every test runs with both forward variants: the shared-memory-staged kernel (default) and the chunked kernel
+    (tuning key 10; where each 16-byte output chunk has one source -- other shapes fall back by themselves)."""
+    ops.set_tuning(10, 1 if request.param == "chunked" else 0)
+    yield request.param
+    ops.set_tuning(10, 0)
+
+
 def make(B, H, W, ca, cb, n_planes, seed, dtype=torch.float32):
     g = torch.Generator().manual_seed(seed)
     a = (torch.randn(B, H, W, ca, generator=g) * 2).to(dtype)
@@ -38,13 +47,17 @@ def make(B, H, W, ca, cb, n_planes, seed, dtype=torch.float32):
     (1, 8, 8, 2, 0, 3),         # F/16 = 2 (the reference-decoder fixture, num_filters = 32): scalar path
     (2, 5, 7, 6, 3, 2),         # odd channel counts everywhere
 ])
-def test_concat_matches_oracle_and_torch(B, H, W, ca, cb, n_planes, act, dtype):
+def test_concat_matches_oracle_and_torch(B, H, W, ca, cb, n_planes, act, dtype, concat_impl):
     a, b, planes, g_out = make(B, H, W, ca, cb, n_planes, seed=ca + cb + W, dtype=dtype)
     ad = a.to(DEV).requires_grad_(True)
     bd = b.to(DEV).requires_grad_(True) if b is not None else None
     pd = [p.to(DEV).requires_grad_(True) for p in planes]
     out = ops.concat_nhwc(ad, pd, b=bd, act=act)
-    assert ops.last_kernel().startswith("concat_fwd<%s,%s," % ("f32" if dtype == torch.float32 else "bf16", "elu" if act else "id"))
+    tag = "<%s,%s," % ("f32" if dtype == torch.float32 else "bf16", "elu" if act else "id")
+    assert ops.last_kernel().startswith(("concat_fwd" + tag, "concat_fwd_chunk" + tag)), ops.last_kernel()
+    V = 4 if dtype == torch.float32 else 8
+    if ca % V == 0 and cb % V == 0 and n_planes == 0:
+        assert ops.last_kernel().startswith("concat_fwd_chunk" if concat_impl == "chunked" else "concat_fwd<"), ops.last_kernel()
     ref = T.concat_elu(npf(a), [npf(p) for p in planes], None if b is None else npf(b), act)
     tol = 1e-6 if dtype == torch.float32 else 2 ** -8
     np.testing.assert_allclose(npf(out), ref, rtol=tol, atol=tol * 1e-2)
@@ -78,8 +91,10 @@ def test_concat_matches_oracle_and_torch(B, H, W, ca, cb, n_planes, act, dtype):
     (1, 6, 10, 128, 96, 1, 3),      # block3 concat: 225 -> 228
     (1, 3, 5, 512, 384, 0, 0),      # block5 concat [up, skip]: 896 channels, 8-pixel tiles
     (1, 5, 7, 6, 3, 2, 1),          # scalar path with padding
+    (1, 33, 37, 32, 8, 3, 5),       # 1221 pixels (more than one 1024-pixel work item of the chunked kernel); bfloat16: 3 + 5 = one 8-element chunk
+    (3, 9, 11, 16, 0, 1, 3),        # single plane + 3 zero channels
 ])
-def test_concat_pad_and_folded_batchnorm(B, H, W, ca, cb, n_planes, pad, dtype):
+def test_concat_pad_and_folded_batchnorm(B, H, W, ca, cb, n_planes, pad, dtype, concat_impl):
     a, b, planes, g_out = make(B, H, W, ca, cb, n_planes, seed=ca + pad, dtype=dtype)
     g = torch.Generator().manual_seed(7)
     scale = torch.rand(ca, generator=g) + 0.5
@@ -87,6 +102,9 @@ def test_concat_pad_and_folded_batchnorm(B, H, W, ca, cb, n_planes, pad, dtype):
     bd = b.to(DEV) if b is not None else None
     out = ops.concat_forward(a.to(DEV), [p.to(DEV) for p in planes], bd, act=True, pad=pad, scale=scale.to(DEV), shift=shift.to(DEV))
     assert "elu+affine" in ops.last_kernel() and ops.last_kernel().endswith("+%d>" % pad), ops.last_kernel()
+    V = 4 if dtype == torch.float32 else 8
+    if concat_impl == "chunked" and ca % V == 0 and cb % V == 0 and n_planes + pad in (0, V):
+        assert ops.last_kernel().startswith("concat_fwd_chunk<"), ops.last_kernel()
     ref = T.concat_elu(npf(a), [npf(p) for p in planes], None if b is None else npf(b), True, pad=pad, scale=scale.numpy(), shift=shift.numpy())
     tol = 2e-6 if dtype == torch.float32 else 2 ** -7
     np.testing.assert_allclose(npf(out), ref, rtol=tol, atol=tol)

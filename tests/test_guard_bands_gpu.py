@@ -256,3 +256,30 @@ def test_depthconv_forward_guard_bands(B, H, W, C, dtype):
     A.check()
     ref = tail_oracle.depth_tail_forward(npf(x), w.numpy(), act_in=True, max_depth=10.0)
     np.testing.assert_allclose(npf(out), ref, rtol=1e-5 if dtype == torch.float32 else 2 ** -7, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,ca,cb,n_planes,pad", [(1, 1, 1, 8, 0, 3, 1), (1, 3, 5, 32, 0, 3, 1), (2, 7, 9, 16, 24, 1, 3), (1, 33, 37, 32, 8, 3, 5),
+                                                      (1, 5, 3, 64, 32, 0, 0)])
+def test_concat_chunked_guard_bands(B, H, W, ca, cb, n_planes, pad, dtype):
+    """Shapes the chunked forward takes (float32: n_planes + pad == 4; bfloat16: == 8 or staged fallback), ragged pixel counts."""
+    g = torch.Generator().manual_seed(ca + W + pad)
+    a = (torch.randn(B, H, W, ca, generator=g) * 2).to(dtype)
+    b = torch.randn(B, H, W, cb, generator=g).to(dtype) if cb else None
+    planes = [torch.randn(B, H, W, 1, generator=g).to(dtype) for _ in range(n_planes)]
+    scale = torch.rand(ca, generator=g) + 0.5
+    shift = torch.randn(ca, generator=g)
+    A = Arena()
+    out = A.output((B, H, W, ca + cb + n_planes + pad), dtype)
+    ops.set_tuning(10, 1)
+    try:
+        ops.concat_forward(A.input(a), [A.input(p) for p in planes], A.input(b) if cb else None, True, pad=pad, scale=A.input(scale), shift=A.input(shift), out=out)
+    finally:
+        ops.set_tuning(10, 0)
+    A.check()
+    V = 4 if dtype == torch.float32 else 8
+    if ca % V == 0 and cb % V == 0 and n_planes + pad in (0, V):
+        assert ops.last_kernel().startswith("concat_fwd_chunk<"), ops.last_kernel()
+    ref = tail_oracle.concat_elu(npf(a), [npf(p) for p in planes], None if b is None else npf(b), True, pad=pad, scale=scale.numpy(), shift=shift.numpy())
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7
+    np.testing.assert_allclose(npf(out), ref, rtol=tol, atol=tol)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick decoder session: decoder + slice + depthconv tests, step profile, config-3 bench
 mkdir -p gpurun_out
-python -m pytest tests/test_decoder_gpu.py tests/test_slice_gpu.py tests/test_depthconv_gpu.py -m gpu -q --timeout 600 > gpurun_out/pytest_dec.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_dec.log
+python -m pytest tests/test_decoder_gpu.py tests/test_concat_gpu.py tests/test_guard_bands_gpu.py -k "decoder or concat" -m gpu -q --timeout 600 > gpurun_out/pytest_dec.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_dec.log
 python tools/profile_decoder.py > gpurun_out/profile_decoder.json 2> gpurun_out/profile_decoder.err; echo "profile exit $?"
 python - <<'PY'
 import json
