@@ -7,9 +7,10 @@ size_t btslpg_depthconv_backward_workspace_bytes(int channels) {
     return (size_t)kDcHeaderBytes + (size_t)kDcMaxBlocks * 9 * channels * sizeof(float);
 }
 
-int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, BtsTensor *g_x, BtsTensor *g_kernel,
+int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, int act_in, BtsTensor *g_x, BtsTensor *g_kernel,
                               void *workspace, size_t workspace_bytes, void *stream) {
     View xv, gv, gxv;
+    if (act_in != 0 && act_in != 1) return fail(BTSLPG_EINVAL, "act_in: %d (0 none, 1 ELU)", act_in);
     if (int e = parse_nhwc(x, "x", xv)) return e;
     const int C = (int)xv.C;
     if (C != 16 && C != 32) return fail(BTSLPG_ESHAPE, "x: %d channels; the fused backward is built for C = 16 and C = 32 (F/16 of the reference's encoders)", C);
@@ -42,9 +43,10 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
     DeviceGuard guard(xv.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", xv.dev, cudaGetErrorString(guard.err));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    auto go = [&](auto tag, auto ctag) -> int {
+    auto go = [&](auto tag, auto ctag, auto etag) -> int {
         using T = decltype(tag);
         constexpr int CC = decltype(ctag)::value;
+        constexpr bool ELU = decltype(etag)::value != 0;
         DepthConvBwdParams<T> p;
         p.x = reinterpret_cast<const T *>(xv.ptr);
         p.g = reinterpret_cast<const T *>(gv.ptr);
@@ -58,19 +60,20 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
         p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
         p.div_cb = FastDiv(p.col_blocks);
         p.div_h = FastDiv(p.H);
-        static const int resident = occupancy_blocks(depthconv_bwd_kernel<T, CC>, kDcThreads);
+        static const int resident = occupancy_blocks(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads);
         uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
         if (blocks > (uint32_t)kDcMaxBlocks) blocks = kDcMaxBlocks;
         if (gw) {
             const size_t fit = (workspace_bytes - kDcHeaderBytes) / ((size_t)9 * CC * sizeof(float));
             if (fit < blocks) blocks = (uint32_t)fit;
         }
-        depthconv_bwd_kernel<T, CC><<<blocks, kDcThreads, 0, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_bwd<%s,C%d>", ElemTraits<T>::kName, CC);
+        depthconv_bwd_kernel<T, CC, ELU><<<blocks, kDcThreads, 0, st>>>(p);
+        snprintf(tl_kernel, sizeof(tl_kernel), ELU ? "depthconv_bwd<%s,C%d,elu>" : "depthconv_bwd<%s,C%d>", ElemTraits<T>::kName, CC);
         return check_launch("btslpg_depthconv_backward");
     };
-    if (xv.dtype == kF32) return C == 32 ? go(float{}, IntC<32>{}) : go(float{}, IntC<16>{});
-    return C == 32 ? go(__nv_bfloat16{}, IntC<32>{}) : go(__nv_bfloat16{}, IntC<16>{});
+    auto by_act = [&](auto tag, auto ctag) -> int { return act_in ? go(tag, ctag, IntC<1>{}) : go(tag, ctag, IntC<0>{}); };
+    if (xv.dtype == kF32) return C == 32 ? by_act(float{}, IntC<32>{}) : by_act(float{}, IntC<16>{});
+    return C == 32 ? by_act(__nv_bfloat16{}, IntC<32>{}) : by_act(__nv_bfloat16{}, IntC<16>{});
 }
 
 int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int act_in, int act_out, float out_scale, BtsTensor *y, void *stream) {

@@ -72,7 +72,7 @@ __device__ __forceinline__ void dc_reduce_partials(const float *partial, uint32_
     }
 }
 
-template <typename T, int C> __global__ void __launch_bounds__(kDcThreads, 2) depthconv_bwd_kernel(const __grid_constant__ DepthConvBwdParams<T> prm) {
+template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThreads, 2) depthconv_bwd_kernel(const __grid_constant__ DepthConvBwdParams<T> prm) {
     constexpr int LPP = C / 4;                 // lanes per pixel
     constexpr int PPW = 32 / LPP;              // pixels per warp pass
     constexpr int NW = kDcThreads / 32;
@@ -124,6 +124,17 @@ template <typename T, int C> __global__ void __launch_bounds__(kDcThreads, 2) de
                 const uint32_t px = base + u * NW * PPW;
                 if (px >= npx) break;
                 float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float dact[4];
+                if constexpr (ELU) {
+                    // x is the PRE-activation of iconv1 (bts_decoder.py:100): the layer input is elu(x), d elu / d x = x > 0 ? 1 : exp(x)
+                    // (the same 4-instruction ELU as the forward, so that forward and backward see one function)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float ex = ex2_sfu(xv[u][e] * kLog2e);
+                        dact[e] = xv[u][e] > 0.0f ? 1.0f : ex;
+                        xv[u][e] = xv[u][e] > 0.0f ? xv[u][e] : ex - 1.0f;
+                    }
+                }
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
@@ -136,6 +147,10 @@ template <typename T, int C> __global__ void __launch_bounds__(kDcThreads, 2) de
                             acc[t][e] = fmaf(gv, xv[u][e], acc[t][e]);
                         }
                     }
+                if constexpr (ELU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) out[e] *= dact[e];
+                }
                 if (prm.g_x) store_elems<T, 4>(prm.g_x + (row0 + px) * C + 4 * cg, out);
             }
         }

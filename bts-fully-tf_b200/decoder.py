@@ -269,12 +269,13 @@ class BtsDecoder(nn.Module):
             x = _nhwc_view(iconv1_raw.contiguous(memory_format=torch.channels_last))
             return ops.depthconv_forward(x, ops.kernel9c(self.depth_conv.weight), act_in=True,
                                          sigmoid_scale=None if return_logit else self.max_depth)
-        iconv1 = F.elu(iconv1_raw)
         if fused_tail:
-            # bts_decoder.py:102 with autograd: hand-written forward, ONE hand-written pass for both gradients (ops.depth_conv)
-            logit = _to_nchw(ops.depth_conv(_nhwc_view(iconv1.contiguous(memory_format=torch.channels_last)), self.depth_conv.weight))
+            # bts_decoder.py:100-102 with autograd: iconv1's ELU inside the hand-written forward, ELU' inside the ONE
+            # hand-written pass that yields both gradients (ops.depth_conv): no ELU tensor, no ELU passes
+            logit = _to_nchw(ops.depth_conv(_nhwc_view(iconv1_raw.contiguous(memory_format=torch.channels_last)), self.depth_conv.weight,
+                                            act_in=True))
         else:
-            logit = self.depth_conv(iconv1)                                            # (B,1,H,W): same memory as NHWC (B,H,W,1)
+            logit = self.depth_conv(F.elu(iconv1_raw))                                 # (B,1,H,W): same memory as NHWC (B,H,W,1)
         if return_logit:
             return _nhwc_view(logit)
         if not torch.is_grad_enabled():                                                # bts_decoder.py:102-103 in one pass

@@ -515,8 +515,9 @@ def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
 # ---------------------------------------------------------------------------------------------
 # last convolution Conv2D(1, 3x3, 'same'): hand-written forward (with the neighbouring ELU / sigmoid folded in) and backward
 # ---------------------------------------------------------------------------------------------
-def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True):
+def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True, act_in=False):
     """x (B,H,W,C) NHWC, kernel9c float32 [9*C] ([tap][c] == Keras HWIO (3,3,C,1)), g_out (B,H,W,1).
+    act_in: x is the pre-activation and the convolution saw elu(x) (see depthconv_forward); g_x is then d loss / d x.
     Returns (g_x-or-None, g_kernel [9*C] float32-or-None), both from one pass."""
     lib = load()
     C = x.shape[-1]
@@ -524,7 +525,7 @@ def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True):
     g_k = torch.empty(9 * C, dtype=torch.float32, device=x.device) if need_g_kernel else None
     ws = _workspace(x.device, int(lib.btslpg_depthconv_backward_workspace_bytes(C))) if need_g_kernel else None
     rx, rk, rg, rgx, rgk = as_ref(x), as_ref(kernel9c), as_ref(g_out), as_ref(g_x), as_ref(g_k)
-    check(lib.btslpg_depthconv_backward(rx.ptr, rk.ptr, rg.ptr, ptr_or_null(rgx), ptr_or_null(rgk),
+    check(lib.btslpg_depthconv_backward(rx.ptr, rk.ptr, rg.ptr, int(bool(act_in)), ptr_or_null(rgx), ptr_or_null(rgk),
                                         ctypes.c_void_p(ws.data_ptr() if ws is not None else 0), ws.numel() if ws is not None else 0,
                                         current_stream_ptr(x.device)))
     return g_x, g_k
@@ -548,30 +549,32 @@ def depthconv_forward(x, kernel9c, act_in=False, sigmoid_scale=None, out=None):
 
 
 class DepthConvFunction(torch.autograd.Function):
-    """x NHWC (B,H,W,C), weight torch OIHW (1,C,3,3) -> (B,H,W,1): hand-written forward (exact float32) and one
-    hand-written pass for both gradients."""
+    """x NHWC (B,H,W,C), weight torch OIHW (1,C,3,3) -> (B,H,W,1): hand-written forward (float32-accurate) and one
+    hand-written pass for both gradients.  act_in: x is the PRE-activation of iconv1 and the ELU (bts_decoder.py:100) runs
+    inside both kernels (no ELU tensor, no separate ELU forward / backward pass)."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, weight):
+    def forward(ctx, x_nhwc, weight, act_in=False):
         x_nhwc = x_nhwc.contiguous()
         ctx.save_for_backward(x_nhwc, weight)
-        return depthconv_forward(x_nhwc, kernel9c(weight))
+        ctx.act_in = bool(act_in)
+        return depthconv_forward(x_nhwc, kernel9c(weight), act_in=act_in)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
         x, weight = ctx.saved_tensors
-        g_x, g_k = depthconv_backward(x, kernel9c(weight), g_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g_x, g_k = depthconv_backward(x, kernel9c(weight), g_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1], act_in=ctx.act_in)
         g_w = None
         if g_k is not None:
             C = x.shape[-1]
             g_w = g_k.view(3, 3, C, 1).permute(3, 2, 0, 1).to(weight.dtype)                      # back to OIHW
-        return g_x, g_w
+        return g_x, g_w, None
 
 
-def depth_conv(x_nhwc, weight):
-    """The decoder's last convolution with autograd; C in (16, 32) takes the fused backward."""
-    return DepthConvFunction.apply(x_nhwc, weight)
+def depth_conv(x_nhwc, weight, act_in=False):
+    """The decoder's last convolution with autograd; C in (16, 32).  act_in=True: conv(elu(x)) with the ELU folded in."""
+    return DepthConvFunction.apply(x_nhwc, weight, act_in)
 
 
 def launch_count():

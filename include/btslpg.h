@@ -268,13 +268,16 @@ BTSLPG_API int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, c
  *   x        (B,H,W,C)  the layer input, C = 16 or 32 (F/16), contiguous NHWC
  *   kernel   float32, 9*C elements: the Keras HWIO kernel (3,3,C,1) as it lies in memory ([tap][c])
  *   g_out    (B,H,W[,1]) gradient of the layer's (pre-activation) output
+ *   act_in   0: x is the layer input; 1: x is the PRE-activation of iconv1 (bts_decoder.py:100) and the layer input is
+ *            elu(x), as in btslpg_depthconv_forward(act_in = 1): g_kernel is taken against elu(x) and g_x is the gradient
+ *            with respect to x itself (times elu'(x)) -- the framework's separate ELU forward and backward passes disappear
  *   g_x      (B,H,W,C)  d loss / d x, nullable
  *   g_kernel float32 [9*C] d loss / d kernel in the same layout, nullable; reduced deterministically through
  *            `workspace` (btslpg_depthconv_backward_workspace_bytes(C) bytes, first 256 zeroed once)
  * Exact float32 arithmetic.
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API size_t btslpg_depthconv_backward_workspace_bytes(int channels);
-BTSLPG_API int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, BtsTensor *g_x,
+BTSLPG_API int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const BtsTensor *g_out, int act_in, BtsTensor *g_x,
                                          BtsTensor *g_kernel, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------

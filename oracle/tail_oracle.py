@@ -158,6 +158,15 @@ def depth_tail_forward(x_raw, w9c, act_in=True, max_depth=None):
     return y
 
 
+def depth_tail_backward(x_raw, w9c, g_out):
+    """Gradients of depth_tail_forward(x_raw, w9c, act_in=True, max_depth=None) (bts_decoder.py:100-102), float64:
+    (d loss / d x_raw, d loss / d kernel (9, C)) for g_out = d loss / d logit.  elu'(x) = 1 for x > 0, exp(x) otherwise."""
+    x = np.asarray(x_raw, np.float64)
+    xe = np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    g_xe, g_w = depthconv_backward(xe, w9c, g_out)
+    return g_xe * np.where(x > 0, 1.0, np.exp(np.minimum(x, 0))), g_w
+
+
 def depthconv_backward(x, w9c, g_out):
     """Gradients of depthconv_forward: (g_x (B,H,W,C), g_w (9, C)), float64."""
     x = np.asarray(x, np.float64)

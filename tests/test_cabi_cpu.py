@@ -116,12 +116,13 @@ def test_argument_validation_of_the_decoder_glue_entry_points(lib):
     assert lib.btslpg_affine_act(x.ptr, None, None, 0, out.ptr, None) == -3                                  # shape differs
     g = fake_cuda(torch.rand(1, 4, 4, 1))
     k = fake_cuda(torch.rand(72))
-    assert lib.btslpg_depthconv_backward(x.ptr, k.ptr, g.ptr, x.ptr, None, None, 0, None) == -3              # C must be 16 or 32
+    assert lib.btslpg_depthconv_backward(x.ptr, k.ptr, g.ptr, 0, x.ptr, None, None, 0, None) == -3           # C must be 16 or 32
     assert b"C = 16 and C = 32" in lib.btslpg_last_error()
     y1 = fake_cuda(torch.rand(1, 4, 4, 1))
     assert lib.btslpg_depthconv_forward(x.ptr, k.ptr, 1, 1, 10.0, y1.ptr, None) == -3                        # C must be 16 or 32
     x32 = fake_cuda(torch.rand(1, 4, 4, 32))
     k288 = fake_cuda(torch.rand(288))
+    assert lib.btslpg_depthconv_backward(x32.ptr, k288.ptr, y1.ptr, 2, x32.ptr, None, None, 0, None) == -1   # act_in out of range
     assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 2, 0, 1.0, y1.ptr, None) == -1                    # act_in out of range
     assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 1, 3, 1.0, y1.ptr, None) == -1                    # act_out out of range
     assert lib.btslpg_depthconv_forward(x32.ptr, k288.ptr, 1, 1, 1.0, None, None) == -1                      # y missing

@@ -45,6 +45,45 @@ def test_depthconv_backward_vs_oracle(B, H, W, C, dtype):
     assert none is None and torch.equal(g_k2, g_k)                                               # bit-reproducible reduction
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [16, 32])
+@pytest.mark.parametrize("B,H,W", [(1, 1, 1), (2, 3, 5), (1, 7, 37), (2, 5, 130), (1, 16, 128)])
+def test_depthconv_backward_with_elu_vs_oracle(B, H, W, C, dtype):
+    """act_in = 1: x is iconv1's pre-activation (bts_decoder.py:100); g_kernel against elu(x), g_x = d loss / d x."""
+    g = torch.Generator().manual_seed(H * 1000 + W + C + 1)
+    x = (torch.randn(B, H, W, C, generator=g) * 1.5).to(dtype)
+    w9c = (torch.randn(9 * C, generator=g) * 0.2)
+    g_out = torch.randn(B, H, W, 1, generator=g).to(dtype)
+    g_x, g_k = ops.depthconv_backward(x.to(DEV), w9c.to(DEV), g_out.to(DEV), act_in=True)
+    assert ops.last_kernel() == "depthconv_bwd<%s,C%d,elu>" % ("f32" if dtype == torch.float32 else "bf16", C)
+    ref_gx, ref_gw = T.depth_tail_backward(npf(x), w9c.numpy(), npf(g_out))
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7
+    assert np.abs(npf(g_x) - ref_gx).max() <= tol * max(np.abs(ref_gx).max(), 1e-30)
+    assert np.abs(npf(g_k).reshape(9, C) - ref_gw).max() <= 1e-5 * max(np.abs(ref_gw).max(), 1e-30)
+    g_x2, g_k2 = ops.depthconv_backward(x.to(DEV), w9c.to(DEV), g_out.to(DEV), act_in=True)
+    assert torch.equal(g_x2, g_x) and torch.equal(g_k2, g_k)                                     # bit-reproducible
+
+
+@pytest.mark.parametrize("C", [16, 32])
+def test_depth_conv_with_elu_autograd_matches_framework_ops(C):
+    """ops.depth_conv(x, w, act_in=True) == conv2d(elu(x)) of the framework (TF32 off), values and both gradients."""
+    torch.manual_seed(C + 7)
+    B, H, W = 2, 24, 40
+    x = torch.randn(B, H, W, C, device=DEV, requires_grad=True)
+    conv = torch.nn.Conv2d(C, 1, 3, padding=1, bias=False).to(DEV)
+    y = ops.depth_conv(x, conv.weight, act_in=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    gx, gw = x.grad.clone(), conv.weight.grad.clone()
+    x.grad = None
+    conv.weight.grad = None
+    y2 = conv(F.elu(x.permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
+    y2.backward(g)
+    assert float((y.detach() - y2.detach()).abs().max()) <= 2e-6 * float(y2.detach().abs().max())
+    assert float((gx - x.grad).abs().max()) <= 2e-6 * float(x.grad.abs().max())
+    assert float((gw - conv.weight.grad).abs().max()) <= 1e-5 * float(conv.weight.grad.abs().max())
+
+
 @pytest.mark.parametrize("C", [16, 32])
 def test_depth_conv_autograd_matches_library_convolution(C):
     torch.manual_seed(C)
@@ -59,7 +98,7 @@ def test_depth_conv_autograd_matches_library_convolution(C):
     conv.weight.grad = None
     y2 = conv(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     y2.backward(g)
-    assert float((y - y2).abs().max()) <= 2e-6 * float(y2.abs().max())                  # both exact float32, different summation order
+    assert float((y.detach() - y2.detach()).abs().max()) <= 2e-6 * float(y2.detach().abs().max())    # float32-accurate on both sides
     assert float((gx - x.grad).abs().max()) <= 2e-6 * float(x.grad.abs().max())
     assert float((gw - conv.weight.grad).abs().max()) <= 1e-5 * float(conv.weight.grad.abs().max())
     # forward against the oracle too (Keras HWIO (3,3,C,1) == [tap][c])

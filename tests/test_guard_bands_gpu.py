@@ -238,6 +238,12 @@ def test_depthconv_guard_bands(B, H, W, C, dtype):
     A = Arena()
     g_x, g_k = ops.depthconv_backward(A.input(x), A.input(w), A.input(go))
     A.check()
+    A2 = Arena()
+    g_xe, g_ke = ops.depthconv_backward(A2.input(x), A2.input(w), A2.input(go), act_in=True)
+    A2.check()
+    ref_gxe, ref_gwe = tail_oracle.depth_tail_backward(npf(x), w.numpy(), npf(go))
+    assert np.abs(npf(g_xe) - ref_gxe).max() <= (2e-6 if dtype == torch.float32 else 2 ** -7) * max(np.abs(ref_gxe).max(), 1e-30)
+    assert np.abs(npf(g_ke).reshape(9, C) - ref_gwe).max() <= 1e-5 * max(np.abs(ref_gwe).max(), 1e-30)
     ref_gx, ref_gw = tail_oracle.depthconv_backward(npf(x), w.numpy(), npf(go))
     tol = 2e-6 if dtype == torch.float32 else 2 ** -7
     assert np.abs(npf(g_x) - ref_gx).max() <= tol * max(np.abs(ref_gx).max(), 1e-30)
