@@ -15,6 +15,8 @@ Files written
   lpg_pole_r8.npz     U(0,1) coefficients that reach the theta->pi/3 pole (den <= 0)
   decoder_small.npz   bts_decoder.py:26-105 whole, num_filters=32, float64 run on
                       float32-representable inputs/weights, inference BN and training BN
+  decoder_f256.npz    the same at num_filters=256 (the channel counts of the fused fast paths); kernels are redrawn by
+                      oracle/decoder_fixture.regen_kernels (checked bit for bit here), gradients of large kernels sampled
   lpg_full_size_samples.npz   the layer at FULL size (2 x 480 x 640, r = 8/4/2, seeded numpy inputs): 4096 sampled
                       outputs per scale instead of the 2.4 MB maps (the "full-size" pin of SURVEY 8(c))
   tail_silog.npz      bts.py:27-41 si_log_loss (nyu and kitti thresholds) on depth_est =
@@ -35,6 +37,7 @@ REF = os.environ.get("BTS_REFERENCE", "/root/reference")
 
 sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_shim"))
 sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
 
 import custom_layers  # noqa: E402  (the reference file, unmodified)
 import bts_decoder  # noqa: E402    (the reference file, unmodified)
@@ -130,6 +133,54 @@ def golden_decoder():
     print("decoder_small: %d convs, depth %s" % (out["n_convs"], out["infer_depth_est"].shape))
 
 
+def golden_decoder_f256():
+    """bts_decoder.py:26-105 whole at num_filters = 256 (F/16 = 16, heads at C = 64 / 64 / 32): the channel counts that take the
+    fused fast paths (head kernels, concat with pad channels, sub-pixel upconv, last convolution with the ELU folded in).
+    Kernels are NOT stored (2 M weights): oracle/decoder_fixture.regen_kernels redraws them; checked here bit for bit."""
+    from oracle import decoder_fixture
+    F, seed = 256, 4321
+    B, H, W = 1, 64, 64
+    chans = dict(dense=16, s2=6, s4=6, s8=8, s16=12)
+    out = {"seed": seed, "num_filters": F}
+    for tag, training in (("infer", False), ("train", True)):
+        shim_layers.reset(seed=seed, dtype=torch.float64)
+        g = torch.Generator().manual_seed(77)
+        mk = lambda s, c: torch.randn(B, H // s, W // s, c, generator=g).float().double().requires_grad_(True)  # noqa: E731
+        feats = [mk(32, chans["dense"]), mk(2, chans["s2"]), mk(4, chans["s4"]), mk(8, chans["s8"]), mk(16, chans["s16"])]
+        depth = bts_decoder.decoder_model(feats, 10.0, num_filters=F, is_training=training)
+        g_depth = torch.randn(depth.shape, generator=g).float().double()
+        depth.backward(g_depth)
+        convs = [l for l in shim_layers.CREATED if isinstance(l, shim_layers.Conv2D)]
+        named = {l.name: l for l in shim_layers.CREATED}
+        shapes = [tuple(l.kernel.shape) for l in convs]
+        regen = decoder_fixture.regen_kernels(shapes, seed)
+        for l, k in zip(convs, regen):
+            assert torch.equal(l.kernel.detach(), k), "regen_kernels does not reproduce the recorded run"
+        if tag == "infer":
+            for k, f in zip(["dense", "s2", "s4", "s8", "s16"], feats):
+                out["feat_" + k] = f.detach().numpy().astype(np.float32)
+            out["g_depth"] = g_depth.numpy().astype(np.float32)
+            out["kernel_shapes"] = np.array(shapes, np.int64)
+            out["kernel_sums"] = np.array([float(k.sum()) for k in regen], np.float64)
+        heads = [l for l in convs if l.filters == 3]
+        for r, l in zip((8, 4, 2), heads):
+            out["%s_head%d_out" % (tag, r)] = l.last_output.detach().numpy()
+        for r in (8, 4, 2):
+            out["%s_depth_%dx%d_scaled" % (tag, r, r)] = named["depth_%dx%d_scaled" % (r, r)].last_output.detach().numpy().astype(np.float32)
+        out[tag + "_depth_est"] = depth.detach().numpy()
+        for i, l in enumerate(convs):
+            gk = l.kernel.grad.reshape(-1)
+            idx = decoder_fixture.sample_index(gk.numel())
+            out["%s_gkernel_%02d" % (tag, i)] = gk[idx].numpy()
+            out["%s_gkernel_absmax_%02d" % (tag, i)] = float(gk.abs().max())
+            out["%s_gkernel_sum_%02d" % (tag, i)] = float(gk.sum())
+        for k, f in zip(["dense", "s2", "s4", "s8", "s16"], feats):
+            out["%s_gfeat_%s" % (tag, k)] = f.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "decoder_f256.npz"), **out)
+    print("decoder_f256: %d convs, %d weights regenerated, depth %s, %d bytes" % (
+        len(shapes), sum(int(np.prod(s)) for s in shapes), out["infer_depth_est"].shape, os.path.getsize(os.path.join(HERE, "decoder_f256.npz"))))
+
+
 def full_size_inputs(r, B=2, H=480, W=640):
     """Seeded inputs of the full-size pin (numpy Generator streams are stable across platforms)."""
     rng = np.random.default_rng(4000 + r)
@@ -207,5 +258,6 @@ if __name__ == "__main__":
     golden_lpg()
     golden_pole()
     golden_decoder()
+    golden_decoder_f256()
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("total fixture bytes:", tot)

@@ -54,6 +54,41 @@ def test_decoder_matches_reference_fixture(golden_dir, tag, training):
         assert np.abs(f.grad.cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, k
 
 
+@pytest.mark.parametrize("tag,training", [("infer", False), ("train", True)])
+def test_decoder_f256_matches_reference_fixture(golden_dir, tag, training):
+    """The UNMODIFIED reference decoder_model at num_filters = 256 (tests/golden/decoder_f256.npz): the channel counts
+    that take every fused fast path -- TMA-staged heads at C = 64 / 64 / 32, concats with pad channels, sub-pixel upconvs,
+    the last convolution with iconv1's ELU (and, in inference, sigmoid * max_depth) folded in, its fused backward."""
+    from oracle import decoder_fixture
+    z = np.load(os.path.join(golden_dir, "decoder_f256.npz"))
+    kernels = decoder_fixture.regen_kernels([tuple(s) for s in z["kernel_shapes"]], int(z["seed"]))
+    np.testing.assert_allclose([float(k.sum()) for k in kernels], z["kernel_sums"], rtol=0, atol=1e-9)     # the same draws as the recorded run
+    feats = [torch.from_numpy(z["feat_" + k]).float().to(DEV).requires_grad_(True) for k in ("dense", "s2", "s4", "s8", "s16")]
+    dec = BtsDecoder([f.shape[-1] for f in feats], 10.0, num_filters=int(z["num_filters"])).to(DEV)
+    dec.load_keras_kernels([k.float() for k in kernels])
+    if not training:
+        with torch.no_grad():                                   # the inference path proper (folded BatchNorm, fused tail)
+            d_inf = decoder_model([f.detach() for f in feats], 10.0, num_filters=256, is_training=False, decoder=dec)
+        assert ops.last_kernel() == "depthconv_fwd<f32,C16,elu>", ops.last_kernel()
+        np.testing.assert_allclose(d_inf.cpu().numpy(), z["infer_depth_est"], rtol=5e-4, atol=1e-5)
+    depth = decoder_model(feats, 10.0, num_filters=256, is_training=training, decoder=dec)
+    for r in (8, 4, 2):
+        np.testing.assert_allclose(dec.intermediates["reduction_%dx%d" % (r, r)].detach().cpu().numpy(), z["%s_head%d_out" % (tag, r)],
+                                   rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(dec.intermediates["depth_%dx%d_scaled" % (r, r)].detach().cpu().numpy(),
+                                   z["%s_depth_%dx%d_scaled" % (tag, r, r)], rtol=5e-4, atol=1e-5)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), z[tag + "_depth_est"], rtol=5e-4, atol=1e-5)
+    depth.backward(torch.from_numpy(z["g_depth"]).float().to(DEV))
+    for i, g in enumerate(dec.keras_kernel_grads()):
+        flat = g.detach().reshape(-1).cpu()
+        got = flat[decoder_fixture.sample_index(flat.numel())].numpy()
+        scale = float(z["%s_gkernel_absmax_%02d" % (tag, i)])
+        assert np.abs(got - z["%s_gkernel_%02d" % (tag, i)]).max() <= 2e-3 * scale + 1e-7, "kernel %d" % i
+    for k, f in zip(("dense", "s2", "s4", "s8", "s16"), feats):
+        ref = z["%s_gfeat_%s" % (tag, k)]
+        assert np.abs(f.grad.cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, k
+
+
 def test_fused_heads_equal_unfused_composition():
     """ReductionLPG (one kernel) == torch 1x1 conv + sigmoid -> LocalPlanarGuidance layer -> slice, at
     channel counts that take the fused fast path (F=256: C = 64, 64, 32)."""

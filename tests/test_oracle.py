@@ -189,3 +189,20 @@ def test_full_size_pin(golden_dir, r):
     out32 = c_oracle.lpg_forward_f32(coef, r)
     np.testing.assert_allclose(out32.reshape(-1)[idx][good], z["r%d_out" % r][good], rtol=2e-6)
     assert int((out64 < 0).sum()) == int(z["r%d_n_negative" % r])      # the pole is crossed in the same places
+
+
+def test_decoder_f256_fixture_kernels_regenerate(golden_dir):
+    """tests/golden/decoder_f256.npz stores no kernels: oracle/decoder_fixture.regen_kernels redraws the glorot_uniform
+    kernels of the recorded reference run (make_golden.py checked them bit for bit); their float64 sums pin the draws."""
+    import numpy as np
+    import os
+    from oracle import decoder_fixture
+    z = np.load(os.path.join(golden_dir, "decoder_f256.npz"))
+    shapes = [tuple(int(v) for v in s) for s in z["kernel_shapes"]]
+    assert len(shapes) == 25 and shapes[-1] == (3, 3, 16, 1) and shapes[-2] == (3, 3, 19, 16)       # depth conv, iconv1 (F/16 + 3 inputs)
+    assert [s for s in shapes if s[3] == 3 and s[0] == 1] == [(1, 1, 64, 3), (1, 1, 64, 3), (1, 1, 32, 3)]   # reduction_8x8 / 4x4 / 2x2
+    kernels = decoder_fixture.regen_kernels(shapes, int(z["seed"]))
+    np.testing.assert_allclose([float(k.sum()) for k in kernels], z["kernel_sums"], rtol=0, atol=1e-9)
+    for k, s in zip(kernels, shapes):
+        limit = (6.0 / (s[0] * s[1] * (s[2] + s[3]))) ** 0.5
+        assert float(k.abs().max()) <= limit
