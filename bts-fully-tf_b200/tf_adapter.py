@@ -232,3 +232,51 @@ def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
         return y, grad
 
     return op(upconv1_linear, d2, d4, d8)
+
+
+def depth_tail(iconv1_linear, kernel, max_depth=None):  # pragma: no cover
+    """bts_decoder.py:100-103 fused.  `iconv1_linear`: the output of iconv1's convolution built with activation=None;
+    `kernel`: the (3,3,C,1) kernel variable of the last Conv2D (C = 16 or 32).  max_depth given (inference): returns
+    depth_est = sigmoid(conv(elu(iconv1_linear))) * max_depth from ONE kernel.  max_depth None (training): returns the
+    logit with a custom gradient -- ONE backward kernel for d loss / d iconv1_linear (ELU' included) and d loss / d kernel;
+    feed it to si_log_loss_wrapper's fused form together with max_depth."""
+    _require_tf()
+    lib = _cabi.load()
+
+    def fwd(x_, k_):
+        with tf.device(x_.device):
+            y_ = tf.zeros(x_.shape[:3] + [1], x_.dtype)
+        rx, rk, ry = _ref(x_), _ref(tf.reshape(k_, [-1])), _ref(y_)
+        _cabi.check(lib.btslpg_depthconv_forward(rx.ptr, rk.ptr, 1, 1 if max_depth is not None else 0,
+                                                 float(max_depth if max_depth is not None else 1.0), ry.ptr, ctypes.c_void_p(0)))
+        return y_
+
+    if max_depth is not None:
+        y = tf.py_function(fwd, [iconv1_linear, kernel], iconv1_linear.dtype)
+        y.set_shape(iconv1_linear.shape[:3] + [1])
+        return y
+
+    @tf.custom_gradient
+    def op(x, k):
+        y = tf.py_function(fwd, [x, k], x.dtype)
+        y.set_shape(x.shape[:3] + [1])
+
+        def grad(g_out):
+            def bwd(x_, k_, g_):
+                C = int(x_.shape[3])
+                with tf.device(x_.device):
+                    g_x = tf.zeros(x_.shape, x_.dtype)
+                    g_k = tf.zeros([9 * C], tf.float32)
+                    ws = tf.zeros([int(lib.btslpg_depthconv_backward_workspace_bytes(C))], tf.uint8)
+                rx, rk, rg, rgx, rgk, rw = _ref(x_), _ref(tf.reshape(k_, [-1])), _ref(g_), _ref(g_x), _ref(g_k), _ref(ws)
+                _cabi.check(lib.btslpg_depthconv_backward(rx.ptr, rk.ptr, rg.ptr, 1, rgx.ptr, rgk.ptr, ctypes.c_void_p(rw.struct.data),
+                                                          int(ws.shape[0]), ctypes.c_void_p(0)))
+                return g_x, tf.reshape(g_k, k_.shape)
+            g_x, g_k = tf.py_function(bwd, [x, k, g_out], [x.dtype, tf.float32])
+            g_x.set_shape(x.shape)
+            g_k.set_shape(k.shape)
+            return g_x, g_k
+
+        return y, grad
+
+    return op(iconv1_linear, kernel)
