@@ -91,3 +91,41 @@ def test_reference_shaped_wrappers_host_logic():
     args = types.SimpleNamespace(min_depth_eval=1e-3, max_depth_eval=80.0, garg_crop=True, eigen_crop=False, dataset="kitti")
     fns = eval_metrics.metrics_list_factory(args)
     assert [f.__name__ for f in fns] == list(T.METRIC_NAMES)
+
+
+def test_depth_tail_oracle_gradient_matches_finite_differences():
+    """oracle/tail_oracle.depth_tail_backward (bts_decoder.py:100-102: ELU -> Conv2D(1, 3x3, 'same')) against central
+    differences of depth_tail_forward in float64, and the forward against a direct triple loop."""
+    import numpy as np
+    from oracle import tail_oracle as T
+    rng = np.random.default_rng(5)
+    B, H, W, C = 1, 4, 5, 3
+    x = rng.standard_normal((B, H, W, C)) * 1.5
+    w = rng.standard_normal((9, C)) * 0.3
+    g = rng.standard_normal((B, H, W, 1))
+    y = T.depth_tail_forward(x, w, act_in=True)
+    xe = np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    ref = np.zeros((B, H, W, 1))
+    for i in range(H):
+        for j in range(W):
+            for ky in range(3):
+                for kx in range(3):
+                    ii, jj = i + ky - 1, j + kx - 1
+                    if 0 <= ii < H and 0 <= jj < W:                       # padding='same': zeros of the ACTIVATED map
+                        ref[0, i, j, 0] += (xe[0, ii, jj] * w[ky * 3 + kx]).sum()
+    np.testing.assert_allclose(y, ref, rtol=1e-12, atol=1e-12)
+    d = T.depth_tail_forward(x, w, act_in=True, max_depth=80.0)
+    np.testing.assert_allclose(d, 80.0 / (1.0 + np.exp(-ref)), rtol=1e-12)
+    gx, gw = T.depth_tail_backward(x, w, g)
+    eps = 1e-6
+    f = lambda xx, ww: float((T.depth_tail_forward(xx, ww, act_in=True) * g).sum())   # noqa: E731
+    for idx in [(0, 0, 0, 0), (0, 1, 2, 1), (0, 3, 4, 2), (0, 2, 0, 1)]:
+        xp, xm = x.copy(), x.copy()
+        xp[idx] += eps
+        xm[idx] -= eps
+        assert abs((f(xp, w) - f(xm, w)) / (2 * eps) - gx[idx]) <= 1e-6 * max(1.0, abs(gx[idx]))
+    for idx in [(0, 0), (4, 1), (8, 2)]:
+        wp, wm = w.copy(), w.copy()
+        wp[idx] += eps
+        wm[idx] -= eps
+        assert abs((f(x, wp) - f(x, wm)) / (2 * eps) - gw[idx]) <= 1e-6 * max(1.0, abs(gw[idx]))
