@@ -199,13 +199,17 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
 // 1.1 ms at B = 32, 480x640 for a layer whose floor is 0.1 ms (the raw conv output read once, one float per pixel written).
 // Here x is read ONCE:
 //   phase 1  every pixel of a 32x32 output tile plus its one-pixel halo gets its nine per-tap dot products
-//            P[t][q] = sum_c elu(x[q][c]) * w[t][c].  Four lanes share a pixel (C/4 channels each: a warp instruction
-//            fetches whole 32-byte sectors), the lane's 9 x C/4 weights stay in registers as packed pairs (FFMA2: two
-//            channels per instruction), the four partial sums are combined by a fixed xor tree (reduce-scatter, so a
-//            lane ends with the taps it stores) and land in shared memory, tap-major.  Pixels outside the image give
+//            P[t][q] = sum_c elu(x[q][c]) * w[t][c], stored in shared memory, tap-major.  Pixels outside the image give
 //            P = 0 (padding='same' pads the ACTIVATED map with zeros; elu(0) = 0).
 //   phase 2  y[p] = sum_t P[t][p + t] in tap order, then the optional sigmoid * max_depth, one coalesced store per row.
-// FP32 FMAs on purpose: 2.25 FMA per input byte is under the machine balance, and TF32 would miss the 1e-5 budget.
+// Two phase-1 variants share phase 2:
+//   depthconv_fwd_kernel      (this one; tuning key 9 = 1) the first version, kept as the measured comparison: FP32 pipe, four
+//                             lanes share a pixel (C/4 channels each: a warp instruction fetches whole 32-byte sectors), the
+//                             lane's 9 x C/4 weights stay in registers as packed pairs (FFMA2), the four partial sums are
+//                             combined by a fixed xor tree (reduce-scatter: a lane ends with the taps it stores).
+//                             Exact float32 FMAs; bound by instruction issue (435 us at B = 32, 480x640, C = 32).
+//   depthconv_fwd_mma_kernel  (below; the default) the contraction on the tensor cores with the 3xTF32 split and a cp.async
+//                             ring for the inputs (340 us).
 // The ELU inside the sum is x > 0 ? x : ex2(x*log2e) - 1 (4 instructions per element instead of the 13 of the
 // expm1 form used where ELU values are an OUTPUT): its absolute error (<= 2.4e-7 per activation) enters a 9*C-term sum
 // of |w| ~ 0.1 products, i.e. < 1e-6 relative to the logit's scale.
