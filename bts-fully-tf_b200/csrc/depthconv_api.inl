@@ -96,6 +96,7 @@ int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int ac
     const int64_t npix = xv.B * xv.H * xv.W;
     if (npix == 0) return 0;
     if (npix * C >= ((int64_t)1 << 31) * 4) return fail(BTSLPG_ESHAPE, "x: too large");
+    if (xv.H * xv.W * C >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "x: one image has 2^31 elements or more (the kernels index inside an image with 32 bits)");
     const int64_t tiles_x = (xv.W + kDfTile - 1) / kDfTile, tiles_y = (xv.H + kDfTile - 1) / kDfTile;
     if (xv.B * tiles_x * tiles_y >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "x: too many tiles");
     DeviceGuard guard(xv.dev);
