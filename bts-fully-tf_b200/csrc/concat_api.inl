@@ -81,6 +81,8 @@ template <typename T> int concat_tile_px(int64_t ct, int images) {
 
 template <typename KernelT> void concat_allow_smem(KernelT kernel, int smem) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // as many staged images per SM as the registers allow: ask for the largest shared-memory carve-out
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <typename KernelT> int concat_blocks(KernelT kernel, int smem, uint64_t ntiles) {

@@ -129,7 +129,9 @@ template <typename T> __device__ __forceinline__ size_t subpixel_offset(const Co
     return (((size_t)(rowY >> 1) * prm.sub_w + (X >> 1)) * 4 + ((rowY & 1) << 1 | (X & 1))) * prm.ca;
 }
 
-template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_fwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
+// 8 CTAs per SM (a 32-register cap, no spills): the affine / sub-pixel / pad additions had pushed the kernel to 40 registers,
+// i.e. 6 resident CTAs, and the plain concat1 pass from 565 us to 640 us (B = 32, 480x640)
+template <typename T> __global__ void __launch_bounds__(kConcatThreads, 8) concat_fwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
     extern __shared__ __align__(16) unsigned char concat_smem[];
     T *img = reinterpret_cast<T *>(concat_smem);
     const uint32_t P = prm.tile_px, ct = prm.ct;
