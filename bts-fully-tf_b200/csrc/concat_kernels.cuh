@@ -94,6 +94,18 @@ template <typename T> __device__ __forceinline__ void flat_g2s(const T *g, T *s,
         *reinterpret_cast<uint4 *>(s + i) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
+// the same copy as asynchronous LDGSTS: no registers, every 16-byte piece of the tile in flight at once (the register
+// form above compiles to one load in flight per thread: LDG -> STS -> LDG ...).  Finish with flat_g2s_wait().
+template <typename T> __device__ __forceinline__ void flat_g2s_async(const T *g, T *s, uint32_t n) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s);
+    for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * (uint32_t)sizeof(T)), "l"(g + i) : "memory");
+}
+__device__ __forceinline__ void flat_g2s_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 template <typename T> __device__ __forceinline__ void flat_s2g(const T *s, T *g, uint32_t n) {
     constexpr int V = 16 / (int)sizeof(T);
     for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
@@ -107,17 +119,25 @@ template <typename T> __device__ __forceinline__ void flat_s2g(const T *s, T *g,
 template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(const T *src, T *img, uint32_t npx, uint32_t C, const FastDiv &divC,
                                                                               uint32_t ct, uint32_t c0, const float *aff = nullptr) {
     constexpr int V = 16 / (int)sizeof(T);
-    const uint32_t n = npx * C;
-    for (uint32_t i = threadIdx.x * V; i < n; i += kConcatThreads * V) {
-        float v[V];
-        load_elems<T, V, 4>(src + i, v);
-        uint32_t p, c;
-        divC.divmod(i, p, c);                          // C is a multiple of V: the V elements belong to one pixel
+    const uint32_t n = npx * C;                        // a multiple of V, at least V
+    // two 16-byte loads in flight per thread: the second index is clamped (always a legal address), its result used only in range
+    for (uint32_t i = threadIdx.x * V; i < n; i += 2 * kConcatThreads * V) {
+        const uint32_t j = i + kConcatThreads * V;
+        float v[2][V];
+        load_elems<T, V, 4>(src + i, v[0]);
+        load_elems<T, V, 4>(src + min(j, n - V), v[1]);
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            float x = ACT ? elu_fwd(v[e]) : v[e];
-            if (aff) x = fmaf(x, aff[c + e], aff[C + c + e]);      // shared-memory copy of (scale, shift)
-            smem_put<T>(img, p * ct + c0 + c + e, x);
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t iu = u ? j : i;
+            if (iu >= n) break;
+            uint32_t p, c;
+            divC.divmod(iu, p, c);                     // C is a multiple of V: the V elements belong to one pixel
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                float x = ACT ? elu_fwd(v[u][e]) : v[u][e];
+                if (aff) x = fmaf(x, aff[c + e], aff[C + c + e]);      // shared-memory copy of (scale, shift)
+                smem_put<T>(img, p * ct + c0 + c + e, x);
+            }
         }
     }
 }
@@ -297,8 +317,9 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_b
         const bool full_in = (npx % 8) == 0;
         const bool full = full_in && prm.vec;
         if (full_in) {
-            flat_g2s<T>(prm.g_out + p0 * ct, gimg, npx * ct);
-            if (prm.act) flat_g2s<T>(prm.y + p0 * ct, yimg, npx * ct);
+            flat_g2s_async<T>(prm.g_out + p0 * ct, gimg, npx * ct);
+            if (prm.act) flat_g2s_async<T>(prm.y + p0 * ct, yimg, npx * ct);
+            flat_g2s_wait();
         } else {
             for (uint32_t i = threadIdx.x; i < npx * ct; i += kConcatThreads) {
                 gimg[i] = prm.g_out[p0 * ct + i];
