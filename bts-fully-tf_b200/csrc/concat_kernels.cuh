@@ -120,12 +120,12 @@ template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(co
                                                                               uint32_t ct, uint32_t c0, const float *aff = nullptr) {
     constexpr int V = 16 / (int)sizeof(T);
     const uint32_t n = npx * C;                        // a multiple of V, at least V
-    // two 16-byte loads in flight per thread: the second index is clamped (always a legal address), its result used only in range
+    // two 16-byte loads in flight per thread (both are issued before the first is used)
     for (uint32_t i = threadIdx.x * V; i < n; i += 2 * kConcatThreads * V) {
         const uint32_t j = i + kConcatThreads * V;
         float v[2][V];
         load_elems<T, V, 4>(src + i, v[0]);
-        load_elems<T, V, 4>(src + min(j, n - V), v[1]);
+        if (j < n) load_elems<T, V, 4>(src + j, v[1]);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const uint32_t iu = u ? j : i;
