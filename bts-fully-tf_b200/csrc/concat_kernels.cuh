@@ -120,12 +120,14 @@ template <typename T, bool ACT> __device__ __forceinline__ void scatter_dense(co
                                                                               uint32_t ct, uint32_t c0, const float *aff = nullptr) {
     constexpr int V = 16 / (int)sizeof(T);
     const uint32_t n = npx * C;                        // a multiple of V, at least V
-    // two 16-byte loads in flight per thread (both are issued before the first is used)
+    // two 16-byte loads in flight per thread.  The second index is CLAMPED (always a legal address; its value is used only
+    // in range) rather than the load made conditional: under the kernel's 32-register cap the conditional form spills the
+    // loaded vector right behind the load (the warp then waits for it before the first load is even issued).
     for (uint32_t i = threadIdx.x * V; i < n; i += 2 * kConcatThreads * V) {
         const uint32_t j = i + kConcatThreads * V;
         float v[2][V];
         load_elems<T, V, 4>(src + i, v[0]);
-        if (j < n) load_elems<T, V, 4>(src + j, v[1]);
+        load_elems<T, V, 4>(src + min(j, n - V), v[1]);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const uint32_t iu = u ? j : i;
