@@ -280,3 +280,56 @@ def depth_tail(iconv1_linear, kernel, max_depth=None):  # pragma: no cover
         return y, grad
 
     return op(iconv1_linear, kernel)
+
+
+def reduction_lpg(feat, kernel, upratio, ds_stride=0):  # pragma: no cover
+    """bts_decoder.py:79-81 / 86-88 / 93-94 fused: the reduction head Conv2D(3, 1, activation='sigmoid', use_bias=False), its
+    LocalPlanarGuidance(upratio) and the strided down-sample Lambda as ONE forward and ONE backward kernel.
+    feat (B,h,w,C); kernel: the head's (1,1,C,3) kernel variable.  Returns (reduction (B,h,w,3), depth (B,H,W,1),
+    depth_ds (B,H/d,W/d,1) or None); gradients flow to feat and kernel from depth and depth_ds (reduction is the
+    saved tensor, as in layers.ReductionLPG)."""
+    _require_tf()
+    lib = _cabi.load()
+    r, d = int(upratio), int(ds_stride)
+
+    @tf.custom_gradient
+    def op(x, k):
+        def fwd(x_, k_):
+            B, h, w = (int(v) for v in x_.shape[:3])
+            with tf.device(x_.device):
+                coef = tf.zeros([B, h, w, 3], x_.dtype)
+                full = tf.zeros([B, h * r, w * r, 1], x_.dtype)
+                ds = tf.zeros([B, h * r // d, w * r // d, 1], x_.dtype) if d else tf.zeros([0], x_.dtype)
+            rx, rk, rc, ro = _ref(x_), _ref(tf.reshape(tf.cast(k_, tf.float32), [-1, 3])), _ref(coef), _ref(full)
+            rd = _ref(ds) if d else None
+            _cabi.check(lib.btslpg_reduce_forward(rx.ptr, rk.ptr, r, rc.ptr, ro.ptr, rd.ptr if d else None, d, ctypes.c_void_p(0)))
+            return coef, full, ds
+        coef, full, ds = tf.py_function(fwd, [x, k], [x.dtype] * 3)
+        coef.set_shape(x.shape[:3] + [3])
+        full.set_shape([x.shape[0], x.shape[1] * r, x.shape[2] * r, 1])
+        if d:
+            ds.set_shape([x.shape[0], x.shape[1] * r // d, x.shape[2] * r // d, 1])
+
+        def grad(g_coef_unused, g_full, g_ds):
+            def bwd(x_, k_, c_, gf_, gd_):
+                C = int(x_.shape[3])
+                npix = int(x_.shape[0]) * int(x_.shape[1]) * int(x_.shape[2])
+                with tf.device(x_.device):
+                    g_x = tf.zeros(x_.shape, x_.dtype)
+                    g_k = tf.zeros([C, 3], tf.float32)
+                    ws = tf.zeros([int(lib.btslpg_reduce_backward_workspace_bytes(npix, C))], tf.uint8)
+                refs = [_ref(x_), _ref(tf.reshape(tf.cast(k_, tf.float32), [-1, 3])), _ref(c_), _ref(gf_), _ref(gd_) if d else None,
+                        _ref(g_x), _ref(g_k), _ref(ws)]
+                _cabi.check(lib.btslpg_reduce_backward(refs[0].ptr, refs[1].ptr, refs[2].ptr, refs[3].ptr, refs[4].ptr if d else None, r, d,
+                                                       refs[5].ptr, refs[6].ptr, None, ctypes.c_void_p(refs[7].struct.data), int(ws.shape[0]),
+                                                       ctypes.c_void_p(0)))
+                return g_x, tf.reshape(g_k, k_.shape)
+            g_x, g_k = tf.py_function(bwd, [x, k, coef, g_full, g_ds], [x.dtype, tf.float32])
+            g_x.set_shape(x.shape)
+            g_k.set_shape(k.shape)
+            return g_x, g_k
+
+        return (coef, full, ds), grad
+
+    coef, full, ds = op(feat, kernel)
+    return coef, full, (ds if d else None)
