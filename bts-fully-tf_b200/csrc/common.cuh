@@ -226,4 +226,9 @@ __device__ __forceinline__ F2 rcp2(F2 a) {      // two MUFU.RCP; the pair stays 
     return f2(rcp_approx(l), rcp_approx(h));
 }
 
+// an int as a type (tag dispatch of compile-time variants)
+template <int V> struct IntC {
+    static constexpr int value = V;
+};
+
 }  // namespace btslpg

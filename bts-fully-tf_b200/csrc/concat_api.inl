@@ -1,4 +1,4 @@
-// concat_api.inl -- C ABI for the fused activation + NHWC concat (bts_decoder.py:98-99, :42); included by btslpg_api.cu.
+// concat_api.inl -- C ABI for the fused activation + NHWC concat (bts_decoder.py:98-99, :42); included by its own .cu translation unit.
 
 namespace {
 

@@ -1,4 +1,4 @@
-// depthconv_api.inl -- C ABI for the forward and the backward of the last convolution (bts_decoder.py:102); included by btslpg_api.cu.
+// depthconv_api.inl -- C ABI for the forward and the backward of the last convolution (bts_decoder.py:102); included by its own .cu translation unit.
 
 extern "C" {
 
@@ -60,7 +60,7 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
         p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
         p.div_cb = FastDiv(p.col_blocks);
         p.div_h = FastDiv(p.H);
-        static const int resident = occupancy_blocks(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads);
+        static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads); });
         uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
         if (blocks > (uint32_t)kDcMaxBlocks) blocks = kDcMaxBlocks;
         if (gw) {
@@ -118,13 +118,13 @@ int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *kernel, int ac
         p.act_out = act_out;
         p.out_scale = out_scale;
         if (g_tune_depthconv_impl.load() == 1) {
-            static const int resident = occupancy_blocks_smem(depthconv_fwd_kernel<T, CC, ELU>, kDfThreads, 0);
+            static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(depthconv_fwd_kernel<T, CC, ELU>, kDfThreads, 0); });
             const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
             depthconv_fwd_kernel<T, CC, ELU><<<blocks, kDfThreads, 0, st>>>(p);
             snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd_fp32pipe<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");
         } else {
             constexpr int smem = DcfMmaCfg<T, CC>::kSmemBytes;
-            static const int resident = occupancy_blocks_smem(depthconv_fwd_mma_kernel<T, CC, ELU>, kDfThreads, smem);
+            static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(depthconv_fwd_mma_kernel<T, CC, ELU>, kDfThreads, smem); });
             const uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
             depthconv_fwd_mma_kernel<T, CC, ELU><<<blocks, kDfThreads, smem, st>>>(p);
             snprintf(tl_kernel, sizeof(tl_kernel), "depthconv_fwd<%s,C%d,%s>", ElemTraits<T>::kName, CC, ELU ? "elu" : "lin");

@@ -1,0 +1,8 @@
+// head_api.cu -- one translation unit of libbtslpg.so (compiled in parallel with the others by build.py).
+#include "api_common.cuh"
+#include "head_kernels.cuh"
+
+using namespace btslpg;
+using namespace btslpg_api;
+
+#include "head_api.inl"

@@ -1,4 +1,4 @@
-// head_api.inl -- C ABI for the fused reduction-head + LPG entry points (included by btslpg_api.cu).
+// head_api.inl -- C ABI for the fused reduction-head + LPG entry points (included by its own .cu translation unit).
 
 namespace {
 
@@ -52,35 +52,10 @@ bool head_maps_ok(const LayerGeom &g) {
     return true;
 }
 
-template <typename KernelT> int occupancy_blocks(KernelT kernel, int threads) {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
-    if (per_sm < 1) per_sm = 1;
-    if (sms < 1) sms = 148;
-    return per_sm * sms;
-}
-
-std::atomic<int> g_tune_head_impl{0};   // 0 = TMA-staged (default), 1 = register-staged loads
-
-template <typename KernelT> int occupancy_blocks_smem(KernelT kernel, int threads, int smem) {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    // ask for the largest shared-memory carve-out so that as many ring-carrying CTAs as the registers allow are resident
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (per_sm < 1) per_sm = 1;
-    if (sms < 1) sms = 148;
-    return per_sm * sms;
-}
-
 template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdParams<T> &p, cudaStream_t st) {
     const int threads = 256;
     if (g_tune_head_impl.load() == 1) {
-        static const int resident = occupancy_blocks(head_lpg_fwd_kernel<T, R, D, M>, threads);
+        static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks(head_lpg_fwd_kernel<T, R, D, M>, threads); });
         uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
         if (blocks > (uint32_t)resident) blocks = resident;
         head_lpg_fwd_kernel<T, R, D, M><<<blocks, threads, 0, st>>>(p);
@@ -88,7 +63,7 @@ template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdPara
         return check_launch("btslpg_reduce_forward");
     }
     constexpr int smem = head_tma_smem_bytes<T, R, M, true>(256 / 32);
-    static const int resident = occupancy_blocks_smem(head_lpg_fwd_tma_kernel<T, R, D, M>, threads, smem);
+    static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(head_lpg_fwd_tma_kernel<T, R, D, M>, threads, smem); });
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;
     head_lpg_fwd_tma_kernel<T, R, D, M><<<blocks, threads, smem, st>>>(p);
@@ -99,7 +74,7 @@ template <typename T, int R, int D, int M> int launch_head_fwd(const HeadFwdPara
 template <typename T, int R, int D, int M> int launch_head_bwd(HeadBwdParams<T> &p, uint32_t max_blocks, cudaStream_t st) {
     const int threads = 256;
     if (g_tune_head_impl.load() == 1) {
-        static const int resident = occupancy_blocks(head_lpg_bwd_kernel<T, R, D, M>, threads);
+        static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks(head_lpg_bwd_kernel<T, R, D, M>, threads); });
         uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
         if (blocks > (uint32_t)resident) blocks = resident;
         if (blocks > max_blocks) blocks = max_blocks;
@@ -108,7 +83,7 @@ template <typename T, int R, int D, int M> int launch_head_bwd(HeadBwdParams<T> 
         return check_launch("btslpg_reduce_backward");
     }
     constexpr int smem = head_tma_smem_bytes<T, R, M, false>(256 / 32);
-    static const int resident = occupancy_blocks_smem(head_lpg_bwd_tma_kernel<T, R, D, M>, threads, smem);
+    static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(head_lpg_bwd_tma_kernel<T, R, D, M>, threads, smem); });
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
     if (blocks > (uint32_t)resident) blocks = resident;
     if (blocks > max_blocks) blocks = max_blocks;

@@ -1,136 +1,14 @@
-// btslpg_api.cu -- the C ABI of libbtslpg.so (declared in include/btslpg.h): argument
+// lpg_api.cu -- the LPG entry points and the introspection helpers of the C ABI of libbtslpg.so (declared in include/btslpg.h): argument
 // validation, variant selection and kernel launches.  No allocation, no synchronisation, no
 // CPU fallback: a host pointer or an unsupported layout is an error, never a slow path on the CPU.
-#include <cuda_runtime.h>
-
-#include <atomic>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-
-#include "../../include/btslpg.h"
-#include "head_kernels.cuh"
+#include "api_common.cuh"
 #include "lpg_kernels.cuh"
-#include "tail_kernels.cuh"
-#include "concat_kernels.cuh"
-#include "upsample_kernels.cuh"
-#include "slice_kernels.cuh"
-#include "depthconv_kernels.cuh"
 
 using namespace btslpg;
+using namespace btslpg_api;
 
 namespace {
 
-thread_local char tl_error[512] = "";
-thread_local char tl_kernel[128] = "";
-std::atomic<uint64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
-std::atomic<int> g_fwd_threads{0}, g_bwd_threads{0};
-extern std::atomic<int> g_tune_head_impl;
-std::atomic<int> g_tune_concat_impl{0};      // concat forward: 0 = staged kernel (default), 1 = chunked kernel where it applies (experiment)
-std::atomic<int> g_tune_depthconv_impl{0};   // last-convolution forward: 0 = tensor-core phase 1 (default), 1 = FP32-pipe phase 1
-
-int fail(int code, const char *fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-enum DType { kF32 = 0, kBF16 = 1 };
-
-// A tensor viewed as (B, H, W, C) with element strides.
-struct View {
-    char *ptr = nullptr;
-    int dtype = -1;
-    int dev = -1;
-    int64_t B = 0, H = 0, W = 0, C = 0;
-    int64_t sB = 0, sH = 0, sW = 0, sC = 0;
-    int esize() const { return dtype == kF32 ? 4 : 2; }
-    bool aligned(int bytes) const { return (reinterpret_cast<uintptr_t>(ptr) % bytes) == 0; }
-};
-
-int parse_common(const BtsTensor *t, const char *name, View &v) {
-    if (!t) return fail(BTSLPG_EINVAL, "%s: tensor is NULL", name);
-    if (!t->data && t->ndim > 0) {
-        int64_t n = 1;
-        for (int k = 0; k < t->ndim; ++k) n *= t->shape[k];
-        if (n != 0) return fail(BTSLPG_EINVAL, "%s: data pointer is NULL", name);
-    }
-    if (t->device.device_type != 2 && t->device.device_type != 13)
-        return fail(BTSLPG_EDEVICE, "%s: not a CUDA tensor (DLPack device_type %d); host tensors are not accepted -- "
-                                    "there is no CPU fallback", name, (int)t->device.device_type);
-    if (t->dtype.lanes != 1) return fail(BTSLPG_EDTYPE, "%s: dtype lanes must be 1", name);
-    if (t->dtype.code == 2 && t->dtype.bits == 32) v.dtype = kF32;
-    else if (t->dtype.code == 4 && t->dtype.bits == 16) v.dtype = kBF16;
-    else return fail(BTSLPG_EDTYPE, "%s: dtype (code %d, bits %d) is not float32 or bfloat16", name, (int)t->dtype.code, (int)t->dtype.bits);
-    v.dev = t->device.device_id;
-    v.ptr = static_cast<char *>(t->data) + t->byte_offset;
-    if (!t->shape) return fail(BTSLPG_ESHAPE, "%s: shape is NULL", name);
-    return 0;
-}
-
-void strides_of(const BtsTensor *t, int64_t *s) {
-    if (t->strides) {
-        for (int k = 0; k < t->ndim; ++k) s[k] = t->strides[k];
-    } else {
-        int64_t acc = 1;
-        for (int k = t->ndim - 1; k >= 0; --k) { s[k] = acc; acc *= t->shape[k]; }
-    }
-}
-
-// (B,h,w,C) NHWC tensor
-int parse_nhwc(const BtsTensor *t, const char *name, View &v) {
-    if (int e = parse_common(t, name, v)) return e;
-    if (t->ndim != 4) return fail(BTSLPG_ESHAPE, "%s: expected a rank-4 NHWC tensor, got rank %d", name, (int)t->ndim);
-    int64_t s[4];
-    strides_of(t, s);
-    v.B = t->shape[0]; v.H = t->shape[1]; v.W = t->shape[2]; v.C = t->shape[3];
-    v.sB = s[0]; v.sH = s[1]; v.sW = s[2]; v.sC = s[3];
-    if (v.B < 0 || v.H < 0 || v.W < 0 || v.C < 0) return fail(BTSLPG_ESHAPE, "%s: negative extent", name);
-    return 0;
-}
-
-// single-channel map given as (B,H,W,1) or (B,H,W)
-int parse_map(const BtsTensor *t, const char *name, View &v) {
-    if (int e = parse_common(t, name, v)) return e;
-    if (t->ndim != 3 && t->ndim != 4)
-        return fail(BTSLPG_ESHAPE, "%s: expected (B,H,W,1) or (B,H,W), got rank %d", name, (int)t->ndim);
-    if (t->ndim == 4 && t->shape[3] != 1)
-        return fail(BTSLPG_ESHAPE, "%s: last dimension must be 1, got %lld", name, (long long)t->shape[3]);
-    int64_t s[4];
-    strides_of(t, s);
-    v.B = t->shape[0]; v.H = t->shape[1]; v.W = t->shape[2]; v.C = 1;
-    v.sB = s[0]; v.sH = s[1]; v.sW = s[2]; v.sC = 1;
-    return 0;
-}
-
-bool is_contig_nhwc(const View &v) {
-    return v.sC == 1 && v.sW == v.C && v.sH == v.W * v.C && v.sB == v.H * v.W * v.C;
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    bool switched = false;
-    cudaError_t err = cudaSuccess;
-    explicit DeviceGuard(int dev) {
-        err = cudaGetDevice(&prev);
-        if (err == cudaSuccess && prev != dev) {
-            err = cudaSetDevice(dev);
-            switched = (err == cudaSuccess);
-        }
-    }
-    ~DeviceGuard() {
-        if (switched) cudaSetDevice(prev);
-    }
-};
-
-int check_launch(const char *what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(BTSLPG_ECUDA, "%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return 0;
-}
 
 int block_threads(bool fwd, int r) {
     int t = fwd ? g_fwd_threads.load() : g_bwd_threads.load();
@@ -139,40 +17,6 @@ int block_threads(bool fwd, int r) {
     if (t > 256) t = 256;
     t = (t + 31) / 32 * 32;
     return t;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Shape / layout checks shared by forward and backward.
-// ---------------------------------------------------------------------------------------------
-struct LayerGeom {
-    View coef, full, ds;
-    bool has_full = false, has_ds = false;
-    int r = 0, d = 0;
-};
-
-int check_geom(LayerGeom &g, const char *coef_name, const char *full_name, const char *ds_name) {
-    if (g.r < 1 || g.r > 64) return fail(BTSLPG_EINVAL, "upratio must be in [1, 64], got %d", g.r);
-    if (g.coef.C != 3) return fail(BTSLPG_ESHAPE, "%s: last dimension must be 3 [phi, theta, dist], got %lld", coef_name, (long long)g.coef.C);
-    const int64_t H = g.coef.H * g.r, W = g.coef.W * g.r;
-    if (g.has_full) {
-        if (g.full.B != g.coef.B || g.full.H != H || g.full.W != W)
-            return fail(BTSLPG_ESHAPE, "%s: expected (%lld,%lld,%lld[,1]) = (B, h*%d, w*%d), got (%lld,%lld,%lld)", full_name,
-                        (long long)g.coef.B, (long long)H, (long long)W, g.r, g.r, (long long)g.full.B, (long long)g.full.H, (long long)g.full.W);
-        if (g.full.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", full_name, coef_name);
-        if (g.full.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", full_name, coef_name);
-    }
-    if (g.has_ds) {
-        if (g.d < 1 || g.r % g.d != 0) return fail(BTSLPG_EINVAL, "ds_stride %d must be >= 1 and divide upratio %d", g.d, g.r);
-        if (g.ds.B != g.coef.B || g.ds.H != H / g.d || g.ds.W != W / g.d)
-            return fail(BTSLPG_ESHAPE, "%s: expected (%lld,%lld,%lld[,1]) = full[:, ::%d, ::%d], got (%lld,%lld,%lld)", ds_name,
-                        (long long)g.coef.B, (long long)(H / g.d), (long long)(W / g.d), g.d, g.d, (long long)g.ds.B, (long long)g.ds.H, (long long)g.ds.W);
-        if (g.ds.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "%s: dtype differs from %s", ds_name, coef_name);
-        if (g.ds.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "%s: on a different device than %s", ds_name, coef_name);
-    } else {
-        g.d = 0;
-    }
-    if (g.coef.B * g.coef.H * g.coef.W >= (int64_t)1 << 31) return fail(BTSLPG_ESHAPE, "%s: more than 2^31 coarse pixels", coef_name);
-    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -298,14 +142,25 @@ template <typename T> LpgGenericParams<T> make_generic_params(const LayerGeom &g
 // ---------------------------------------------------------------------------------------------
 // Variant dispatch: (T, R, PX, ROWS, D) are compile-time.
 // ---------------------------------------------------------------------------------------------
+// A patch split over LPP = R/ROWS consecutive warps exchanges its partial sums through shared memory indexed by the
+// CTA-local warp id: every group of LPP warps must lie inside ONE CTA, i.e. the CTA size is a multiple of 32*LPP.
+inline int split_threads(int threads, int lpp) {
+    const int unit = 32 * lpp;
+    threads = (threads + unit - 1) / unit * unit;
+    if (threads > 256) threads = 256 / unit * unit;
+    return threads < unit ? unit : threads;
+}
+
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_fwd_variant(const LpgFwdParams<T> &p, int threads, cudaStream_t st) {
+    threads = split_threads(threads, R / ROWS);
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
     lpg_fwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_fwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
 }
 template <typename T, int R, int PX, int ROWS, int D>
 void launch_bwd_variant(const LpgBwdParams<T> &p, int threads, cudaStream_t st) {
+    threads = split_threads(threads, R / ROWS);
     const uint32_t nthreads = threads_for(p.groups, R / ROWS);
     lpg_bwd_vec_kernel<T, R, PX, ROWS, D><<<(nthreads + threads - 1) / threads, threads, 0, st>>>(p);
     snprintf(tl_kernel, sizeof(tl_kernel), "lpg_bwd_vec<%s,r%d,px%d,rows%d,ds%d>", ElemTraits<T>::kName, R, PX, ROWS, D);
@@ -331,43 +186,6 @@ template <typename T, typename P, bool FWD> void dispatch_vec(const P &p, int r,
     }
     if constexpr (sizeof(T) == 4) { BTSLPG_VARIANTS_F32(BTSLPG_TRY) } else { BTSLPG_VARIANTS_BF16(BTSLPG_TRY) }
 #undef BTSLPG_TRY
-}
-
-int parse_layer_fwd(const BtsTensor *coef, int upratio, BtsTensor *out_full, BtsTensor *out_ds, int ds_stride, LayerGeom &g) {
-    if (int e = parse_nhwc(coef, "coef", g.coef)) return e;
-    if (int e = parse_map(out_full, "out_full", g.full)) return e;
-    g.has_full = true;
-    g.has_ds = out_ds != nullptr;
-    if (g.has_ds) {
-        if (int e = parse_map(out_ds, "out_ds", g.ds)) return e;
-    }
-    g.r = upratio;
-    g.d = ds_stride;
-    return check_geom(g, "coef", "out_full", "out_ds");
-}
-
-int parse_layer_bwd(const BtsTensor *coef, const BtsTensor *g_full, const BtsTensor *g_ds, int upratio, int ds_stride,
-                    BtsTensor *g_coef, LayerGeom &g, View &gc) {
-    if (int e = parse_nhwc(coef, "coef", g.coef)) return e;
-    g.has_full = g_full != nullptr;
-    g.has_ds = g_ds != nullptr;
-    if (g.has_full) {
-        if (int e = parse_map(g_full, "g_full", g.full)) return e;
-    }
-    if (g.has_ds) {
-        if (int e = parse_map(g_ds, "g_ds", g.ds)) return e;
-    }
-    g.r = upratio;
-    g.d = ds_stride;
-    if (int e = check_geom(g, "coef", "g_full", "g_ds")) return e;
-    if (g_coef) {
-        if (int e = parse_nhwc(g_coef, "g_coef", gc)) return e;
-        if (gc.B != g.coef.B || gc.H != g.coef.H || gc.W != g.coef.W || gc.C != 3)
-            return fail(BTSLPG_ESHAPE, "g_coef: shape must equal coef's (B,h,w,3)");
-        if (gc.dtype != g.coef.dtype) return fail(BTSLPG_EDTYPE, "g_coef: dtype differs from coef");
-        if (gc.dev != g.coef.dev) return fail(BTSLPG_EDEVICE, "g_coef: on a different device than coef");
-    }
-    return 0;
 }
 
 template <typename T> int run_forward(const LayerGeom &g, cudaStream_t st) {
@@ -564,10 +382,3 @@ int btslpg_backward_multi(const BtsLpgBackwardArgs *layers, int n, void *stream)
 }
 
 }  // extern "C"
-
-#include "head_api.inl"
-#include "tail_api.inl"
-#include "concat_api.inl"
-#include "upsample_api.inl"
-#include "slice_api.inl"
-#include "depthconv_api.inl"

@@ -103,7 +103,7 @@ __device__ __forceinline__ void sincos_quadrant2(F2 a, Angles &o) {
 
 // out-of-range path (huge, inf or NaN inputs): results come back in registers, so taking it does not
 // force the fast path's values through local memory
-__device__ __noinline__ float4 decode_angles_slow(float phi, float theta) {
+static __device__ __noinline__ float4 decode_angles_slow(float phi, float theta) {
     float4 r;
     sincosf(phi, &r.x, &r.y);
     sincosf(theta, &r.z, &r.w);
@@ -178,9 +178,6 @@ template <int ROWS, int D, int SUB> __device__ __forceinline__ constexpr bool ds
     return D != 0 && ((SUB * ROWS + k) % (D ? D : 1)) == 0;
 }
 
-template <int V> struct IntC {
-    static constexpr int value = V;
-};
 // call f(IntC<sub>) with `sub` (0 <= sub < N, warp-uniform) turned into a compile-time constant
 template <int N, typename F> __device__ __forceinline__ void dispatch_sub(int sub, F &&f) {
     static_assert(N == 1 || N == 2 || N == 4, "patches are split over 1, 2 or 4 warps");

@@ -1,4 +1,4 @@
-// slice_api.inl -- C ABI for the strided affine + activation copy (DenseASPP glue, bts_decoder.py:46-76); included by btslpg_api.cu.
+// slice_api.inl -- C ABI for the strided affine + activation copy (DenseASPP glue, bts_decoder.py:46-76); included by its own .cu translation unit.
 
 namespace {
 

@@ -1,17 +1,6 @@
-// tail_api.inl -- C ABI for the decoder-tail entry points (silog loss, eval metrics); included by btslpg_api.cu.
+// tail_api.inl -- C ABI for the decoder-tail entry points (silog loss, eval metrics); included by its own .cu translation unit.
 
 namespace {
-
-// flat (B,H,W[,1]) map: contiguous, 16-byte aligned
-int parse_flat(const BtsTensor *t, const char *name, View &v, int64_t &n) {
-    if (int e = parse_map(t, name, v)) return e;
-    n = v.B * v.H * v.W;
-    // strides of extent-1 dimensions carry no information (torch reports arbitrary values there)
-    if (n > 0 && !((v.W == 1 || v.sW == 1) && (v.H == 1 || v.sH == v.W) && (v.B == 1 || v.sB == v.H * v.W)))
-        return fail(BTSLPG_ELAYOUT, "%s: must be contiguous", name);
-    if (!v.aligned(16)) return fail(BTSLPG_ELAYOUT, "%s: must be 16-byte aligned", name);
-    return 0;
-}
 
 int same_as(const View &a, int64_t na, const View &ref, int64_t nref, const char *name, const char *ref_name) {
     if (na != nref || a.B != ref.B || a.H != ref.H || a.W != ref.W) return fail(BTSLPG_ESHAPE, "%s: shape differs from %s", name, ref_name);
@@ -20,27 +9,11 @@ int same_as(const View &a, int64_t na, const View &ref, int64_t nref, const char
     return 0;
 }
 
-// float32 device vector with at least `need` elements
-int parse_f32_vec(const BtsTensor *t, const char *name, int64_t need, int dev, float *&ptr) {
-    View v;
-    if (int e = parse_common(t, name, v)) return e;
-    if (v.dtype != kF32) return fail(BTSLPG_EDTYPE, "%s: must be float32", name);
-    if (v.dev != dev) return fail(BTSLPG_EDEVICE, "%s: on a different device", name);
-    int64_t n = 1;
-    for (int k = 0; k < t->ndim; ++k) n *= t->shape[k];
-    if (n < need) return fail(BTSLPG_ESHAPE, "%s: needs at least %lld float32 elements, got %lld", name, (long long)need, (long long)n);
-    if (t->strides && t->ndim > 0 && t->shape[t->ndim - 1] > 1 && t->strides[t->ndim - 1] != 1)
-        return fail(BTSLPG_ELAYOUT, "%s: must be contiguous", name);
-    if (!v.aligned(4)) return fail(BTSLPG_ELAYOUT, "%s: misaligned", name);
-    ptr = reinterpret_cast<float *>(v.ptr);
-    return 0;
-}
-
 // persistent grid: one wave of resident CTAs (occupancy of this kernel x SMs), never more than the work needs
 template <typename KernelT> int tail_blocks(KernelT kernel, int64_t n, int elems_per_vec) {
     const int64_t nvec = n / elems_per_vec;
     int64_t b = (nvec + 2 * kTailThreads - 1) / (2 * kTailThreads);      // two vectors per thread and iteration
-    static const int64_t resident = occupancy_blocks(kernel, kTailThreads);   // queried once per kernel
+    static PerDevice per_dev; const int64_t resident = per_dev.get([&] { return occupancy_blocks(kernel, kTailThreads); });   // queried once per kernel
     if (b > resident) b = resident;
     if (b > kTailMaxBlocks) b = kTailMaxBlocks;
     if (b < 1) b = 1;

@@ -1,4 +1,4 @@
-// upsample_api.inl -- C ABI for the nearest x2 up-sampling (bts_decoder.py:31, :38, :97); included by btslpg_api.cu.
+// upsample_api.inl -- C ABI for the nearest x2 up-sampling (bts_decoder.py:31, :38, :97); included by its own .cu translation unit.
 
 namespace {
 
