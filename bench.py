@@ -17,7 +17,11 @@ Timing hygiene: >= 3 warm-up steps; each step works on one of several disjoint b
 launching stream; max over ranks; SM clocks and throttle reasons sampled through NVML.
 
 `--impl reference`: times the CPU restatement of the reference (oracle/lpg_literal.py, all host
-threads) on bounded samples of the same workload; rank 0 only.
+threads) on the same workload (whole batch per step, the given step / warm-up counts); rank 0 only.
+
+`extras` carries the numbers DESIGN.md / BASELINE.md quote next to the headline: the fused head kernels the decoder
+actually launches (extras.heads), bf16 I/O (extras.bf16), the decoder-tail kernels (extras.tail), and BASELINE configs
+3-5 (extras.decoder_config3/4/5: decoder images/s, inference and the data-parallel training step with its all-reduce).
 """
 import argparse
 import json
@@ -54,7 +58,10 @@ def parse_args():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--ref-sample-batch", type=int, default=4, help="--impl reference: images per step sample")
+    ap.add_argument("--ref-sample-batch", type=int, default=0, help="--impl reference: images per step (0 = the whole batch, the default)")
+    ap.add_argument("--ref-max-seconds", type=float, default=240.0, help="--impl reference: wall-clock guard of the timed loop")
+    ap.add_argument("--skip-train", action="store_true", help="skip the training-step context lines (extras.decoder_config4 / 5)")
+    ap.add_argument("--decoder-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -136,33 +143,42 @@ def time_cpu_baseline(a, budget_s):
 
 
 def run_reference_arm(a):
-    """--impl reference: rank 0 only; the CPU restatement on all host threads, K bounded samples."""
+    """--impl reference: rank 0 only; the CPU restatement of the reference on all host threads, on the SAME config as the
+    B200 arm: every step is one forward + backward of the three LPG layers over the whole batch (a full pass takes ~0.3 s on
+    32 cores), exactly --steps timed steps after --warmup warm-up steps.  --ref-sample-batch N (< batch) restricts a step to
+    N images for slow hosts; a wall-clock guard (--ref-max-seconds) stops early and reports the steps actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sb = max(1, min(a.batch, a.ref_sample_batch))
+    sb = a.batch if a.ref_sample_batch <= 0 else max(1, min(a.batch, a.ref_sample_batch))
     run, nbytes = cpu_reference_pass(sb, a.height, a.width)
-    steps = max(1, min(a.steps, 20))
-    warm = max(1, min(a.warmup, 3))
+    steps, warm = max(1, a.steps), max(a.warmup, 3)          # the B200 arm clamps its warm-up the same way
+    t_guard = time.perf_counter()
     for _ in range(warm):
         run()
+        if time.perf_counter() - t_guard > a.ref_max_seconds / 4:
+            break
+    done = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         run()
+        done += 1
+        if time.perf_counter() - t0 > a.ref_max_seconds:
+            break
     dt = time.perf_counter() - t0
-    value = nbytes * steps / dt / 1e9
+    value = nbytes * done / dt / 1e9
+    sample = "%d steps x %d of %d images, fwd+bwd of the three LPG layers at %dx%d" % (done, sb, a.batch, a.height, a.width)
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": done,
+        "warmup": warm, "ms_per_step": round(dt / done * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "step_sample": "%d of %d images per step" % (sb, a.batch),
                    "note": "TensorFlow is not installable in this image: this is the op-by-op torch-CPU restatement "
                            "of the reference layer (oracle/lpg_literal.py), not TensorFlow"},
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d images, fwd+bwd of the three LPG layers at %dx%d" % (steps, sb, a.height, a.width)},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,59 +245,44 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # the B200 arm
 # --------------------------------------------------------------------------------------------
-def decoder_context(device, rank, world, barrier, global_batch=64, H=480, W=640, steps=5, warmup=3):
-    """BASELINE config 3: BTS-NYU DenseNet-161 decoder, batched inference at 480x640, global batch 64 sharded over the
-    ranks (strong scaling), synthetic encoder taps of the reference's shapes (bts.py:72,80), random-init decoder."""
+def _tools():
+    tp = os.path.join(ROOT, "tools")
+    if tp not in sys.path:
+        sys.path.insert(0, tp)
+
+
+def decoder_context(cfg_id, rank, local_rank, world, steps=5, warmup=3):
+    """BASELINE configs 3-5 (tools/bench_decoder.py): the decoder with this repo's kernels around cuDNN's convolutions, global
+    batch sharded over the ranks (strong scaling), synthetic encoder taps of the reference's shapes (bts.py:72,80).  Config 3:
+    batched inference as one CUDA graph.  Configs 4 / 5: the data-parallel training step of trainer.DataParallelStep -- the
+    gradient all-reduce is the one collective of the design, so these are the lines that exercise NCCL."""
     import torch
-    import torch.distributed as dist
-    from bts_fully_tf_b200 import ops, parallel
-    from bts_fully_tf_b200.decoder import BtsDecoder
-    chans, filters = [2208, 96, 96, 192, 384], 512
-    lo, hi = parallel.shard_range(global_batch, world, rank)
-    b = hi - lo
+    _tools()
+    import bench_decoder
     torch.backends.cudnn.benchmark = True            # TensorFlow autotunes cuDNN by default as well
-    torch.manual_seed(rank)
-    feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=device)) for s, c in zip((32, 2, 4, 8, 16), chans)]
-    dec = BtsDecoder(chans, 10.0, num_filters=filters).to(device).eval()
-    graph = None
-    with torch.no_grad():
-        for _ in range(warmup):
-            out = dec(feats)
-        ops.reset_launch_count()
-        out = dec(feats)
-        launches = ops.launch_count()
-        try:        # the whole step as one CUDA graph: it is launch-bound at small per-GPU batches
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    out = dec(feats)
-            torch.cuda.current_stream().wait_stream(side)
-            g.replay()
-            graph = g
-        except Exception:  # noqa: BLE001
-            graph = None
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            if graph is not None:
-                graph.replay()
-            else:
-                out = dec(feats)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return {"workload": "BTS-NYU DenseNet-161 decoder inference 480x640, global batch %d (BASELINE config 3; encoder out of scope: "
-                        "synthetic taps)" % global_batch,
-            "images_per_s": round(global_batch * steps / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 3), "per_gpu_batch": b,
-            "scaling": "strong", "steps": steps, "warmup": warmup, "own_kernel_launches_per_step": launches, "cuda_graph": graph is not None,
-            "conv_math": "TF32 on cuDNN (autotuned)", "result_mean": float(out.float().mean())}
+    return bench_decoder.run_config(cfg_id, rank, local_rank, world, steps=steps, warmup=warmup)
+
+
+def heads_context(peak):
+    """The fused reduction-head + LPG kernels the decoder launches (bts_decoder.py:79-94) at config-2 shapes, both encoders,
+    float32: 12 points (forward and backward of r = 8 / 4 / 2), same timing hygiene as the headline."""
+    _tools()
+    import sweep_head
+    out = sweep_head.collect(dtypes=("f32",))
+    pts = out["points"]
+    fr = [p["frac"] for p in pts]
+    return {"points": pts, "min_frac": min(fr), "max_frac": max(fr), "peak": out["peak"],
+            "note": "B=32, 480x640; densenet161 C=128/128/64, resnet50 C=64/64/32; algorithmic bytes per BASELINE.md section 3"}
+
+
+def tail_context():
+    """silog fwd/bwd, the nine metrics, fused ELU + concat1 fwd/bwd, the last convolution fwd/bwd at B=32, 480x640, float32."""
+    _tools()
+    import bench_tail
+    r = bench_tail.collect(["--skip-cpu", "--skip-literal", "--steps", "64"])
+    keep = ("silog_fwd", "silog_bwd", "eval_metrics", "concat1_fwd", "concat1_bwd", "depthconv_fwd_C32", "depthconv_bwd_C32",
+            "depthconv_fwd_C16", "depthconv_bwd_C16")
+    return {k: {kk: r[k][kk] for kk in ("us", "GBps", "frac_of_peak", "kernel") if kk in r[k]} for k in keep if k in r}
 
 
 def main():
@@ -460,12 +461,25 @@ def main():
                          "frac_of_peak": round(nb / (msw / max(K, 50) * 1e-3) / 1e9 / peak, 4)}
         extras["per_pass"] = per
 
+    # ---- bf16 I/O (float32 arithmetic) on the same launches: half the bytes, same instruction count
+    if not a.skip_extras and a.dtype == "f32" and best == "multi":
+        try:
+            bsets = [DeviceSet(B, H, W, torch.bfloat16, device, generator=gen) for _ in range(a.sets)]
+            bf = {}
+            for what, nb in (("both", step_bytes // 2), ("fwd", fwd_b // 2), ("bwd", bwd_b // 2)):
+                fnb, _ = make_runner(True, what, bsets)
+                msb = time_steps(fnb, max(K, 50), WU)
+                us = msb / max(K, 50) * 1e3
+                bf[what] = {"us": round(us, 2), "GBps": round(nb / us / 1e3, 1), "frac_of_peak": round(nb / us / 1e3 / peak, 4)}
+            extras["bf16"] = {"workload": "the same three-scale launches with bfloat16 tensors (float32 arithmetic)", **bf}
+            del bsets
+        except Exception as exc:  # noqa: BLE001
+            extras["bf16"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
     # ---- end to end: host buffers in, host buffers out, through the public API
-    e2e = None
-    if not a.skip_e2e:
-        pipe = HostLpgPipeline(B, H, W, dtype, device, slots=2, fused=(best == "multi"))
+    def time_e2e(run_kernels=True, return_ds=True, slots=3, n_e2e=20):
+        pipe = HostLpgPipeline(B, H, W, dtype, device, slots=slots, fused=(best == "multi"), return_ds=return_ds, run_kernels=run_kernels)
         host = HostSet(sets[0])
-        n_e2e = max(3, min(K, 20))
         for _ in range(3):
             pipe.step(host)
         pipe.drain()
@@ -485,27 +499,58 @@ def main():
             t = torch.tensor([ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        # the results really are on the host: checksum one of them against the device copy
-        chk = float(host.layers[-1]["g_coef"].float().abs().sum())
-        e2e = {"value": round(world * step_bytes * n_e2e / (ms * 1e-3) / 1e9, 2), "unit": UNIT,
-               "h2d_bytes_per_step": host.bytes_in(), "d2h_bytes_per_step": host.bytes_out(), "steps": n_e2e,
-               "ms_per_step": round(ms / n_e2e, 3), "result_checksum": chk,
-               "path": "bts_fully_tf_b200.host_io.HostLpgPipeline -> libbtslpg.so (pinned host in/out, 3 streams)"}
+        chk = float(host.layers[-1]["g_coef"].float().abs().sum())       # the results really are on the host
+        out = {"value": round(world * step_bytes * n_e2e / (ms * 1e-3) / 1e9, 2), "ms_per_step": round(ms / n_e2e, 3), "steps": n_e2e,
+               "h2d": host.bytes_in(), "d2h": host.bytes_out(return_ds), "checksum": chk,
+               "pcie_GBps_per_gpu": round((host.bytes_in() + host.bytes_out(return_ds)) * n_e2e / (ms * 1e-3) / 1e9, 2)}
+        del pipe, host
+        return out
+
+    e2e = None
+    if not a.skip_e2e:
+        n_e2e = max(3, min(K, 20))
+        main_leg = time_e2e(True, True, 3, n_e2e)
+        copy_leg = time_e2e(False, True, 3, n_e2e)          # same buffers / streams / events, no kernels: the platform's ceiling
+        e2e = {"value": main_leg["value"], "unit": UNIT, "h2d_bytes_per_step": main_leg["h2d"], "d2h_bytes_per_step": main_leg["d2h"],
+               "steps": n_e2e, "ms_per_step": main_leg["ms_per_step"], "result_checksum": main_leg["checksum"],
+               "pcie_GBps_per_gpu": main_leg["pcie_GBps_per_gpu"],
+               "copy_only_ceiling": {"value": copy_leg["value"], "ms_per_step": copy_leg["ms_per_step"], "pcie_GBps_per_gpu": copy_leg["pcie_GBps_per_gpu"],
+                                     "what": "the same pinned buffers, three streams and events with the kernel launches removed"},
+               "frac_of_copy_ceiling": round(main_leg["value"] / copy_leg["value"], 4) if copy_leg["value"] else None,
+               "path": "bts_fully_tf_b200.host_io.HostLpgPipeline -> libbtslpg.so (pinned host in/out, 3 streams, 3 device slots)"}
+        if not a.skip_extras:
+            try:
+                nods = time_e2e(True, False, 3, n_e2e)
+                extras["e2e_without_ds_readback"] = {"value": nods["value"], "ms_per_step": nods["ms_per_step"], "d2h_bytes_per_step": nods["d2h"],
+                                                     "note": "out_ds = out_full[:, ::d, ::d] is not copied back (the host can slice it)"}
+            except Exception as exc:  # noqa: BLE001
+                extras["e2e_without_ds_readback"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- context for the second half of BASELINE.json's metric ("BTS decoder images/s at 1/2/4/8 B200"): config 3,
-    # the decoder with this repo's kernels around cuDNN's convolutions; a failure here never touches the headline line
-    if not a.skip_decoder:
-        try:
-            del all_sets, sets
-            if not a.skip_e2e:
-                del pipe, host
+    del all_sets, sets
+    torch.cuda.empty_cache()
+
+    # ---- the kernels the decoder actually launches (fused heads) and the decoder-tail kernels, same hygiene (N = 1 only)
+    if not a.skip_extras and world == 1 and a.dtype == "f32":
+        for key, fn in (("heads", lambda: heads_context(peak)), ("tail", tail_context)):
+            try:
+                extras[key] = fn()
+            except Exception as exc:  # noqa: BLE001
+                extras[key] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
             torch.cuda.empty_cache()
-            extras["decoder_config3"] = decoder_context(device, rank, world, barrier)
-        except Exception as exc:  # noqa: BLE001
-            extras["decoder_config3"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
+    # ---- context for the second half of BASELINE.json's metric ("BTS decoder images/s at 1/2/4/8 B200"): config 3 (batched
+    # inference) and the data-parallel training steps of configs 4 / 5 -- the only lines with a collective (the gradient
+    # all-reduce); a failure here never touches the headline line
+    if not a.skip_decoder:
+        for cfg_id in (3,) + (() if a.skip_train else (5, 4)):
+            try:
+                extras["decoder_config%d" % cfg_id] = decoder_context(cfg_id, rank, local_rank, world, steps=a.decoder_steps)
+            except Exception as exc:  # noqa: BLE001
+                extras["decoder_config%d" % cfg_id] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu:

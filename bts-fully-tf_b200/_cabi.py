@@ -47,6 +47,12 @@ class BtsLpgBackwardArgs(ctypes.Structure):
                 ("upratio", ctypes.c_int32), ("ds_stride", ctypes.c_int32), ("g_coef", ctypes.POINTER(BtsTensor))]
 
 
+class BtsAdamConfig(ctypes.Structure):
+    _fields_ = [("lr_start", ctypes.c_float), ("lr_end", ctypes.c_float), ("total_steps", ctypes.c_int64), ("power", ctypes.c_float),
+                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("epsilon", ctypes.c_float), ("l1", ctypes.c_float),
+                ("l2", ctypes.c_float), ("grad_scale", ctypes.c_float), ("zero_grad", ctypes.c_int32)]
+
+
 _TP = ctypes.POINTER(BtsTensor)
 
 # name -> (restype, argtypes); every symbol include/btslpg.h declares
@@ -69,6 +75,10 @@ SYMBOLS = {
                                              ctypes.c_int, _TP, ctypes.c_void_p]),
     "btslpg_eval_metrics": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p, ctypes.c_size_t,
                                            ctypes.c_void_p]),
+    "btslpg_eval_metrics_png16": (ctypes.c_int, [_TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_float, _TP, ctypes.c_void_p,
+                                                 ctypes.c_size_t, ctypes.c_void_p]),
+    "btslpg_adam_step": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, ctypes.POINTER(BtsAdamConfig), ctypes.c_int, ctypes.c_void_p]),
+    "btslpg_device_synchronize": (ctypes.c_int, [ctypes.c_int]),
     "btslpg_concat_forward": (ctypes.c_int, [_TP, ctypes.c_int, ctypes.c_int, _TP, _TP, _TP, ctypes.POINTER(_TP), ctypes.c_int, ctypes.c_int,
                                              _TP, ctypes.c_void_p]),
     "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int,
@@ -156,6 +166,10 @@ def _torch_dtype_code(t):
         return 2, 16
     if t.dtype == torch.float64:
         return 2, 64
+    if t.dtype == torch.uint16:
+        return 1, 16
+    if t.dtype == torch.int16:         # carries the uint16 PNG image on hosts without an unsigned 16-bit dtype
+        return 1, 16
     raise ValueError("unsupported tensor dtype %s" % (t.dtype,))
 
 

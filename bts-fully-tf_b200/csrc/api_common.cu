@@ -21,3 +21,12 @@ int fail(int code, const char *fmt, ...) {
 }
 
 }  // namespace btslpg_api
+
+extern "C" int btslpg_device_synchronize(int device_id) {
+    using namespace btslpg_api;
+    DeviceGuard guard(device_id);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", device_id, cudaGetErrorString(guard.err));
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaDeviceSynchronize: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -108,35 +108,79 @@ int btslpg_silog_backward(const BtsTensor *depth_est, const BtsTensor *y_true, f
     return y.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
 }
 
-int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval, float max_depth_eval, BtsTensor *metrics,
-                        void *workspace, size_t workspace_bytes, void *stream) {
+int btslpg_eval_metrics_png16(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval, float max_depth_eval, BtsTensor *metrics,
+                              float png_max_depth, BtsTensor *png, void *workspace, size_t workspace_bytes, void *stream) {
     View yt, yp;
     int64_t n = 0, np_ = 0;
-    if (int e = parse_flat(y_true, "y_true", yt, n)) return e;
+    const bool with_metrics = y_true != nullptr;
     if (int e = parse_flat(y_pred, "y_pred", yp, np_)) return e;
-    if (int e = same_as(yp, np_, yt, n, "y_pred", "y_true")) return e;
+    if (with_metrics) {
+        if (int e = parse_flat(y_true, "y_true", yt, n)) return e;
+        if (int e = same_as(yp, np_, yt, n, "y_pred", "y_true")) return e;
+    } else if (!png) {
+        return fail(BTSLPG_EINVAL, "y_true and png are both NULL: nothing to compute");
+    }
     float *out = nullptr;
-    if (!metrics) return fail(BTSLPG_EINVAL, "metrics: tensor is NULL");
-    if (int e = parse_f32_vec(metrics, "metrics", 10, yt.dev, out)) return e;
-    if (int e = check_tail_ws(workspace, workspace_bytes, "btslpg_eval_metrics")) return e;
-    DeviceGuard guard(yt.dev);
-    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", yt.dev, cudaGetErrorString(guard.err));
+    if (with_metrics) {
+        if (!metrics) return fail(BTSLPG_EINVAL, "metrics: tensor is NULL");
+        if (int e = parse_f32_vec(metrics, "metrics", 10, yp.dev, out)) return e;
+        if (int e = check_tail_ws(workspace, workspace_bytes, "btslpg_eval_metrics")) return e;
+    }
+    uint16_t *png_ptr = nullptr;
+    if (png) {
+        // uint16 image (kDLUInt = 1, 16 bits), same number of elements as y_pred, contiguous, 16-byte aligned
+        if (png->device.device_type != 2 && png->device.device_type != 13)
+            return fail(BTSLPG_EDEVICE, "png: not a CUDA tensor; host tensors are not accepted -- there is no CPU fallback");
+        if (png->dtype.code != 1 || png->dtype.bits != 16 || png->dtype.lanes != 1) return fail(BTSLPG_EDTYPE, "png: must be uint16");
+        if (png->device.device_id != yp.dev) return fail(BTSLPG_EDEVICE, "png: on a different device than y_pred");
+        int64_t m = 1, acc = 1;
+        for (int k = 0; k < png->ndim; ++k) m *= png->shape[k];
+        if (m != np_) return fail(BTSLPG_ESHAPE, "png: needs %lld elements like y_pred, got %lld", (long long)np_, (long long)m);
+        if (png->strides) {
+            for (int k = png->ndim - 1; k >= 0; --k) {
+                if (png->shape[k] != 1 && png->strides[k] != acc) return fail(BTSLPG_ELAYOUT, "png: must be contiguous");
+                acc *= png->shape[k];
+            }
+        }
+        png_ptr = reinterpret_cast<uint16_t *>(static_cast<char *>(png->data) + png->byte_offset);
+        if (reinterpret_cast<uintptr_t>(png_ptr) % 16) return fail(BTSLPG_ELAYOUT, "png: must be 16-byte aligned");
+        if (!(png_max_depth > 0.0f)) return fail(BTSLPG_EINVAL, "png_max_depth must be positive");
+    }
+    n = np_;
+    DeviceGuard guard(yp.dev);
+    if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", yp.dev, cudaGetErrorString(guard.err));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
         MetricsParams<T> p;
-        p.y_true = reinterpret_cast<const T *>(yt.ptr);
+        p.y_true = with_metrics ? reinterpret_cast<const T *>(yt.ptr) : nullptr;
         p.y_pred = reinterpret_cast<const T *>(yp.ptr);
         p.out = out;
         p.workspace = workspace;
         p.n = (uint64_t)n;
         p.min_depth = min_depth_eval;
         p.max_depth = max_depth_eval;
-        eval_metrics_kernel<T><<<tail_blocks(eval_metrics_kernel<T>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "eval_metrics<%s>", ElemTraits<T>::kName);
+        p.png = png_ptr;
+        p.png_max_depth = png_max_depth;
+        if (with_metrics && png_ptr) {
+            eval_metrics_kernel<T, true, true><<<tail_blocks(eval_metrics_kernel<T, true, true>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "eval_metrics_png16<%s>", ElemTraits<T>::kName);
+        } else if (with_metrics) {
+            eval_metrics_kernel<T, false, true><<<tail_blocks(eval_metrics_kernel<T, false, true>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "eval_metrics<%s>", ElemTraits<T>::kName);
+        } else {
+            eval_metrics_kernel<T, true, false><<<tail_blocks(eval_metrics_kernel<T, true, false>, n, TailVec<T>::N), kTailThreads, 0, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "depth_png16<%s>", ElemTraits<T>::kName);
+        }
         return check_launch("btslpg_eval_metrics");
     };
-    return yt.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+    return yp.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval, float max_depth_eval, BtsTensor *metrics,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (!y_true) return fail(BTSLPG_EINVAL, "y_true: tensor is NULL");
+    return btslpg_eval_metrics_png16(y_true, y_pred, min_depth_eval, max_depth_eval, metrics, 1.0f, nullptr, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -279,7 +279,25 @@ template <typename T> struct MetricsParams {
     void *workspace;
     uint64_t n;
     float min_depth, max_depth;
+    uint16_t *png;       // bts_predict.py:140-141 output, nullable (PNG template flag)
+    float png_max_depth;
 };
+
+// bts_predict.py:140-141: `pred_depth * 65536 / args.max_depth` in float32, then numpy's `.astype(np.uint16)`: the C cast of
+// x86-64 numpy (float -> int32 by truncation, low 16 bits kept: a prediction that rounds to max_depth wraps to 0, NaN and
+// out-of-range values give 0 -- the reference does not clamp, so neither does this).
+__device__ __forceinline__ uint16_t png16(float depth, float max_depth) {
+    const float v = __fdiv_rn(depth * 65536.0f, max_depth);
+    const int i = (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;      // cvttss2si: "integer indefinite" when out of range / NaN
+    return (uint16_t)(unsigned)i;
+}
+template <int N> __device__ __forceinline__ void png16_store(uint16_t *dst, const float (&pr)[N], float max_depth) {
+    uint32_t w[N / 2];
+#pragma unroll
+    for (int e = 0; e < N / 2; ++e) w[e] = (uint32_t)png16(pr[2 * e], max_depth) | ((uint32_t)png16(pr[2 * e + 1], max_depth) << 16);
+    if constexpr (N == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 __device__ __forceinline__ void metrics_accum(float gt, float pr, float lo_, float hi_, float (&acc)[10]) {
     const bool valid = gt < hi_ && gt > lo_;                                 // :39
@@ -305,7 +323,9 @@ __device__ __forceinline__ void metrics_accum(float gt, float pr, float lo_, flo
     acc[9] += ratio < 1.953125f ? w : 0.0f;                                  // :55  1.25 ** 3
 }
 
-template <typename T> __global__ void __launch_bounds__(kTailThreads) eval_metrics_kernel(const __grid_constant__ MetricsParams<T> prm) {
+// PNG: additionally write the uint16 depth image of bts_predict.py:140-141 from the same read of y_pred (N4's second half);
+// METRICS = false (no ground truth, as in bts_predict.py): the scaling pass alone.
+template <typename T, bool PNG, bool METRICS> __global__ void __launch_bounds__(kTailThreads) eval_metrics_kernel(const __grid_constant__ MetricsParams<T> prm) {
     constexpr int N = TailVec<T>::N;
     __shared__ double tot[10];
     const uint64_t nvec = prm.n / N;
@@ -317,22 +337,33 @@ template <typename T> __global__ void __launch_bounds__(kTailThreads) eval_metri
         const uint64_t i2 = i + stride;
         const bool two = i2 < nvec;
         float gt[2][N], pr[2][N];
-        load_elems<T, N, 4>(prm.y_true + i * N, gt[0]);
+        if constexpr (METRICS) load_elems<T, N, 4>(prm.y_true + i * N, gt[0]);
         load_elems<T, N, 4>(prm.y_pred + i * N, pr[0]);
         if (two) {
-            load_elems<T, N, 4>(prm.y_true + i2 * N, gt[1]);
+            if constexpr (METRICS) load_elems<T, N, 4>(prm.y_true + i2 * N, gt[1]);
             load_elems<T, N, 4>(prm.y_pred + i2 * N, pr[1]);
         }
+        if constexpr (PNG) png16_store<N>(prm.png + i * N, pr[0], prm.png_max_depth);
+        if constexpr (METRICS) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) metrics_accum(gt[0][e], pr[0][e], prm.min_depth, prm.max_depth, acc);
+            for (int e = 0; e < N; ++e) metrics_accum(gt[0][e], pr[0][e], prm.min_depth, prm.max_depth, acc);
+        }
         if (two) {
+            if constexpr (PNG) png16_store<N>(prm.png + i2 * N, pr[1], prm.png_max_depth);
+            if constexpr (METRICS) {
 #pragma unroll
-            for (int e = 0; e < N; ++e) metrics_accum(gt[1][e], pr[1][e], prm.min_depth, prm.max_depth, acc);
+                for (int e = 0; e < N; ++e) metrics_accum(gt[1][e], pr[1][e], prm.min_depth, prm.max_depth, acc);
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (uint64_t i = nvec * N; i < prm.n; ++i) metrics_accum(load1(prm.y_true + i), load1(prm.y_pred + i), prm.min_depth, prm.max_depth, acc);
+        for (uint64_t i = nvec * N; i < prm.n; ++i) {
+            const float pv = load1(prm.y_pred + i);
+            if constexpr (PNG) prm.png[i] = png16(pv, prm.png_max_depth);
+            if constexpr (METRICS) metrics_accum(load1(prm.y_true + i), pv, prm.min_depth, prm.max_depth, acc);
+        }
     }
+    if constexpr (!METRICS) return;
     const TailWorkspace ws(prm.workspace);
     if (tail_grid_sum<10>(acc, ws, tot) && threadIdx.x == 0) {
         const double n = tot[0], m1 = tot[1] / n, m2 = tot[2] / n;

@@ -157,6 +157,15 @@ class BtsDecoder(nn.Module):
         self.iconv1 = _conv(nf + 3, nf)
         self.depth_conv = _conv(nf, 1)
         self.intermediates = {}
+        self._loss_ws = None
+        self.reset_parameters_keras()
+
+    def reset_parameters_keras(self):
+        """Keras defaults of the reference's layers (bts_decoder.py builds every Conv2D without an initializer argument):
+        kernel_initializer = glorot_uniform; BatchNormalization gamma = 1, beta = 0 (torch's defaults already)."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
 
     # --- weights in Keras order / layout -----------------------------------------------------
     def conv_modules(self):
@@ -291,7 +300,10 @@ class BtsDecoder(nn.Module):
         (losses.depth_silog); gradient flows from `loss` into the decoder."""
         from . import losses
         logit = self.forward(decoder_inputs, return_logit=True)
-        return losses.depth_silog(logit, y_true, self.max_depth, dataset)
+        ws = self._loss_ws
+        if ws is None or ws.device != logit.device:
+            ws = self._loss_ws = ops.tail_workspace(logit.device)          # one scratch for the life of the module, not one per step
+        return losses.depth_silog(logit, y_true, self.max_depth, dataset, ws)
 
 
 def decoder_model(decoder_inputs, max_depth, num_filters=256, is_training=False, decoder=None):

@@ -15,16 +15,25 @@ from . import ops
 
 
 class _FusedMetrics:
+    """Cache of the last (y_true, y_pred) pair's metric vector.  The pair is held by strong reference and compared by
+    IDENTITY plus torch's version counters: a freed batch whose addresses the caching allocator hands to the next batch
+    can never alias the cached entry (keys made of data_ptr() / id() can).  Kernels that write a tensor through a raw
+    pointer (out= buffers, CUDA-graph replays) do not bump the version counter -- call `invalidate()` after such a
+    write, or use `all_metrics()` which never caches."""
+
     def __init__(self, min_depth_eval, max_depth_eval):
         self.lo, self.hi = float(min_depth_eval), float(max_depth_eval)
-        self._key = None
-        self._value = None
+        self.invalidate()
+
+    def invalidate(self):
+        self._yt = self._yp = self._value = None
+        self._versions = None
 
     def __call__(self, y_true, y_pred):
-        key = (y_true.data_ptr(), y_pred.data_ptr(), y_true._version, y_pred._version, tuple(y_true.shape))
-        if key != self._key:
+        versions = (y_true._version, y_pred._version)
+        if not (self._yt is y_true and self._yp is y_pred and self._versions == versions):
             self._value = ops.eval_metrics(y_true, y_pred, self.lo, self.hi)
-            self._key = key
+            self._yt, self._yp, self._versions = y_true, y_pred, versions
         return self._value
 
 
@@ -38,6 +47,7 @@ def metrics_list_factory(args):
         return metric
 
     by_name = {name: make(i, name) for i, name in enumerate(ops.METRIC_NAMES)}
+    by_name["silog"].invalidate = fused.invalidate          # reachable from the list for raw-pointer writers
     return [by_name[n] for n in ("silog", "abs_rel", "log10", "rmse", "sq_rel", "rmse_log", "d1", "d2", "d3")]
 
 

@@ -98,16 +98,22 @@ class HostSet:
     def bytes_in(self):
         return sum(H[k].numel() * H[k].element_size() for H in self.layers for k in DeviceSet.INPUTS if H[k] is not None)
 
-    def bytes_out(self):
-        return sum(H[k].numel() * H[k].element_size() for H in self.layers for k in DeviceSet.OUTPUTS if H[k] is not None)
+    def bytes_out(self, return_ds=True):
+        return sum(H[k].numel() * H[k].element_size() for H in self.layers for k in DeviceSet.OUTPUTS
+                   if H[k] is not None and (return_ds or k != "out_ds"))
 
 
 class HostLpgPipeline:
     """LPG forward+backward of one decoder for HOST tensors, software-pipelined over `slots` device sets."""
 
-    def __init__(self, B, H, W, dtype, device, slots=2, scales=DECODER_SCALES, fused=True):
+    def __init__(self, B, H, W, dtype, device, slots=2, scales=DECODER_SCALES, fused=True, return_ds=True, run_kernels=True):
+        """return_ds=False: the strided copies out_ds (= out_full[:, ::d, ::d], bts_decoder.py:81,88) are not copied back to the
+        host -- a host consumer can slice them from out_full; saves 12 MB of the 169 MB device->host traffic per step at config 2.
+        run_kernels=False: the copy-only leg of the bench (same buffers, streams and events, no kernel launches) that measures
+        the platform's host<->device ceiling for this traffic pattern."""
         self.device = torch.device(device)
         self.fused = fused
+        self.return_ds, self.run_kernels = bool(return_ds), bool(run_kernels)
         self.slots = [DeviceSet(B, H, W, dtype, device, scales, fill=False) for _ in range(slots)]
         self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
@@ -130,14 +136,15 @@ class HostLpgPipeline:
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_compute):
             self.s_compute.wait_event(self.ev_in[k])
-            dev.forward(self.fused)
-            dev.backward(self.fused)
+            if self.run_kernels:
+                dev.forward(self.fused)
+                dev.backward(self.fused)
             self.ev_compute[k].record(self.s_compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_compute[k])
             for L, Hh in zip(dev.layers, host.layers):
                 for name in DeviceSet.OUTPUTS:
-                    if L[name] is not None:
+                    if L[name] is not None and (self.return_ds or name != "out_ds"):
                         Hh[name].copy_(L[name], non_blocking=True)
             self.ev_out[k].record(self.s_out)
         self.count += 1

@@ -94,17 +94,22 @@ class ReductionLPG(torch.nn.Module):
         limit = math.sqrt(6.0 / (in_channels + 3))        # glorot_uniform, fan_in = C, fan_out = 3
         self.kernel = torch.nn.Parameter((torch.rand(1, 1, in_channels, 3) * 2 - 1) * limit)
         self._grad_view = None
+        self._grad_written = None
 
-    def bind_gradient_view(self, view):
+    def bind_gradient_view(self, view, on_written=None):
         """Let backward write d loss / d kernel straight into `view` (a float32 slice of a flat gradient
-        bucket, see parallel.GradientBucket) instead of handing it to autograd for accumulation."""
+        bucket, see parallel.GradientBucket / trainer.FlatState) instead of handing it to autograd for accumulation.
+        The kernel OVERWRITES the slice (it does not accumulate: zero-initialised buckets and one backward per step).
+        `on_written()` is called right after the backward kernel has been enqueued -- the bucket's cue that this
+        parameter's gradient is complete (autograd's own hooks never fire for it, since it sees no gradient)."""
         if view is not None and (view.dtype != torch.float32 or view.numel() != self.kernel.numel() or not view.is_contiguous()):
             raise ValueError("gradient view must be a contiguous float32 tensor with %d elements" % self.kernel.numel())
         self._grad_view = view
+        self._grad_written = on_written if view is not None else None
 
     @property
     def name(self):
         return self.layer_name
 
     def forward(self, feat):
-        return ops.reduce_lpg(feat, self.kernel, self.upratio, self.ds_stride, self._grad_view)
+        return ops.reduce_lpg(feat, self.kernel, self.upratio, self.ds_stride, self._grad_view, self._grad_written)

@@ -23,7 +23,7 @@ def si_log_loss_wrapper(dataset):
     return si_log_loss
 
 
-def depth_silog(logit, y_true, max_depth, dataset):
-    """Returns (depth_est, loss); gradient flows from `loss` to `logit`."""
+def depth_silog(logit, y_true, max_depth, dataset, workspace=None):
+    """Returns (depth_est, loss); gradient flows from `loss` to `logit`.  workspace: see ops.depth_silog."""
     assert dataset in GT_TH
-    return ops.depth_silog(logit, y_true, max_depth, GT_TH[dataset])
+    return ops.depth_silog(logit, y_true, max_depth, GT_TH[dataset], workspace)

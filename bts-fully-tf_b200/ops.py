@@ -206,7 +206,7 @@ class ReduceLpgFunction(torch.autograd.Function):
     """Differentiable fused head: (feat, kernel) -> (reduction, depth, depth_ds)."""
 
     @staticmethod
-    def forward(ctx, feat, kernel, upratio, ds_stride, g_kernel_out=None):
+    def forward(ctx, feat, kernel, upratio, ds_stride, g_kernel_out=None, on_written=None):
         feat_c = feat.contiguous()
         coef, full, ds = reduce_lpg_forward(feat_c, kernel, upratio, ds_stride)
         ctx.save_for_backward(feat_c, kernel, coef)
@@ -214,6 +214,7 @@ class ReduceLpgFunction(torch.autograd.Function):
         # optional [C][3] float32 view into a flat gradient bucket: backward writes g_kernel there
         # directly (the bucket is what the all-reduce sends) instead of returning it to autograd
         ctx.g_kernel_out = g_kernel_out
+        ctx.on_written = on_written
         ctx.set_materialize_grads(False)
         if ds is None:
             ds = full.new_empty(0)
@@ -231,7 +232,7 @@ class ReduceLpgFunction(torch.autograd.Function):
             g_ds = None
         need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if (g_full is None and g_ds is None) or not (need_f or need_k):
-            return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None, None
+            return (torch.zeros_like(feat) if need_f else None), (torch.zeros_like(kernel) if need_k else None), None, None, None, None
         direct = ctx.g_kernel_out if need_k else None
         g_full, g_ds = _unit_stride_map(g_full), _unit_stride_map(g_ds)
         g_feat, g_kernel, _ = reduce_lpg_backward(feat, kernel, coef, g_full, g_ds, ctx.upratio, ctx.ds_stride,
@@ -239,15 +240,18 @@ class ReduceLpgFunction(torch.autograd.Function):
                                                   g_kernel_out=None if direct is None else direct.view(-1, 3))
         if direct is not None:
             g_kernel = None                      # already in the bucket; nothing for autograd to accumulate
+            if ctx.on_written is not None:
+                ctx.on_written()
         elif g_kernel is not None:
             g_kernel = g_kernel.reshape(kernel.shape).to(kernel.dtype)
-        return g_feat, g_kernel, None, None, None
+        return g_feat, g_kernel, None, None, None, None
 
 
-def reduce_lpg(feat, kernel, upratio, ds_stride=0, g_kernel_out=None):
+def reduce_lpg(feat, kernel, upratio, ds_stride=0, g_kernel_out=None, on_written=None):
     """Functional fused head with autograd.  Returns (reduction, depth[, depth_ds]).
-    g_kernel_out: optional float32 view (same numel as kernel) that receives d loss / d kernel in backward."""
-    coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride), g_kernel_out)
+    g_kernel_out: optional float32 view (same numel as kernel) that receives d loss / d kernel in backward (overwritten,
+    not accumulated); on_written: called once that backward kernel is enqueued."""
+    coef, full, ds = ReduceLpgFunction.apply(feat, kernel, int(upratio), int(ds_stride), g_kernel_out, on_written)
     return (coef, full, ds) if ds_stride else (coef, full)
 
 
@@ -298,8 +302,8 @@ class DepthSilogFunction(torch.autograd.Function):
     depth_est is returned for inspection / metrics; only `loss` carries gradient."""
 
     @staticmethod
-    def forward(ctx, logit, y_true, max_depth, gt_threshold):
-        depth_est, loss, ws = silog_forward(logit.contiguous(), y_true.contiguous(), max_depth, gt_threshold)
+    def forward(ctx, logit, y_true, max_depth, gt_threshold, workspace=None):
+        depth_est, loss, ws = silog_forward(logit.contiguous(), y_true.contiguous(), max_depth, gt_threshold, workspace=workspace)
         ctx.save_for_backward(depth_est, y_true.contiguous(), ws)
         ctx.max_depth, ctx.gt_threshold = max_depth, gt_threshold
         ctx.mark_non_differentiable(depth_est)
@@ -309,7 +313,7 @@ class DepthSilogFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, _g_depth, g_loss):
         depth_est, y_true, ws = ctx.saved_tensors
-        return silog_backward(depth_est, y_true, ctx.max_depth, ctx.gt_threshold, ws, g_loss, wrt_logit=True), None, None, None
+        return silog_backward(depth_est, y_true, ctx.max_depth, ctx.gt_threshold, ws, g_loss, wrt_logit=True), None, None, None, None
 
 
 class SilogLossFunction(torch.autograd.Function):
@@ -330,9 +334,10 @@ class SilogLossFunction(torch.autograd.Function):
         return None, silog_backward(yp, yt, 1.0, ctx.gt_threshold, ws, g_loss, wrt_logit=False), None
 
 
-def depth_silog(logit, y_true, max_depth, gt_threshold):
-    """Fused decoder tail with autograd: returns (depth_est, loss)."""
-    return DepthSilogFunction.apply(logit, y_true, float(max_depth), float(gt_threshold))
+def depth_silog(logit, y_true, max_depth, gt_threshold, workspace=None):
+    """Fused decoder tail with autograd: returns (depth_est, loss).  `workspace` (tail_workspace(device)): a caller-owned
+    scratch reused from step to step (one forward/backward pair in flight at a time) instead of a fresh zeroed one per call."""
+    return DepthSilogFunction.apply(logit, y_true, float(max_depth), float(gt_threshold), workspace)
 
 
 def si_log_loss(y_true, y_pred, gt_threshold):
@@ -355,6 +360,54 @@ def eval_metrics(y_true, y_pred, min_depth_eval, max_depth_eval, out=None, works
     check(lib.btslpg_eval_metrics(rt.ptr, rp.ptr, float(min_depth_eval), float(max_depth_eval), ro.ptr,
                                   ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), current_stream_ptr(y_true.device)))
     return out
+
+
+def eval_metrics_png16(y_pred, png_max_depth, y_true=None, min_depth_eval=1e-3, max_depth_eval=80.0, out=None, png=None, workspace=None):
+    """The metrics pass that also writes the uint16 depth image of bts_predict.py:140-141
+    (`(pred * 65536 / max_depth).astype(np.uint16)`) from the same read of y_pred.  y_true None (bts_predict.py has no ground
+    truth): the scaling pass alone.  Returns (png uint16 tensor shaped like y_pred, metrics-or-None)."""
+    lib = load()
+    y_pred = y_pred.contiguous()
+    if png is None:
+        png = torch.empty(y_pred.shape, dtype=torch.uint16, device=y_pred.device)
+    rt = rm = None
+    if y_true is not None:
+        if out is None:
+            out = torch.empty(10, dtype=torch.float32, device=y_pred.device)
+        if workspace is None:
+            workspace = tail_workspace(y_pred.device)
+        rt, rm = as_ref(y_true.contiguous()), as_ref(out)
+    rp, rg = as_ref(y_pred), as_ref(png)
+    check(lib.btslpg_eval_metrics_png16(ptr_or_null(rt), rp.ptr, float(min_depth_eval), float(max_depth_eval), ptr_or_null(rm),
+                                        float(png_max_depth), rg.ptr, ctypes.c_void_p(workspace.data_ptr() if workspace is not None else 0),
+                                        workspace.numel() if workspace is not None else 0, current_stream_ptr(y_pred.device)))
+    return png, (out if y_true is not None else None)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused optimizer step over flat buffers (custom_optimizers.py:47-59 + Keras Adam + bts_train.py:125-131)
+# ---------------------------------------------------------------------------------------------
+def adam_config(lr_start, lr_end=None, total_steps=0, power=0.9, beta1=0.9, beta2=0.999, epsilon=1e-3, l1=0.0, l2=0.0,
+                grad_scale=1.0, zero_grad=True):
+    """BtsAdamConfig with the reference's defaults: Keras Adam betas, --adam_eps 1e-3 (bts_train.py:86), polynomial decay to
+    0.1 * lr_start when no end rate is given (bts_train.py:126)."""
+    if lr_end is None:
+        lr_end = lr_start * 0.1 if total_steps > 0 else lr_start
+    return _cabi.BtsAdamConfig(float(lr_start), float(lr_end), int(total_steps), float(power), float(beta1), float(beta2), float(epsilon),
+                               float(l1), float(l2), float(grad_scale), 1 if zero_grad else 0)
+
+
+def adam_state(device):
+    """Device-resident optimizer state words: [0] int32 completed updates, [1] float32 last learning rate."""
+    return torch.zeros(4, dtype=torch.float32, device=device)
+
+
+def adam_step(param, grad, m, v, state, cfg, advance=True):
+    """One fused AdamW update of the flat float32 buffers (param, m, v updated in place; grad consumed, zeroed when
+    cfg.zero_grad).  `state` from adam_state(); the step counter is read and advanced on the device."""
+    lib = load()
+    rp, rg, rm, rv, rs = as_ref(param), as_ref(grad), as_ref(m), as_ref(v), as_ref(state)
+    check(lib.btslpg_adam_step(rp.ptr, rg.ptr, rm.ptr, rv.ptr, rs.ptr, ctypes.byref(cfg), 1 if advance else 0, current_stream_ptr(param.device)))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,8 +65,11 @@ class GradientBucket:
 
     `.grad` of every parameter is made a view of the buffer, so autograd accumulates in place;
     `view(p)` returns the slice for kernels that write a gradient directly (the fused head's
-    g_kernel).  `all_reduce()` sums the buffer over ranks on a side stream and scales by 1/world
-    (Keras averages the per-replica losses), `wait()` joins that stream.
+    g_kernel -- it OVERWRITES its slice, so the bucket supports one backward per `zero()`, not gradient
+    accumulation over several).  `all_reduce()` sums the buffer over ranks on a side stream and scales by 1/world
+    (Keras averages the per-replica losses), `wait()` joins that stream.  Use `zero()` instead of
+    `optimizer.zero_grad()` (whose default set_to_none=True would detach the views).  The overlapped, CUDA-graph
+    training step is trainer.DataParallelStep; this class is the simple blocking form.
     """
 
     def __init__(self, params, device=None):
@@ -101,14 +104,29 @@ class GradientBucket:
                 n += 1
         return n
 
+    def attach(self):
+        """(Re-)point every p.grad at its slice of the buffer.  torch's default `zero_grad(set_to_none=True)` drops the
+        views, after which autograd would allocate gradients OUTSIDE the bucket and the all-reduce would exchange stale
+        zeros: use `bucket.zero()` (which re-attaches) instead of `zero_grad()`, or call this after it."""
+        for p in self.params:
+            off, _ = self.offsets[id(p)]
+            if p.grad is None or p.grad.data_ptr() != self.buffer.data_ptr() + 4 * off:
+                p.grad = self.view(p)
+
     def zero(self):
         self.buffer.zero_()
+        self.attach()
 
     def nbytes(self):
         return self.numel * 4
 
     def all_reduce(self, average=True):
         """Launch the exchange step; overlappable with whatever the caller enqueues next."""
+        for p in self.params:                                   # a detached view means the gradients are not in the buffer
+            off, _ = self.offsets[id(p)]
+            if p.grad is None or p.grad.data_ptr() != self.buffer.data_ptr() + 4 * off:
+                raise RuntimeError("GradientBucket: a parameter's .grad no longer aliases the bucket (zero_grad(set_to_none=True)?); "
+                                   "use bucket.zero() / bucket.attach()")
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         world = dist.get_world_size()

@@ -8,10 +8,16 @@ name, constructor, `build`, `call` and `get_config` (custom_layers.py:25-61), so
 unchanged.  Tensors cross into libbtslpg.so as DLPack capsules (zero copy): TF allocates inputs and
 outputs, the library only launches kernels on TF's buffers.
 
-Stream note: TF runs its GPU ops on its own compute stream, which is not exposed to Python.  The
-binding therefore launches on the legacy default stream (stream = NULL), which implicitly
-synchronises with TF's blocking streams; `tf.experimental.dlpack.to_dlpack` itself waits for the
-producer op, as DLPack requires.
+Status: EXPERIMENTAL -- written against the TF 2.x Python API, never executed (no TensorFlow here).
+
+Stream note: TF runs its GPU ops on its own compute stream, created with CU_STREAM_NON_BLOCKING and not exposed to
+Python, so a launch on the legacy default stream is NOT ordered against TF's work.  Every entry point below therefore
+brackets its launch with a device-wide barrier (`btslpg_device_synchronize`): one before the launch, after the output
+buffers have been allocated (TF's producers of the inputs and its `tf.zeros` fills are complete), and one after it (the
+results are written before TF's consumers are enqueued).  That is correct but serialises host and device at every call,
+and `tf.py_function` runs its body under the GIL; the production binding is a `tf.load_op_library` custom op whose
+`Compute()` passes `ctx->eigen_gpu_device().stream()` as the ABI's stream argument -- it needs
+TensorFlow's headers to build, which this image does not have.
 """
 import ctypes
 
@@ -34,6 +40,21 @@ def _capsule(t):
     return tf.experimental.dlpack.to_dlpack(t)
 
 
+def _sync(ref):  # pragma: no cover
+    """Device-wide barrier on the device of a described tensor (see the stream note in the module docstring)."""
+    _cabi.check(_cabi.load().btslpg_device_synchronize(int(ref.struct.device.device_id)))
+
+
+def _gpu_py_function(fn, inputs, tout):  # pragma: no cover
+    """tf.py_function pinned to the device of its first input, so that the body receives device tensors (the library
+    rejects host tensors: there is no CPU path)."""
+    dev = getattr(inputs[0], "device", "") or None
+    if dev:
+        with tf.device(dev):
+            return tf.py_function(fn, inputs, tout)
+    return tf.py_function(fn, inputs, tout)
+
+
 def _forward_eager(coef, upratio, ds_stride):  # pragma: no cover
     lib = _cabi.load()
     B, h, w, _ = coef.shape
@@ -43,7 +64,9 @@ def _forward_eager(coef, upratio, ds_stride):  # pragma: no cover
         ds = tf.zeros((B, H // ds_stride, W // ds_stride, 1), coef.dtype) if ds_stride else None
     rc, rf = _cabi.from_dlpack_capsule(_capsule(coef)), _cabi.from_dlpack_capsule(_capsule(full))
     rd = _cabi.from_dlpack_capsule(_capsule(ds)) if ds_stride else None
+    _sync(rc)
     _cabi.check(lib.btslpg_forward(rc.ptr, int(upratio), rf.ptr, _cabi.ptr_or_null(rd), int(ds_stride), ctypes.c_void_p(0)))
+    _sync(rc)
     return full, ds
 
 
@@ -52,8 +75,10 @@ def _backward_eager(coef, g_full, g_ds, upratio, ds_stride):  # pragma: no cover
     with tf.device(coef.device):
         g_coef = tf.zeros(coef.shape, coef.dtype)
     refs = [_cabi.from_dlpack_capsule(_capsule(t)) if t is not None else None for t in (coef, g_full, g_ds, g_coef)]
+    _sync(refs[0])
     _cabi.check(lib.btslpg_backward(refs[0].ptr, _cabi.ptr_or_null(refs[1]), _cabi.ptr_or_null(refs[2]), int(upratio),
                                     int(ds_stride if g_ds is not None else 0), refs[3].ptr, ctypes.c_void_p(0)))
+    _sync(refs[0])
     return g_coef
 
 
@@ -66,11 +91,11 @@ def local_planar_guidance(inputs, upratio):  # pragma: no cover
         def fwd(x_):
             return _forward_eager(x_, upratio, 0)[0]
 
-        y = tf.py_function(fwd, [x], x.dtype)
+        y = _gpu_py_function(fwd, [x], x.dtype)
         y.set_shape([x.shape[0], x.shape[1] * upratio, x.shape[2] * upratio, 1])
 
         def grad(dy):
-            g = tf.py_function(lambda x_, dy_: _backward_eager(x_, dy_, None, upratio, 0), [x, dy], x.dtype)
+            g = _gpu_py_function(lambda x_, dy_: _backward_eager(x_, dy_, None, upratio, 0), [x, dy], x.dtype)
             g.set_shape(x.shape)
             return g
 
@@ -133,11 +158,13 @@ def si_log_loss_wrapper(dataset):  # pragma: no cover
                 loss = tf.zeros([1], tf.float32)
             state["ws"] = ws
             rt, rp, rl, rw = _ref(yt), _ref(yp), _ref(loss), _ref(ws)
+            _sync(rp)
             _cabi.check(lib.btslpg_silog_forward(None, rt.ptr, 1.0, GT_TH[dataset], rp.ptr, rl.ptr,
                                                  ctypes.c_void_p(rw.struct.data), int(ws.shape[0]), ctypes.c_void_p(0)))
+            _sync(rp)
             return loss[0]
 
-        loss = tf.py_function(fwd, [y_true, y_pred], tf.float32)
+        loss = _gpu_py_function(fwd, [y_true, y_pred], tf.float32)
         loss.set_shape([])
 
         def grad(g_loss):
@@ -147,10 +174,12 @@ def si_log_loss_wrapper(dataset):  # pragma: no cover
                     gl1 = tf.reshape(tf.cast(gl, tf.float32), [1])
                 ws = state["ws"]
                 rt, rp, rg, rgl, rw = _ref(yt), _ref(yp), _ref(g), _ref(gl1), _ref(ws)
+                _sync(rp)
                 _cabi.check(lib.btslpg_silog_backward(rp.ptr, rt.ptr, 1.0, GT_TH[dataset], rgl.ptr, ctypes.c_void_p(rw.struct.data),
                                                       int(ws.shape[0]), 0, rg.ptr, ctypes.c_void_p(0)))
+                _sync(rp)
                 return g
-            g = tf.py_function(bwd, [y_true, y_pred, g_loss], y_pred.dtype)
+            g = _gpu_py_function(bwd, [y_true, y_pred, g_loss], y_pred.dtype)
             g.set_shape(y_pred.shape)
             return None, g
 
@@ -163,12 +192,12 @@ def metrics_list_factory(args):  # pragma: no cover
     """Drop-in for reference custom_eval_metrics.py:21-88: nine named callables, ONE fused pass per (y_true, y_pred)."""
     _require_tf()
     names = ("silog", "abs_rel", "log10", "rmse", "sq_rel", "rmse_log", "d1", "d2", "d3")
-    cache = {}
+    cache = {}        # holds the LAST (y_true, y_pred) pair itself: identity of live objects, never a recycled id()
 
     def all_metrics(y_true, y_pred):
-        key = (id(y_true), id(y_pred))
-        if key not in cache:
+        if not (cache.get("yt") is y_true and cache.get("yp") is y_pred):
             cache.clear()
+            cache["yt"], cache["yp"] = y_true, y_pred
 
             def run(yt, yp):
                 lib = _cabi.load()
@@ -176,13 +205,15 @@ def metrics_list_factory(args):  # pragma: no cover
                 with tf.device(yp.device):
                     out = tf.zeros([10], tf.float32)
                 rt, rp, ro, rw = _ref(yt), _ref(yp), _ref(out), _ref(ws)
+                _sync(rt)
                 _cabi.check(lib.btslpg_eval_metrics(rt.ptr, rp.ptr, float(args.min_depth_eval), float(args.max_depth_eval), ro.ptr,
                                                     ctypes.c_void_p(rw.struct.data), int(ws.shape[0]), ctypes.c_void_p(0)))
+                _sync(rt)
                 return out
-            v = tf.py_function(run, [y_true, y_pred], tf.float32)
+            v = _gpu_py_function(run, [y_true, y_pred], tf.float32)
             v.set_shape([10])
-            cache[key] = v
-        return cache[key]
+            cache["v"] = v
+        return cache["v"]
 
     def make(i, name):
         def metric(y_true, y_pred):
@@ -207,10 +238,12 @@ def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
             ra, ro = _ref(a_), _ref(out)
             rp = [_ref(t) for t in (p0_, p1_, p2_)]
             arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
+            _sync(ra)
             _cabi.check(lib.btslpg_concat_forward(ra.ptr, 0, 1, None, None, None, arr, 3, 0, ro.ptr, ctypes.c_void_p(0)))
+            _sync(ra)
             return out
 
-        y = tf.py_function(fwd, [a, p0, p1, p2], a.dtype)
+        y = _gpu_py_function(fwd, [a, p0, p1, p2], a.dtype)
         y.set_shape(a.shape[:3] + [a.shape[3] + 3])
 
         def grad(g_out):
@@ -221,9 +254,11 @@ def concat1(upconv1_linear, d2, d4, d8):  # pragma: no cover
                 rg, ry, rga = _ref(g_), _ref(y_), _ref(g_a)
                 rp = [_ref(t) for t in g_p]
                 arr = (_cabi._TP * 3)(*[r.ptr for r in rp])
+                _sync(rg)
                 _cabi.check(lib.btslpg_concat_backward(rg.ptr, ry.ptr, 1, rga.ptr, 0, None, arr, 3, 0, ctypes.c_void_p(0)))
+                _sync(rg)
                 return [g_a] + g_p
-            outs = tf.py_function(bwd, [g_out, y], [a.dtype] * 4)
+            outs = _gpu_py_function(bwd, [g_out, y], [a.dtype] * 4)
             outs[0].set_shape(a.shape)
             for o in outs[1:]:
                 o.set_shape(p0.shape)
@@ -247,18 +282,20 @@ def depth_tail(iconv1_linear, kernel, max_depth=None):  # pragma: no cover
         with tf.device(x_.device):
             y_ = tf.zeros(x_.shape[:3] + [1], x_.dtype)
         rx, rk, ry = _ref(x_), _ref(tf.reshape(k_, [-1])), _ref(y_)
+        _sync(rx)
         _cabi.check(lib.btslpg_depthconv_forward(rx.ptr, rk.ptr, 1, 1 if max_depth is not None else 0,
                                                  float(max_depth if max_depth is not None else 1.0), ry.ptr, ctypes.c_void_p(0)))
+        _sync(rx)
         return y_
 
     if max_depth is not None:
-        y = tf.py_function(fwd, [iconv1_linear, kernel], iconv1_linear.dtype)
+        y = _gpu_py_function(fwd, [iconv1_linear, kernel], iconv1_linear.dtype)
         y.set_shape(iconv1_linear.shape[:3] + [1])
         return y
 
     @tf.custom_gradient
     def op(x, k):
-        y = tf.py_function(fwd, [x, k], x.dtype)
+        y = _gpu_py_function(fwd, [x, k], x.dtype)
         y.set_shape(x.shape[:3] + [1])
 
         def grad(g_out):
@@ -269,10 +306,12 @@ def depth_tail(iconv1_linear, kernel, max_depth=None):  # pragma: no cover
                     g_k = tf.zeros([9 * C], tf.float32)
                     ws = tf.zeros([int(lib.btslpg_depthconv_backward_workspace_bytes(C))], tf.uint8)
                 rx, rk, rg, rgx, rgk, rw = _ref(x_), _ref(tf.reshape(k_, [-1])), _ref(g_), _ref(g_x), _ref(g_k), _ref(ws)
+                _sync(rx)
                 _cabi.check(lib.btslpg_depthconv_backward(rx.ptr, rk.ptr, rg.ptr, 1, rgx.ptr, rgk.ptr, ctypes.c_void_p(rw.struct.data),
                                                           int(ws.shape[0]), ctypes.c_void_p(0)))
+                _sync(rx)
                 return g_x, tf.reshape(g_k, k_.shape)
-            g_x, g_k = tf.py_function(bwd, [x, k, g_out], [x.dtype, tf.float32])
+            g_x, g_k = _gpu_py_function(bwd, [x, k, g_out], [x.dtype, tf.float32])
             g_x.set_shape(x.shape)
             g_k.set_shape(k.shape)
             return g_x, g_k
@@ -302,9 +341,11 @@ def reduction_lpg(feat, kernel, upratio, ds_stride=0):  # pragma: no cover
                 ds = tf.zeros([B, h * r // d, w * r // d, 1], x_.dtype) if d else tf.zeros([0], x_.dtype)
             rx, rk, rc, ro = _ref(x_), _ref(tf.reshape(tf.cast(k_, tf.float32), [-1, 3])), _ref(coef), _ref(full)
             rd = _ref(ds) if d else None
+            _sync(rx)
             _cabi.check(lib.btslpg_reduce_forward(rx.ptr, rk.ptr, r, rc.ptr, ro.ptr, rd.ptr if d else None, d, ctypes.c_void_p(0)))
+            _sync(rx)
             return coef, full, ds
-        coef, full, ds = tf.py_function(fwd, [x, k], [x.dtype] * 3)
+        coef, full, ds = _gpu_py_function(fwd, [x, k], [x.dtype] * 3)
         coef.set_shape(x.shape[:3] + [3])
         full.set_shape([x.shape[0], x.shape[1] * r, x.shape[2] * r, 1])
         if d:
@@ -320,11 +361,13 @@ def reduction_lpg(feat, kernel, upratio, ds_stride=0):  # pragma: no cover
                     ws = tf.zeros([int(lib.btslpg_reduce_backward_workspace_bytes(npix, C))], tf.uint8)
                 refs = [_ref(x_), _ref(tf.reshape(tf.cast(k_, tf.float32), [-1, 3])), _ref(c_), _ref(gf_), _ref(gd_) if d else None,
                         _ref(g_x), _ref(g_k), _ref(ws)]
+                _sync(refs[0])
                 _cabi.check(lib.btslpg_reduce_backward(refs[0].ptr, refs[1].ptr, refs[2].ptr, refs[3].ptr, refs[4].ptr if d else None, r, d,
                                                        refs[5].ptr, refs[6].ptr, None, ctypes.c_void_p(refs[7].struct.data), int(ws.shape[0]),
                                                        ctypes.c_void_p(0)))
+                _sync(refs[0])
                 return g_x, tf.reshape(g_k, k_.shape)
-            g_x, g_k = tf.py_function(bwd, [x, k, coef, g_full, g_ds], [x.dtype, tf.float32])
+            g_x, g_k = _gpu_py_function(bwd, [x, k, coef, g_full, g_ds], [x.dtype, tf.float32])
             g_x.set_shape(x.shape)
             g_k.set_shape(k.shape)
             return g_x, g_k

@@ -204,6 +204,17 @@ BTSLPG_API int btslpg_eval_metrics(const BtsTensor *y_true, const BtsTensor *y_p
                                    float max_depth_eval, BtsTensor *metrics, void *workspace,
                                    size_t workspace_bytes, void *stream);
 
+/* btslpg_eval_metrics_png16 -- the same pass that additionally writes the 16-bit depth image bts_predict.py:140-141 saves
+ * (`pred_depth * 65536 / args.max_depth` in float32, then `.astype(np.uint16)`), from the one read of y_pred (SURVEY 8(f)
+ * N4, second half):
+ *   png  uint16 (kDLUInt, 16 bits), as many elements as y_pred, contiguous, 16-byte aligned; NULL = metrics only
+ *   png[i] = (uint16)(int32)trunc(y_pred[i] * 65536 / png_max_depth): numpy's C cast, so a prediction equal to max_depth
+ *            wraps to 0 and NaN gives 0 exactly as the reference's line does (no clamping)
+ *   y_true NULL (bts_predict.py has no ground truth): the scaling pass alone; metrics / workspace may then be NULL. */
+BTSLPG_API int btslpg_eval_metrics_png16(const BtsTensor *y_true, const BtsTensor *y_pred, float min_depth_eval,
+                                         float max_depth_eval, BtsTensor *metrics, float png_max_depth, BtsTensor *png,
+                                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused activation + channel concat of NHWC tensors -- replaces bts_decoder.py:98-99
  *     upconv1 = Conv2D(..., activation='elu')(upsample1)        (the activation: pass the conv's linear output as `a`)
@@ -299,6 +310,34 @@ BTSLPG_API int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *ker
                                         BtsTensor *y, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The optimizer step of the data-parallel training loop as ONE pass over flat float32 buffers -- replaces
+ *   custom_optimizers.py:47-59  AdamW._resource_apply_dense: `var -= lr * (l1*sign(var) + l2*var)` BEFORE the Adam update
+ *   tf.keras.optimizers.Adam    alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t) ; m += (g - m)(1 - beta1) ;
+ *                               v += (g*g - v)(1 - beta2) ; var -= alpha * m / (sqrt(v) + epsilon)      (t = iterations + 1)
+ *   bts_train.py:125-131        lr(step) = (lr_start - lr_end) * (1 - min(step, total_steps)/total_steps)^power + lr_end,
+ *                               evaluated at the 0-based global step (custom_callbacks.py:46-50); lr_start already carries
+ *                               the reference's "x num_replicas" (bts_train.py:125)
+ *   MirroredStrategy's gradient average: grad_scale = 1/N multiplies the all-reduced (summed) gradient on the way in.
+ *   param, grad, m, v   float32, same number of elements, contiguous, 16-byte aligned (slices of flat buckets)
+ *   state   >= 4 32-bit words of device memory: [0] int32 number of completed updates (the kernel reads the step from
+ *           here, so a CUDA graph replay advances without the host), [1] float32 lr of the last update (informational)
+ *   advance != 0: this call is the last chunk of the step -- state[0] += 1 afterwards (a second 1-thread launch)
+ *   cfg->zero_grad != 0: grad is overwritten with zeros as it is consumed (no separate zeroing pass before the next step)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float lr_start, lr_end;   /* lr_end == lr_start or total_steps <= 0: constant learning rate */
+    int64_t total_steps;
+    float power;              /* 0.9 in the reference */
+    float beta1, beta2;       /* Keras defaults 0.9, 0.999 */
+    float epsilon;            /* --adam_eps, 1e-3 (bts_train.py:86) */
+    float l1, l2;             /* decoupled decay of this group (decoder variables: 0, 0 -- bts.py:107 decays the encoder only) */
+    float grad_scale;
+    int32_t zero_grad;
+} BtsAdamConfig;
+BTSLPG_API int btslpg_adam_step(BtsTensor *param, BtsTensor *grad, BtsTensor *m, BtsTensor *v, BtsTensor *state,
+                                const BtsAdamConfig *cfg, int advance, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py ("gpu_launches") and the tests: number of kernel launches issued
  * through this library (process-wide) since the last reset, and the name of the
  * kernel variant the last call dispatched to (e.g. "lpg_fwd_vec<f32,r8,px1,ds4>").
@@ -306,6 +345,11 @@ BTSLPG_API int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *ker
 BTSLPG_API uint64_t btslpg_launch_count(void);
 BTSLPG_API void btslpg_reset_launch_count(void);
 BTSLPG_API const char *btslpg_last_kernel(void);
+
+/* Device-wide barrier (cudaDeviceSynchronize on `device_id`).  NOT used by any torch-hosted path: it exists for hosts that
+ * cannot hand the library their own stream (the experimental tf.py_function binding, tf_adapter.py), which must order the
+ * legacy-stream launches against the framework's non-blocking streams. */
+BTSLPG_API int btslpg_device_synchronize(int device_id);
 
 /* Tuning knobs for experiments (threads per block of the vectorised kernels; 0 = default).
  * btslpg_set_tuning keys: 0 forward block threads, 1 backward block threads, 2 float32 r=8 patch rows

@@ -364,3 +364,30 @@ def test_non_default_stream_and_graph_capture():
         graph.replay()
     s.synchronize()
     assert torch.equal(full, ref_full) and torch.equal(ds, ref_ds) and torch.equal(gc, ref_g)
+
+
+# ------------------------------------------------------------------------------------------------
+# block-size knob: a patch split over LPP warps must keep its warp group inside one CTA
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("threads", [32, 64, 96, 192, 256, 1000])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_block_threads_knob_keeps_parity(threads, dtype):
+    """btslpg_set_block_threads(t): the r = 8 kernels split a patch over 4 consecutive warps that exchange partial sums
+    through shared memory indexed by the CTA-local warp id, so the CTA size is rounded to a multiple of 128 there
+    (lpg_api.cu split_threads); every setting must give the same result as the default."""
+    try:
+        for r, d in RS:
+            coef, g_full, g_ds = make_inputs(2, 9, 12, r, d, seed=r, dtype=dtype)
+            c, gf, gd = coef.to(DEV), g_full.to(DEV), (g_ds.to(DEV) if d else None)
+            ops.set_block_threads(0, 0)
+            full0, _ = ops.lpg_forward(c, r, d)
+            gc0 = ops.lpg_backward(c, gf, gd, r, d)
+            ops.set_block_threads(threads, threads)
+            full1, ds1 = ops.lpg_forward(c, r, d)
+            gc1 = ops.lpg_backward(c, gf, gd, r, d)
+            torch.cuda.synchronize()
+            assert torch.equal(full0, full1) and torch.equal(gc0, gc1), (r, threads, ops.last_kernel())
+            if dtype == torch.float32:
+                parity.check_backward(npf(gc1), coef.numpy(), g_full.numpy(), r, g_ds.numpy() if d else None, d, what="threads=%d" % threads)
+    finally:
+        ops.set_block_threads(0, 0)

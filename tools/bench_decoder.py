@@ -60,38 +60,111 @@ class LiteralHeads:
             head.forward = fwd
 
 
-def run(cfg_id, a, rank, local_rank, world):
+def _max_over_ranks(ms, device, world):
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _timed(step, steps, device, world):
+    """barrier + sync, `steps` steps between two CUDA events on the current stream, barrier + sync; max over ranks (ms)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return _max_over_ranks(e0.elapsed_time(e1), device, world), out
+
+
+def run_config(cfg_id, rank, local_rank, world, steps=5, warmup=3, per_gpu_batch=None, lpg="fused", no_graph=False, measure_comm=True):
+    """One BASELINE config (3: inference, 4 / 5: data-parallel training step) -> result dict (identical on every rank)."""
+    from bts_fully_tf_b200 import ops, trainer
     cfg = CONFIGS[cfg_id]
     device = torch.device("cuda", local_rank)
     chans, F = TAPS[cfg["encoder"]]
-    gb = cfg["global_batch"] if a.per_gpu_batch is None else a.per_gpu_batch * world
+    gb = cfg["global_batch"] if per_gpu_batch is None else per_gpu_batch * world
     lo, hi = parallel.shard_range(gb, world, rank)
     b = hi - lo
     H, W = cfg["H"], cfg["W"]
-    torch.manual_seed(rank)
-    feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=device)) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    torch.manual_seed(0)                                   # identical initial weights on every rank (a replicated model)
     dec = BtsDecoder(chans, cfg["max_depth"], num_filters=F).to(device)
-    if a.lpg == "literal":
+    torch.manual_seed(1000 + rank)                         # a different shard of synthetic data per rank
+    feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=device)) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    if lpg == "literal":
         LiteralHeads.install(dec)
     dec.train(cfg["train"])
     gt = torch.rand(b, H, W, 1, device=device) * cfg["max_depth"]
-    params = list(dec.parameters())
+    res = {"config": cfg_id, "workload": cfg["name"], "metric": "decoder_images_per_s", "unit": "images/s", "n_gpus": world, "per_gpu_batch": b,
+           "global_batch": gb, "steps": steps, "warmup": warmup, "scaling": "strong" if per_gpu_batch is None else "weak", "lpg_path": lpg,
+           "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32", "cudnn_autotune": bool(torch.backends.cudnn.benchmark),
+           "data": "synthetic encoder taps, random-init decoder"}
+
+    if cfg["train"] and lpg == "fused":
+        # the data-parallel training step: forward, fused loss, backward, chunked all-reduce overlapped with backward on a side
+        # stream, fused AdamW -- ONE CUDA graph per rank (trainer.DataParallelStep; bts_train.py:194-209, :125-131)
+        eng = trainer.DataParallelStep(dec, feats, gt, dataset=cfg["dataset"], base_lr=1e-4, total_steps=100000, adam_eps=1e-3, use_graph=not no_graph)
+        ops.reset_launch_count()
+        eng._step_body()                                                  # first eager step (autotuning) also counts this repo's launches
+        own_launches = ops.launch_count()
+        graph_err = None
+        try:
+            eng.warmup_and_capture(max(1, warmup - 1))
+        except Exception as exc:  # noqa: BLE001
+            graph_err = "%s: %s" % (type(exc).__name__, str(exc)[:160])
+            eng.graph = None
+        if world > 1:                                                     # all ranks replay graphs, or none does
+            ok = torch.tensor([1 if eng.graph is not None else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and eng.graph is not None:
+                eng.graph, graph_err = None, "capture failed on another rank"
+        ms, loss = _timed(eng.step, steps, device, world)
+        res.update({"value": round(gb * steps / (ms * 1e-3), 2), "ms_per_step": round(ms / steps, 3), "cuda_graph": eng.graph is not None,
+                    "graph_error": graph_err, "launches_per_step": 1 if eng.graph is not None else None, "own_kernel_launches_per_step": own_launches,
+                    "grad_bucket_bytes": eng.flat.nbytes(), "grad_chunks": [int(hi_ - lo_) * 4 for lo_, hi_, _, _ in eng.flat.chunks],
+                    "allreduce_order": list(eng.comm.launch_order), "nccl_registered_bucket": bool(eng.registered),
+                    "optimizer": "fused AdamW kernel (1/N, decay, Adam, grad zeroing in one pass; device-resident step / lr)",
+                    "result_mean": float(loss), "completed_updates": eng.completed_updates()})
+        if world > 1 and measure_comm:
+            # (a) the whole bucket's all-reduce alone, (b) the same step with the exchange removed: step - (b) = exposed communication
+            g = eng.flat.grad
+            for _ in range(3):
+                dist.all_reduce(g)
+            ms_ar, _ = _timed(lambda: dist.all_reduce(g), 10, device, world)
+            res["allreduce_ms"] = round(ms_ar / 10, 4)
+            try:
+                eng.comm.enabled = False
+                if eng.graph is not None:
+                    eng.capture()
+                eng.step()
+                ms_nc, _ = _timed(eng.step, steps, device, world)
+                res["ms_per_step_without_allreduce"] = round(ms_nc / steps, 3)
+                res["exposed_comm_ms"] = round(max(0.0, (ms - ms_nc) / steps), 4)
+            except Exception as exc:  # noqa: BLE001
+                res["exposed_comm_error"] = "%s: %s" % (type(exc).__name__, str(exc)[:160])
+        eng.close()
+        del eng
+        return res
+
     bucket = opt = None
-    if cfg["train"]:
+    if cfg["train"]:                                                      # literal-LPG comparison arm: plain eager step
+        params = list(dec.parameters())
         bucket = parallel.GradientBucket(params)
-        if a.lpg == "fused":
-            bucket.bind_heads(dec)
-        opt = torch.optim.Adam(params, lr=parallel.scaled_learning_rate(1e-4, world), eps=1e-3)   # bts_train.py:86,125
+        opt = torch.optim.Adam(params, lr=parallel.scaled_learning_rate(1e-4, world), eps=1e-3)
 
     def step():
         if cfg["train"]:
             bucket.zero()
-            if a.lpg == "fused":
-                _, loss = dec.forward_loss(feats, gt, cfg["dataset"])      # fused sigmoid*max_depth + si_log_loss kernels
-            else:
-                loss = si_log_loss(gt, dec(feats), cfg["dataset"])
+            loss = si_log_loss(gt, dec(feats), cfg["dataset"])
             loss.backward()
-            bucket.all_reduce(average=True)            # the one exchange step: decoder gradients only
+            bucket.all_reduce(average=True)
             bucket.wait()
             opt.step()
             return loss
@@ -99,74 +172,41 @@ def run(cfg_id, a, rank, local_rank, world):
             return dec(feats)
 
     graph = None
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         out = step()
-    if not cfg["train"] and not a.no_graph:
-        # inference: the whole decoder step as ONE CUDA graph (≈130 launches, launch-bound at small per-GPU batches);
+    ops.reset_launch_count()
+    out = step()
+    own_launches = ops.launch_count()
+    if not cfg["train"] and not no_graph:
+        # inference: the whole decoder step as ONE CUDA graph (launch-bound at small per-GPU batches);
         # every op of this repo is capture-safe (no synchronisation, no host-side data dependence)
+        eager = step
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                step()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
-                    out = step()
+                    out = eager()
             torch.cuda.current_stream().wait_stream(side)
-            inner = step
 
             def step():                     # noqa: F811
                 graph.replay()
                 return out
             step()
         except Exception as exc:  # noqa: BLE001
-            graph = None
-            step = inner if "inner" in dir() else step
+            graph, step = None, eager
             print("CUDA graph capture failed, running eagerly: %s" % exc, file=sys.stderr)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        out = step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    result = float(out.detach().float().mean())   # device->host read of the step's result
+    ms, out = _timed(step, steps, device, world)
+    res.update({"value": round(gb * steps / (ms * 1e-3), 2), "ms_per_step": round(ms / steps, 3), "cuda_graph": graph is not None,
+                "own_kernel_launches_per_step": own_launches, "result_mean": float(out.detach().float().mean())})
+    return res
 
-    # share of the step spent in the LPG heads (events around the three fused ops, forward only)
-    lpg_ms = None
-    if a.lpg == "fused":
-        with torch.no_grad():
-            red_in = [torch.relu(torch.randn(b, H // r, W // r, c, device=device)) for r, c in ((8, F // 4), (4, F // 4), (2, F // 8))]
-            heads = (dec.reduction_8x8, dec.reduction_4x4, dec.reduction_2x2)
-            for h_, x in zip(heads, red_in):
-                h_(x)
-            torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(10):
-                for h_, x in zip(heads, red_in):
-                    h_(x)
-            s1.record()
-            torch.cuda.synchronize()
-            lpg_ms = s0.elapsed_time(s1) / 10
+
+def run(cfg_id, a, rank, local_rank, world):
+    res = run_config(cfg_id, rank, local_rank, world, a.steps, a.warmup, a.per_gpu_batch, a.lpg, a.no_graph)
     if rank == 0:
-        print(json.dumps({
-            "config": cfg_id, "workload": cfg["name"], "metric": "decoder_images_per_s", "value": round(gb * a.steps / (ms * 1e-3), 2),
-            "unit": "images/s", "n_gpus": world, "per_gpu_batch": b, "global_batch": gb, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": round(ms / a.steps, 3), "scaling": "strong" if a.per_gpu_batch is None else "weak",
-            "lpg_path": a.lpg, "fused_heads_forward_ms": None if lpg_ms is None else round(lpg_ms, 3),
-            "conv_math": "TF32 (cuDNN default)" if torch.backends.cudnn.allow_tf32 else "fp32", "cudnn_autotune": bool(torch.backends.cudnn.benchmark), "cuda_graph": graph is not None,
-            "grad_bucket_bytes": None if bucket is None else bucket.nbytes(), "result_mean": result,
-            "data": "synthetic encoder taps, random-init decoder"}))
+        print(json.dumps(res), flush=True)
 
 
 def main():

@@ -93,7 +93,8 @@ def time_gpu(fn, nsets, steps, warmup, graph=True):
     return e0.elapsed_time(e1) / (reps * per_graph) * 1e3
 
 
-def main():
+def collect(argv=None):
+    """Run the tail micro-benchmarks; returns the result dict (bench.py's extras.tail imports this)."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--height", type=int, default=480)
@@ -108,8 +109,8 @@ def main():
     ap.add_argument("--skip-concat", action="store_true")
     ap.add_argument("--skip-depthconv", action="store_true")
     ap.add_argument("--only-depthconv", action="store_true")
-    a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    a = ap.parse_args(argv)
+    dev = torch.device("cuda", torch.cuda.current_device())
     dtype = torch.float32 if a.dtype == "f32" else torch.bfloat16
     es = 4 if a.dtype == "f32" else 2
     md, th, lo, hi = 10.0, 0.1, 1e-3, 10.0
@@ -211,7 +212,13 @@ def main():
                 ref = lib_path(0).permute(0, 2, 3, 1)
                 ops.depthconv_forward(dsets[0]["x"], w9c, act_in=True, sigmoid_scale=md, out=dsets[0]["y"])
                 res[key]["max_abs_diff_vs_library_tf32"] = float((dsets[0]["y"] - ref).abs().max())
-            del dsets
+            # backward of the same layer: d loss / d x (with ELU') and d loss / d kernel from one pass (bts_decoder.py:102)
+            gouts = [torch.randn(shape, generator=g, device=dev).to(dtype) for _ in dsets]
+            us_b = time_gpu(lambda i: ops.depthconv_backward(dsets[i]["x"], w9c, gouts[i], act_in=True), len(dsets), max(8, a.steps // 8), 2, graph=False)
+            nb = (2 * cdc + 1) * n * es
+            res["depthconv_bwd_C%d" % cdc] = {"us": round(us_b, 2), "algorithmic_bytes": nb, "GBps": round(nb / us_b * 1e-3, 1),
+                                              "frac_of_peak": round(nb / us_b * 1e-3 / pk, 4), "kernel": ops.last_kernel()}
+            del dsets, gouts
             torch.cuda.empty_cache()
     launches = ops.launch_count()
 
@@ -242,8 +249,12 @@ def main():
         dt = (time.perf_counter() - t0) / reps
         res["cpu_baseline"] = {"kind": "port", "cores": cores, "sample": "%d of %d images, silog fwd+bwd, torch-CPU literal" % (sb, a.batch),
                                "GBps": round(6 * sb * a.height * a.width * 4 / dt * 1e-9, 2)}
-    print(json.dumps({"bench": "decoder tail (SURVEY 8(f) N2, N4)", "workload": "batch %d at %dx%d, %s" % (a.batch, a.height, a.width, a.dtype),
-                      "peak_GBps": pk, "peak_source": pk_src, "sets": a.sets, "steps": a.steps, "cuda_graph": not a.no_graph, "gpu_launches": launches, **res}))
+    return {"bench": "decoder tail (SURVEY 8(f) N2, N4)", "workload": "batch %d at %dx%d, %s" % (a.batch, a.height, a.width, a.dtype),
+            "peak_GBps": pk, "peak_source": pk_src, "sets": a.sets, "steps": a.steps, "cuda_graph": not a.no_graph, "gpu_launches": launches, **res}
+
+
+def main():
+    print(json.dumps(collect()))
 
 
 if __name__ == "__main__":

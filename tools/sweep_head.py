@@ -37,17 +37,9 @@ def timed(fn, nsets, n=40):
     return e0.elapsed_time(e1) / (reps * per_graph) * 1e3
 
 
-def main():
-    # --tune KEY=VALUE (btslpg_set_tuning, e.g. 7=1: register-staged loads instead of the TMA ring), --only-r R
-    only_r = None
-    for i, arg in enumerate(sys.argv[1:]):
-        if arg == "--tune":
-            k, v = sys.argv[i + 2].split("=")
-            ops.set_tuning(int(k), int(v))
-        if arg == "--only-r":
-            only_r = int(sys.argv[i + 2])
-    dev = torch.device("cuda:0")
-    B, H, W = 32, 480, 640
+def collect(dtypes=("f32", "bf16"), encoders=("densenet161", "resnet50"), only_r=None, B=32, H=480, W=640, device=None, n=40):
+    """Time every fused head forward / backward of the given decoders; returns {"peak": ..., "points": [...]}."""
+    dev = device or torch.device("cuda:0")
     peak = 6533.8
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -55,8 +47,12 @@ def main():
         pass
     out = {"peak": peak, "points": []}
     nsets = 2
+    all_enc = {"densenet161": (128, 128, 64), "resnet50": (64, 64, 32)}
     for dtype, es, name in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
-        for enc, chans in (("densenet161", (128, 128, 64)), ("resnet50", (64, 64, 32))):
+        if name not in dtypes:
+            continue
+        for enc in encoders:
+            chans = all_enc[enc]
             for (r, d), C in zip(((8, 4), (4, 2), (2, 0)), chans):
                 if only_r is not None and r != only_r:
                     continue
@@ -79,7 +75,7 @@ def main():
                 dsz = HW // (d * d) if d else 0
                 fb = es * B * (C * hw + 3 * hw + HW + dsz) + 4 * 3 * C
                 bb = es * B * (HW + dsz + 3 * hw + 2 * C * hw) + 2 * 4 * 3 * C
-                us = timed(fwd, nsets)
+                us = timed(fwd, nsets, n)
                 out["points"].append(dict(dtype=name, enc=enc, kernel="head_fwd_r%d_C%d" % (r, C), variant=ops.last_kernel(), us=round(us, 2),
                                           MB=round(fb / 1e6, 1), GBps=round(fb / us / 1e3, 1), frac=round(fb / us / 1e3 / peak, 3)))
 
@@ -98,12 +94,24 @@ def main():
                     _cabi.check(lib.btslpg_reduce_backward(refs[0].ptr, refs[1].ptr, refs[2].ptr, refs[3].ptr, _cabi.ptr_or_null(refs[4]), r, d,
                                                            refs[5].ptr, refs[6].ptr, None, ctypes.c_void_p(ws.data_ptr()), ws.numel(),
                                                            _cabi.current_stream_ptr(dev)))
-                us = timed(bwd_static, nsets)
+                us = timed(bwd_static, nsets, n)
                 out["points"].append(dict(dtype=name, enc=enc, kernel="head_bwd_r%d_C%d" % (r, C), variant=ops.last_kernel(), us=round(us, 2),
                                           MB=round(bb / 1e6, 1), GBps=round(bb / us / 1e3, 1), frac=round(bb / us / 1e3 / peak, 3)))
                 del feats, g_full, g_ds, coef, full, ds, gfeat
                 torch.cuda.empty_cache()
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    # --tune KEY=VALUE (btslpg_set_tuning, e.g. 7=1: register-staged loads instead of the TMA ring), --only-r R
+    only_r = None
+    for i, arg in enumerate(sys.argv[1:]):
+        if arg == "--tune":
+            k, v = sys.argv[i + 2].split("=")
+            ops.set_tuning(int(k), int(v))
+        if arg == "--only-r":
+            only_r = int(sys.argv[i + 2])
+    print(json.dumps(collect(only_r=only_r)))
 
 
 if __name__ == "__main__":
