@@ -222,7 +222,13 @@ class DataParallelStep:
                                    zero_grad=True)
         self.state = ops.adam_state(self.device)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
-        self.comm = ChunkedAllReduce(self.flat, self.device, overlap=overlap)
+        # ONE stream for every step, eager or captured.  Autograd pins a parameter's AccumulateGrad node (and with it the stream
+        # it runs on) the first time it is created -- here, when the hooks below are registered -- and keeps it alive for as
+        # long as a hook hangs on it; a node born on the default stream would drag the legacy stream into a later capture on
+        # another stream and invalidate it.  So: hooks are registered, warm-up steps run and the graph is captured on this stream.
+        self.stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self.stream):
+            self.comm = ChunkedAllReduce(self.flat, self.device, overlap=overlap)
         for m in self.decoder.modules():                           # the fused heads write g_kernel straight into the bucket
             if isinstance(m, ReductionLPG) and id(m.kernel) in self.flat.index:
                 m.bind_gradient_view(self.flat.flat_grad_slice(m.kernel), on_written=self.comm.writer_callback(m.kernel))
@@ -258,17 +264,23 @@ class DataParallelStep:
         self.loss.copy_(loss.detach())
         return self.loss
 
+    def _eager_step(self):
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self._step_body()
+        cur.wait_stream(self.stream)
+
     def capture(self):
         """Capture _step_body into one CUDA graph (call after a few eager steps: cuDNN autotuning, workspace allocation)."""
-        side = torch.cuda.Stream(self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(self.stream):
             # thread_local: NCCL's watchdog thread and the autograd worker threads stay free to make CUDA calls (event
             # queries, allocator growth) that a "global" capture would turn into capture-invalidating errors
-            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+            with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
                 self._step_body()
-        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
         self.graph = graph
         return graph
 
@@ -276,18 +288,36 @@ class DataParallelStep:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._step_body()
+            self._eager_step()
         self.steps_done += 1
         return self.loss
 
     def warmup_and_capture(self, warmup=3):
         for _ in range(max(1, warmup)):
-            self._step_body()
+            self._eager_step()
             self.steps_done += 1
         torch.cuda.synchronize(self.device)
         if self.use_graph:
             self.capture()
         return self
+
+    def local_gradients(self):
+        """Diagnostics / tests: this rank's gradient of its per-shard loss, with no exchange and no update (a copy of the flat
+        gradient buffer in the bucket's layout; the bucket is left zeroed).  Returns (flat gradient, loss)."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            enabled, self.comm.enabled = self.comm.enabled, False
+            self.comm.begin_step()
+            _, loss = self.decoder.forward_loss(self.feats, self.gt, self.dataset)
+            loss.backward()
+            self.comm.finish()
+            self.comm.enabled = enabled
+            g = self.flat.grad.clone()
+            self.flat.zero()
+            loss = loss.detach().clone()
+        cur.wait_stream(self.stream)
+        return g, loss
 
     def learning_rate(self):
         """lr of the last completed update (device -> host read)."""

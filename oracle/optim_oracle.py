@@ -43,11 +43,14 @@ def adamw_step(p, g, m, v, step, lr_start, lr_end=None, total_steps=0, power=0.9
         else:
             decay = dtype(l2) * p
         p = p - lr_t * decay
+    # Keras holds beta_1, beta_2 and epsilon as tensors of the VARIABLE's dtype (float32): the values that enter the arithmetic
+    # are float32(0.9), float32(0.999), float32(1e-3), not the Python doubles
+    b1, b2, eps = float(np.float32(beta1)), float(np.float32(beta2)), float(np.float32(epsilon))
     t = step + 1
-    alpha = dtype(float(lr) * np.sqrt(1.0 - float(beta2) ** t) / (1.0 - float(beta1) ** t))
-    m = m + (g - m) * dtype(1.0 - np.float32(beta1) if dtype == np.float32 else 1.0 - beta1)
-    v = v + (g * g - v) * dtype(1.0 - np.float32(beta2) if dtype == np.float32 else 1.0 - beta2)
-    p = p - alpha * m / (np.sqrt(v) + dtype(epsilon))
+    alpha = dtype(float(lr) * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    m = m + (g - m) * dtype(1.0 - b1)
+    v = v + (g * g - v) * dtype(1.0 - b2)
+    p = p - alpha * m / (np.sqrt(v) + dtype(eps))
     return p, m, v, lr
 
 

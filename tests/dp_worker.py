@@ -39,13 +39,7 @@ def main():
         flat = eng.flat
         p0 = flat.param.clone()
         # expected: local gradient by plain autograd (no hooks fire into NCCL: comm disabled), gathered and averaged
-        eng.comm.enabled = False
-        eng.comm.begin_step()
-        _, loss = dec.forward_loss(feats, gt, "nyu")
-        loss.backward()
-        local = flat.grad.clone()
-        flat.zero()
-        eng.comm.enabled = True
+        local, _ = eng.local_gradients()
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         mean_grad = torch.stack(gathered).double().mean(0)

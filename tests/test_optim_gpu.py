@@ -39,9 +39,11 @@ def test_adam_step_matches_oracle(n, decay):
         torch.cuda.synchronize()
         assert int(state.view(torch.int32)[0]) == step + 1
         assert float(state[1]) == float(lr)                                  # the schedule, bit for bit (float32 cast of the float64 formula)
-        np.testing.assert_allclose(dp.cpu().numpy(), rp, rtol=RTOL, atol=RTOL * 8e-4)
-        np.testing.assert_allclose(dm.cpu().numpy(), rm, rtol=RTOL, atol=1e-9)
-        np.testing.assert_allclose(dv.cpu().numpy(), rv, rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(dp.cpu().numpy(), rp, rtol=RTOL, atol=RTOL * 2.5e-3)     # floor: RTOL of the largest single update
+        # the moments are sums of terms of the gradient's scale (0.1 * 0.125, squared for v): entries that cancel towards zero
+        # keep an absolute error of a float32 ulp of that scale, so the absolute floor is 1e-6 of the largest entry
+        np.testing.assert_allclose(dm.cpu().numpy(), rm, rtol=RTOL, atol=1e-6 * np.abs(rm).max())
+        np.testing.assert_allclose(dv.cpu().numpy(), rv, rtol=RTOL, atol=1e-6 * np.abs(rv).max())
     assert torch.equal(dg.cpu(), grad)                                       # zero_grad off: the gradient is left alone
 
 
