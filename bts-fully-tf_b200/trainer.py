@@ -131,8 +131,10 @@ class ChunkedAllReduce:
     On CUDA the collective runs on a side stream behind an event (overlapping the rest of backward) and `wait(c)` makes the
     current stream wait for chunk c; on CPU (gloo, used by the tests of this logic) it runs inline."""
 
-    def __init__(self, flat, device, overlap=True):
+    def __init__(self, flat, device, overlap=True, producer_stream=None):
         self.flat, self.device = flat, torch.device(device)
+        self.producer = producer_stream    # the stream backward runs on (the hooks fire on autograd's worker thread, whose
+        self.hook_streams = set()          # "current stream" need not be it); hook_streams: what the hooks saw (diagnostics)
         self.world = _world()
         self.cuda = self.device.type == "cuda"
         self.overlap = bool(overlap)
@@ -142,19 +144,27 @@ class ChunkedAllReduce:
         self.pending = [0] * len(flat.chunks)
         self.launched = [False] * len(flat.chunks)
         self.launch_order = []             # chunk ids in the order their all-reduce was issued (last step)
-        self.hooks = [p.register_post_accumulate_grad_hook(lambda _p, c=flat.chunk_of[k]: self.ready(c)) for k, p in enumerate(flat.params)]
+        self.done = [False] * len(flat.params)
+        self.hooks = [p.register_post_accumulate_grad_hook(lambda _p, k=k: self.ready(k)) for k, p in enumerate(flat.params)]
 
     def writer_callback(self, p):
-        c = self.flat.chunk_of[self.flat.index[id(p)]]
-        return lambda: self.ready(c)
+        k = self.flat.index[id(p)]
+        return lambda: self.ready(k)
 
     def begin_step(self):
         for c, (_, _, a, b) in enumerate(self.flat.chunks):
             self.pending[c] = b - a + 1
             self.launched[c] = False
+        self.done = [False] * len(self.flat.params)
         self.launch_order = []
 
-    def ready(self, c):
+    def ready(self, k):
+        """Parameter k's gradient is complete.  Counted once per step: a parameter whose gradient a kernel writes into the
+        bucket reports through writer_callback, and autograd may still run its (empty) accumulation hook afterwards."""
+        if self.done[k]:
+            return
+        self.done[k] = True
+        c = self.flat.chunk_of[k]
         self.pending[c] -= 1
         if self.pending[c] == 0 and self.overlap:
             self.launch(c)
@@ -171,7 +181,11 @@ class ChunkedAllReduce:
             dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM)
             return
         cur = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(cur)                               # the chunk's gradients are enqueued on `cur`
+        self.hook_streams.add(cur.cuda_stream)
+        if self.producer is not None:
+            self.stream.wait_stream(self.producer)                 # the chunk's gradients are enqueued on the producer stream
+        if self.producer is None or cur.cuda_stream != self.producer.cuda_stream:
+            self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             work = dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
             work.wait()                                            # the side stream now depends on the collective
@@ -228,7 +242,7 @@ class DataParallelStep:
         # another stream and invalidate it.  So: hooks are registered, warm-up steps run and the graph is captured on this stream.
         self.stream = torch.cuda.Stream(self.device)
         with torch.cuda.stream(self.stream):
-            self.comm = ChunkedAllReduce(self.flat, self.device, overlap=overlap)
+            self.comm = ChunkedAllReduce(self.flat, self.device, overlap=overlap, producer_stream=self.stream)
         for m in self.decoder.modules():                           # the fused heads write g_kernel straight into the bucket
             if isinstance(m, ReductionLPG) and id(m.kernel) in self.flat.index:
                 m.bind_gradient_view(self.flat.flat_grad_slice(m.kernel), on_written=self.comm.writer_callback(m.kernel))
@@ -313,6 +327,24 @@ class DataParallelStep:
             loss.backward()
             self.comm.finish()
             self.comm.enabled = enabled
+            g = self.flat.grad.clone()
+            self.flat.zero()
+            loss = loss.detach().clone()
+        cur.wait_stream(self.stream)
+        return g, loss
+
+    def reduced_gradients(self):
+        """Diagnostics / tests: forward, backward and the (overlapped, chunked) exchange of one step WITHOUT the update.
+        Returns (a copy of the summed flat gradient, loss); the bucket is left zeroed."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.comm.begin_step()
+            _, loss = self.decoder.forward_loss(self.feats, self.gt, self.dataset)
+            loss.backward()
+            self.comm.finish()
+            for c in range(len(self.flat.chunks)):
+                self.comm.wait(c)
             g = self.flat.grad.clone()
             self.flat.zero()
             loss = loss.detach().clone()

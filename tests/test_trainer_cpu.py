@@ -151,3 +151,23 @@ def test_two_rank_gloo_chunked_allreduce_matches_single_process(tmp_path, overla
         torch.sqrt((out * out).mean()).backward()
         expect = flat.grad.clone() if expect is None else expect + flat.grad
     torch.testing.assert_close(r0["grad"], expect / world, rtol=1e-5, atol=1e-7)
+
+
+def test_readiness_is_counted_once_per_parameter():
+    """A parameter whose gradient a kernel writes into the bucket reports through writer_callback AND autograd may still run
+    its (empty) accumulation hook: the second report must not launch the chunk's all-reduce one parameter early
+    (the fused LPG heads did exactly that on the first 2-GPU run: chunks holding a head were exchanged too soon)."""
+    model = _toy()
+    flat = _flat_of(model, fractions=(1.0,))
+    comm = trainer.ChunkedAllReduce(flat, "cpu", overlap=True)
+    comm.begin_step()
+    n = len(flat.params)
+    cb = comm.writer_callback(flat.params[0])
+    cb()
+    cb()                                                   # duplicate report
+    comm.ready(0)                                          # and the hook's
+    assert comm.pending[0] == n - 1 and not comm.launched[0]
+    for k in range(1, n):
+        comm.ready(k)
+    assert comm.pending[0] == 0 and comm.launched[0] and comm.launch_order == [0]
+    comm.close()
