@@ -82,6 +82,25 @@ template <typename T, int R, int D, int M> int launch_head_bwd(HeadBwdParams<T> 
         snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd<%s,r%d,ds%d,C%d>", ElemTraits<T>::kName, R, D, 32 * M);
         return check_launch("btslpg_reduce_backward");
     }
+    if constexpr (R == 8) {
+        // Two kernels for r = 8 (profiles/r02_head_bwd8.md): whole patch per lane, 32-pixel warp tiles -- the faster one per
+        // pixel (0.91 of the HBM peak at B = 128) but coarse: at B = 32, 480x640 its 4800 tiles are 2.03 rounds of the ~2400
+        // resident warps, i.e. three rounds paid for two; and the lane-split kernel with 8-pixel tiles (0.86 at B = 128, 8.1
+        // rounds at B = 32).  The lane-split one is used while the coarse one would run fewer than 6 rounds.
+        constexpr int smem8 = head_bwd8_smem_bytes<T, M>(256 / 32);
+        static PerDevice per_dev8; const int resident = per_dev8.get([&] { return occupancy_blocks_smem(head_lpg_bwd8_kernel<T, D, M>, threads, smem8); });
+        const int impl = g_tune_head_impl.load();        // 2 / 3 force the coarse / the lane-split kernel (A/B measurements)
+        const bool fine = impl == 3 || (impl != 2 && (uint64_t)p.iters < 6ull * (uint64_t)resident * (threads / 32));
+        if (fine) {
+            const uint32_t tiles = (p.npix + 7) / 8;
+            uint32_t blocks = (tiles + (threads / 32) - 1) / (threads / 32);
+            if (blocks > (uint32_t)resident) blocks = resident;
+            if (blocks > max_blocks) blocks = max_blocks;
+            head_lpg_bwd8_kernel<T, D, M><<<blocks, threads, smem8, st>>>(p);
+            snprintf(tl_kernel, sizeof(tl_kernel), "head_lpg_bwd8<%s,r8,ds%d,C%d>", ElemTraits<T>::kName, D, 32 * M);
+            return check_launch("btslpg_reduce_backward");
+        }
+    }
     constexpr int smem = head_tma_smem_bytes<T, R, M, false>(256 / 32);
     static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(head_lpg_bwd_tma_kernel<T, R, D, M>, threads, smem); });
     uint32_t blocks = (p.iters + (threads / 32) - 1) / (threads / 32);
@@ -150,13 +169,18 @@ template <typename T> int run_head_bwd_fast(const HeadGeom &hg, const View *gfea
     uint32_t max_blocks = kHeadMaxBlocks;
     if (gkern) {
         const size_t per_block = (size_t)hg.C * 3 * sizeof(float);
-        if (!workspace || ws_bytes < kHeadWorkspaceHeader + per_block)
+        // rows: one per CTA plus one per group of kHeadGroup CTAs (head_grid_reduce); counters for <= kHeadMaxGroups groups
+        if (!workspace || ws_bytes < kHeadWorkspaceHeader + 2 * per_block)
             return fail(BTSLPG_EWORKSPACE, "reduce_backward: workspace of %zu bytes is too small (need >= %zu; "
                                            "btslpg_reduce_backward_workspace_bytes gives the recommended size)",
-                        ws_bytes, kHeadWorkspaceHeader + per_block);
+                        ws_bytes, kHeadWorkspaceHeader + 2 * per_block);
         if ((reinterpret_cast<uintptr_t>(workspace) % 16) != 0) return fail(BTSLPG_EWORKSPACE, "reduce_backward: workspace must be 16-byte aligned");
-        const size_t fit = (ws_bytes - kHeadWorkspaceHeader) / per_block;
+        const size_t rows = (ws_bytes - kHeadWorkspaceHeader) / per_block;
+        size_t fit = rows * kHeadGroup / (kHeadGroup + 1);
+        while (fit > 1 && fit + (fit + kHeadGroup - 1) / kHeadGroup > rows) --fit;
+        if (fit < 1) fit = 1;
         if (fit < max_blocks) max_blocks = (uint32_t)fit;
+        if (max_blocks > (uint32_t)(kHeadMaxGroups * kHeadGroup)) max_blocks = kHeadMaxGroups * kHeadGroup;
     }
     BTSLPG_HEAD_DISPATCH(launch_head_bwd, T, g.r, g.has_ds, hg.C, p, max_blocks, st);
     return fail(BTSLPG_ELAYOUT, "reduce_backward: no fused variant for upratio %d, C %d", g.r, hg.C);
@@ -184,9 +208,10 @@ extern "C" {
 
 size_t btslpg_reduce_backward_workspace_bytes(int64_t npix, int channels) {
     if (npix <= 0 || channels <= 0) return kHeadWorkspaceHeader;
-    int64_t blocks = (npix + 255) / 256;   // one CTA covers 8 warp iterations of 32 pixels
-    if (blocks > kHeadMaxBlocks) blocks = kHeadMaxBlocks;
+    int64_t blocks = (npix + 63) / 64;     // one CTA covers at least 8 warp tiles of 8 pixels
+    if (blocks > kHeadMaxGroups * kHeadGroup) blocks = kHeadMaxGroups * kHeadGroup;
     if (blocks < 1) blocks = 1;
+    blocks += (blocks + kHeadGroup - 1) / kHeadGroup + 1;           // + one row per group of CTAs (two-level reduction)
     return (size_t)kHeadWorkspaceHeader + (size_t)blocks * channels * 3 * sizeof(float);
 }
 

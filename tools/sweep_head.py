@@ -104,14 +104,17 @@ def collect(dtypes=("f32", "bf16"), encoders=("densenet161", "resnet50"), only_r
 
 def main():
     # --tune KEY=VALUE (btslpg_set_tuning, e.g. 7=1: register-staged loads instead of the TMA ring), --only-r R
-    only_r = None
+    only_r, batch = None, 32
     for i, arg in enumerate(sys.argv[1:]):
+        if arg == "--batch":
+            batch = int(sys.argv[i + 2])
         if arg == "--tune":
             k, v = sys.argv[i + 2].split("=")
             ops.set_tuning(int(k), int(v))
         if arg == "--only-r":
             only_r = int(sys.argv[i + 2])
-    print(json.dumps(collect(only_r=only_r)))
+    dtypes = ("f32",) if "--f32-only" in sys.argv else ("f32", "bf16")
+    print(json.dumps(collect(dtypes=dtypes, only_r=only_r, B=batch)))
 
 
 if __name__ == "__main__":
