@@ -83,6 +83,7 @@ SYMBOLS = {
                                              _TP, ctypes.c_void_p]),
     "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int,
                                               ctypes.c_int, ctypes.c_void_p]),
+    "btslpg_iconv1_forward": (ctypes.c_int, [_TP, ctypes.c_int, ctypes.POINTER(_TP), _TP, ctypes.c_int, _TP, ctypes.c_void_p]),
     "btslpg_upsample2x_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_upsample2x_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_affine_act": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_void_p]),

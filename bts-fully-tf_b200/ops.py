@@ -14,6 +14,9 @@ Reference lines replaced:
   upsample2x_nhwc                bts_decoder.py:31, :38, :97 UpSampling2D(size=2, 'nearest')
   affine_act                     bts_decoder.py:46-76 DenseASPP glue: BN affine + ReLU over channel slices
   depth_conv                     bts_decoder.py:102 last Conv2D(1, 3x3): fused data + weight gradient
+  iconv1_forward                 bts_decoder.py:98-100 ELU + concat1 + iconv1's convolution as one tcgen05 implicit GEMM (inference)
+  adam_step                      custom_optimizers.py:47-59 + Keras Adam + bts_train.py:125-131, one pass over flat buffers
+  eval_metrics_png16             custom_eval_metrics.py:24-88 + bts_predict.py:140-141 (metrics and the uint16 depth image)
 """
 import ctypes
 
@@ -628,6 +631,32 @@ class DepthConvFunction(torch.autograd.Function):
 def depth_conv(x_nhwc, weight, act_in=False):
     """The decoder's last convolution with autograd; C in (16, 32).  act_in=True: conv(elu(x)) with the ELU folded in."""
     return DepthConvFunction.apply(x_nhwc, weight, act_in)
+
+
+# ---------------------------------------------------------------------------------------------
+# iconv1 as a tcgen05 implicit GEMM over the concat's sources (inference)
+# ---------------------------------------------------------------------------------------------
+def kernel_hwio(weight):
+    """torch OIHW (O,I,3,3) conv weight -> float32 Keras HWIO (3,3,I,O) contiguous."""
+    return weight.detach().permute(2, 3, 1, 0).float().contiguous()
+
+
+def iconv1_forward(a, planes, kernel_hwio_, a_subpixel=False, act_out=False, out=None):
+    """bts_decoder.py:98-100 without concat1: out = conv3x3_same([elu(a), d2, d4, d8]) (then ELU if act_out).
+    a: upconv1's linear output (B,H,W,NF), NF in (16, 32), or its sub-pixel form (B,H/2,W/2,4*NF); planes: the three LPG maps
+    (B,H,W,1); kernel_hwio_: float32 (3,3,NF+3,NF).  TF32 tensor-core arithmetic (tcgen05), float32 accumulation.  No autograd."""
+    lib = load()
+    if a_subpixel:
+        B, H, W, nf = a.shape[0], 2 * a.shape[1], 2 * a.shape[2], a.shape[3] // 4
+    else:
+        B, H, W, nf = a.shape
+    if out is None:
+        out = torch.empty((B, H, W, nf), dtype=a.dtype, device=a.device)
+    ra, rk, ro = as_ref(a), as_ref(kernel_hwio_), as_ref(out)
+    rp = [as_ref(p.contiguous()) for p in planes]
+    check(lib.btslpg_iconv1_forward(ra.ptr, 1 if a_subpixel else 0, _tensor_ptr_array(rp), rk.ptr, 1 if act_out else 0, ro.ptr,
+                                    current_stream_ptr(a.device)))
+    return out
 
 
 def launch_count():

@@ -310,6 +310,27 @@ BTSLPG_API int btslpg_depthconv_forward(const BtsTensor *x, const BtsTensor *ker
                                         BtsTensor *y, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * iconv1 as a tcgen05 implicit GEMM that reads the SOURCES of concat1 (SURVEY 8(a) a10 + 8(f) N1) -- replaces, in inference,
+ * bts_decoder.py:98-100:
+ *     upconv1 = Conv2D(F/16, 3, activation='elu')(upsample1)                        only the ACTIVATION (pass the linear output)
+ *     concat1 = Concatenate(axis=3)([upconv1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled])
+ *     iconv1  = Conv2D(F/16, 3, strides=1, padding='same', use_bias=False, activation='elu')(concat1)
+ * concat1 is never materialised: the kernel stages elu(a) and the three planes into shared memory as the A operand of
+ * tcgen05.mma (TMEM accumulators), nine taps as nine address offsets into the same staged rows.
+ *   a        (B,H,W,NF) the LINEAR output of upconv1's convolution, NF = F/16 = 16 or 32; or, a_subpixel != 0,
+ *            (B,H/2,W/2,4*NF) in the sub-pixel layout of btslpg_concat_forward
+ *   planes   3 single-channel maps (B,H,W[,1]): depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled (concat order)
+ *   kernel   float32, the Keras HWIO kernel (3,3,NF+3,NF) as it lies in memory
+ *   act_out  0: out = the convolution (what btslpg_depthconv_forward(act_in = 1) consumes), 1: out = elu(convolution)
+ *   out      (B,H,W,NF)
+ * float32 tensors, contiguous, 32-byte aligned.  Arithmetic: TF32 operands (rounded to nearest), float32 accumulation --
+ * the precision of the library convolution it replaces (cuDNN with TF32 enabled, the framework default); tolerance against
+ * a float64 evaluation: 3e-3 of the largest output magnitude.  Fixed summation order: bit-reproducible.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_iconv1_forward(const BtsTensor *a, int a_subpixel, const BtsTensor *const *planes, const BtsTensor *kernel,
+                                     int act_out, BtsTensor *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The optimizer step of the data-parallel training loop as ONE pass over flat float32 buffers -- replaces
  *   custom_optimizers.py:47-59  AdamW._resource_apply_dense: `var -= lr * (l1*sign(var) + l2*var)` BEFORE the Adam update
  *   tf.keras.optimizers.Adam    alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t) ; m += (g - m)(1 - beta1) ;

@@ -181,3 +181,19 @@ def depthconv_backward(x, w9c, g_out):
             gw[ky, kx] = (g[..., None] * xp[:, ky:ky + H, kx:kx + W, :]).sum(axis=(0, 1, 2))
             gxp[:, ky:ky + H, kx:kx + W, :] += g[..., None] * w[ky, kx]
     return gxp[:, 1:-1, 1:-1, :], gw.reshape(9, C)
+
+
+def iconv1_forward(a_raw, planes, hwio, act_out=False):
+    """bts_decoder.py:98-100 in float64: concat1 = [elu(a_raw), d2, d4, d8] (:98-99), iconv1 = Conv2D(NF, 3, padding='same',
+    use_bias=False)(concat1) with the Keras HWIO kernel (3,3,NF+3,NF), then ELU if act_out (:100)."""
+    cat = concat_elu(a_raw, planes, act=True)                          # (B,H,W,NF+3)
+    B, H, W, C = cat.shape
+    w = np.asarray(hwio, np.float64).reshape(3, 3, C, -1)
+    xp = np.pad(cat, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    y = np.zeros((B, H, W, w.shape[-1]))
+    for ky in range(3):
+        for kx in range(3):
+            y += xp[:, ky:ky + H, kx:kx + W, :] @ w[ky, kx]
+    if act_out:
+        y = np.where(y > 0, y, np.expm1(np.minimum(y, 0)))
+    return y
