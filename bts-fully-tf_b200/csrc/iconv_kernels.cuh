@@ -15,8 +15,9 @@
 //        copy, each input row is staged once and used by nine taps of three output rows.
 //   * B: the Keras HWIO kernel re-laid in shared memory once per CTA as [tap][chunk][n][4] (K-major, LBO = NF*16, SBO = 128).
 //   * D: 128 lanes x NF columns of TMEM, two buffers, so the epilogue of row r overlaps the MMAs of row r + 1.
-// Warp roles (one CTA per SM, 12 warps): warp 0 issues tcgen05.mma (one thread); warps 1-7 load upconv1 / planes, apply the
-// ELU, round to TF32 and store the chunk planes (generic proxy -> fence.proxy.async -> mbarrier); warps 8-11 read TMEM
+// Warp roles (one CTA per SM, 12 warps): warp 0 issues tcgen05.mma (one thread); warps 1-7 copy upconv1 / the planes into the
+// chunk planes with cp.async four rows ahead, then apply the ELU and round to TF32 in place (generic proxy ->
+// fence.proxy.async -> mbarrier); warps 8-11 read TMEM
 // (tcgen05.ld 32x32b), apply the optional output ELU and store NHWC rows.  mbarrier pipelines: ring row full / empty
 // (empty is signalled by tcgen05.commit), accumulator full / empty.
 //
@@ -39,7 +40,8 @@ constexpr int kIcEpiWarp0 = 8;             // warps 8..11 (warp % 4 selects the 
 constexpr int kIcTW = 126;                 // output columns of a strip (128 positions of a tile minus the two halo columns)
 constexpr int kIcPos = 131;                // staged positions per row: 130 needed; 131 keeps the chunk planes on distinct banks
 constexpr int kIcPlane = kIcPos * 16;      // bytes of one chunk plane of a row
-constexpr int kIcRing = 6;                 // staged input rows
+constexpr int kIcRing = 8;                 // ring rows: 3 under the MMAs, 1 being activated, kIcAhead in flight
+constexpr int kIcAhead = 4;                // rows whose cp.async copies are in flight ahead of the row being activated
 
 template <int NF> struct IconvCfg {
     static constexpr int kCin = NF + 3;                          // [upconv1 (NF), d2, d4, d8]
@@ -48,7 +50,9 @@ template <int NF> struct IconvCfg {
     static constexpr int kPlaneChunk = NF / 4;                   // the chunk that holds [d2, d4, d8, 0]
     static constexpr int kRowBytes = kChunks * kIcPlane;
     static constexpr int kWBytes = 9 * kChunks * NF * 16;
-    static constexpr int kTmemCols = 2 * NF < 32 ? 32 : 2 * NF;  // two accumulator buffers; power of two >= 32
+    static constexpr int kParts = 3;                             // partial accumulators per output row (one per kernel row ky)
+    static constexpr int kBufCols = kParts * NF;                 // TMEM columns of one accumulator buffer
+    static constexpr int kTmemCols = 2 * kBufCols <= 128 ? 128 : 256;   // two buffers; power of two
     static constexpr int kBarBytes = 256;
     static constexpr int kSmemBytes = kIcRing * kRowBytes + kWBytes + kBarBytes;
     static_assert(NF == 16 || NF == 32, "iconv1 has F/16 = 16 or 32 filters");
@@ -168,10 +172,19 @@ __global__ void __launch_bounds__(kIcThreads, 1) iconv1_fwd_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        // ================= MMA issuer =================
+        // The whole warp walks the loop (so every value is warp-uniform and lives in the uniform datapath that UTCHMMA reads
+        // its descriptors from); one elected lane issues.  Descriptors are two 32-bit halves: the high half (SBO, version) is a
+        // constant, the low half is (address >> 4) | LBO << 16, so stepping to another tap / chunk pair is ONE integer add of a
+        // compile-time constant.  (First version: 64-bit descriptor arithmetic and a modulo per MMA on a single lane, ~80 cycles
+        // per MMA -- the issue loop, not the tensor pipe (19 % busy) or HBM (22 %), set the pace: 3700 cycles per row.)
+        {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NF >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t ring_addr = smem_u32(ring), w_addr = smem_u32(wsm);
+            constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                  // SBO = 128 B, descriptor version 1
+            const uint32_t a_lo0 = (smem_u32(ring) >> 4) | ((uint32_t)(kIcPlane >> 4) << 16);
+            const uint32_t b_lo0 = (smem_u32(wsm) >> 4) | ((uint32_t)(NF * 16 >> 4) << 16);
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(elected));
             uint32_t seq = 0, g = 0;
             for (uint32_t item = blockIdx.x; item < prm.items; item += gridDim.x) {
                 const IconvItem it = iconv_item(prm, item);
@@ -183,43 +196,55 @@ __global__ void __launch_bounds__(kIcThreads, 1) iconv1_fwd_kernel(const __grid_
                     const uint32_t buf = g & 1;
                     if (g >= 2) mbar_wait(&bar_acce[buf], ((g >> 1) + 1) & 1);       // the epilogue has drained this buffer
                     tc_fence_after();
-                    const uint32_t d_addr = tmem_base + buf * NF;
-                    uint32_t first = 1;
+                    if (elected) {
+                        // Three independent accumulation chains (one per kernel row ky, each in its own TMEM columns), issued
+                        // round-robin: consecutive tcgen05.mma into ONE accumulator complete ~84 cycles apart whatever N is
+                        // (measured: 45 MMAs -> 3700 cycles per row, 27 -> 2300), far above the 16-cycle pipe time of a
+                        // 128 x 32 x 8 step; independent chains overlap.  The epilogue adds the three partial tiles.
+                        const uint32_t d_addr = tmem_base + buf * Cfg::kBufCols;
+                        uint32_t row_lo[3];
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t row_addr = ring_addr + ((top + ky) % kIcRing) * Cfg::kRowBytes;
+                        for (int ky = 0; ky < 3; ++ky) row_lo[ky] = a_lo0 + ((top + ky) % kIcRing) * (uint32_t)(Cfg::kRowBytes >> 4);
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                             for (int jj = 0; jj < Cfg::kMmaPerTap; ++jj) {
-                                const uint64_t ad = umma_desc(row_addr + 2 * jj * kIcPlane + kx * 16, kIcPlane, 128);
-                                const uint64_t bd = umma_desc(w_addr + (((ky * 3 + kx) * CH + 2 * jj) * NF) * 16, NF * 16, 128);
-                                umma_tf32(d_addr, ad, bd, idesc, first ? 0u : 1u);
-                                first = 0;
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky) {
+                                    const uint32_t alo = row_lo[ky] + (uint32_t)((2 * jj * kIcPlane + kx * 16) >> 4);
+                                    const uint32_t blo = b_lo0 + (uint32_t)(((((ky * 3 + kx) * CH + 2 * jj) * NF) * 16) >> 4);
+                                    uint64_t ad, bd;
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(ad) : "r"(alo), "r"(desc_hi));
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(bd) : "r"(blo), "r"(desc_hi));
+                                    umma_tf32(d_addr + ky * NF, ad, bd, idesc, (kx | jj) ? 1u : 0u);
+                                }
                             }
                         }
+                        tc_commit(&bar_accf[buf]);                      // accumulator ready for the epilogue
+                        tc_commit(&bar_empty[top % kIcRing]);           // the top input row is not needed again
+                        if (j == it.rows - 1) {
+                            tc_commit(&bar_empty[(top + 1) % kIcRing]);
+                            tc_commit(&bar_empty[(top + 2) % kIcRing]);
+                        }
                     }
-                    tc_commit(&bar_accf[buf]);                          // accumulator ready for the epilogue
-                    tc_commit(&bar_empty[top % kIcRing]);               // the top input row is not needed again
-                    if (j == it.rows - 1) {
-                        tc_commit(&bar_empty[(top + 1) % kIcRing]);
-                        tc_commit(&bar_empty[(top + 2) % kIcRing]);
-                    }
+                    __syncwarp();
                 }
                 seq += it.rows + 2;
             }
         }
-        __syncwarp();
     } else if (warp <= kIcProdWarps) {
         // ================= producers: stage input rows =================
-        // The loads of row n + 1 are issued BEFORE row n is activated and stored (registers as the prefetch buffer): with the
-        // loads consumed in the same iteration every row paid a full DRAM round trip (first version: 3500 cycles per row
-        // against a 1250-cycle HBM floor).
+        // Two passes per row.  (1) cp.async (LDGSTS) copies of 16 bytes move upconv1's raw values from global memory straight
+        // into the chunk planes of a ring row kIcAhead rows ahead of the one being finished -- no registers, zero-fill outside
+        // the image ('same' pads the ACTIVATED map with zeros and elu(0) = 0), 4-byte copies for the three LPG planes.  (2) When
+        // a row has landed, the producers apply ELU + TF32 rounding to it IN PLACE (conflict-free LDS.128 / STS.128) and hand
+        // it to the tensor core.  With the loads held in registers (first two versions) a CTA had one row (~16 KB) in flight
+        // and ran at 1.0 TB/s: latency-bound.  Here kIcAhead rows (64 KB) are in flight per SM.
         constexpr int NP = kIcProdWarps * 32;
-        constexpr int PPP = NF / 8;                                   // 32-byte pieces per pixel
-        constexpr int UNR = (kIcPos * PPP + NP - 1) / NP;             // pieces per thread and row
+        constexpr int CU = NF / 4;                                    // chunks of upconv1 channels per position
         const int ptid = threadIdx.x - 32;
         const int Hs = prm.H >> 1, Ws = prm.W >> 1;
+        const uint32_t ring_addr = smem_u32(ring);
 
         struct Cursor {                                               // walks the staged rows of this CTA's items in order
             uint32_t item;
@@ -241,90 +266,81 @@ __global__ void __launch_bounds__(kIcThreads, 1) iconv1_fwd_kernel(const __grid_
                 if (c.valid) c.it = iconv_item(prm, c.item);
             }
         };
-        struct RowRegs {
-            uint32_t raw[UNR][8];
-            float pl[3];
-            bool live[UNR], pl_live;
-        };
-        auto row_load = [&](const Cursor &c, RowRegs &R) {
+        auto row_issue = [&](const Cursor &c, uint32_t row_addr) {
             const IconvItem &it = c.it;
             const int y = it.r0 - 1 + c.jr, npos = it.sw + 2;
             const bool yin = y >= 0 && y < prm.H;
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int idx = ptid + u * NP, p = idx / PPP, jj = idx % PPP, x = it.x0 - 1 + p;
-                R.live[u] = idx < npos * PPP && yin && x >= 0 && x < prm.W;
-                if (R.live[u]) {
-                    const float *src = prm.a_subpixel
-                        ? prm.a + ((((size_t)it.b * Hs + (y >> 1)) * Ws + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * NF + 8 * jj
-                        : prm.a + (((size_t)it.b * prm.H + y) * prm.W + x) * NF + 8 * jj;
-                    ldg_nc<8>(src, R.raw[u]);
-                }
+            for (int idx = ptid; idx < npos * CU; idx += NP) {        // consecutive lanes: consecutive 16-byte pieces of a pixel
+                const int pp = idx / CU, cc = idx % CU, x = it.x0 - 1 + pp;
+                const bool in = yin && x >= 0 && x < prm.W;
+                const float *src = prm.a;
+                if (in)
+                    src = prm.a_subpixel
+                        ? prm.a + ((((size_t)it.b * Hs + (y >> 1)) * Ws + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * NF + 4 * cc
+                        : prm.a + (((size_t)it.b * prm.H + y) * prm.W + x) * NF + 4 * cc;
+                const int sz = in ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(row_addr + cc * kIcPlane + pp * 16), "l"(src), "r"(sz) : "memory");
             }
-            const int xp = it.x0 - 1 + ptid;                          // the three LPG planes: one position per thread (npos <= 128 < NP)
-            R.pl_live = ptid < npos && yin && xp >= 0 && xp < prm.W;
-            if (R.pl_live) {
-                const size_t o = ((size_t)it.b * prm.H + y) * prm.W + xp;
-                R.pl[0] = __ldg(prm.p0 + o);
-                R.pl[1] = __ldg(prm.p1 + o);
-                R.pl[2] = __ldg(prm.p2 + o);
+            for (int idx = ptid; idx < npos * 3; idx += NP) {         // the three LPG planes -> lanes 0..2 of chunk [d2, d4, d8, 0]
+                const int k = idx / npos, pp = idx - k * npos, x = it.x0 - 1 + pp;
+                const bool in = yin && x >= 0 && x < prm.W;
+                const float *base = k == 0 ? prm.p0 : (k == 1 ? prm.p1 : prm.p2);
+                const float *src = in ? base + ((size_t)it.b * prm.H + y) * prm.W + x : base;
+                const int sz = in ? 4 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(row_addr + Cfg::kPlaneChunk * kIcPlane + pp * 16 + k * 4), "l"(src), "r"(sz)
+                             : "memory");
             }
         };
-        auto row_store = [&](const Cursor &c, const RowRegs &R, unsigned char *row) {
+        auto row_activate = [&](const Cursor &c, unsigned char *row) {
             const int npos = c.it.sw + 2;
-            if (ptid < npos) {                                        // chunk [d2, d4, d8, 0]
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (R.pl_live) v = make_float4(to_tf32(R.pl[0]), to_tf32(R.pl[1]), to_tf32(R.pl[2]), 0.f);
-                *reinterpret_cast<float4 *>(row + Cfg::kPlaneChunk * kIcPlane + ptid * 16) = v;
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int idx = ptid + u * NP, p = idx / PPP, jj = idx % PPP;
-                if (idx < npos * PPP) {
-                    float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;           // outside the image: 'same' pads the ACTIVATED map with zeros
-                    if (R.live[u]) {
-                        lo4 = make_float4(elu_tf32(__uint_as_float(R.raw[u][0])), elu_tf32(__uint_as_float(R.raw[u][1])),
-                                          elu_tf32(__uint_as_float(R.raw[u][2])), elu_tf32(__uint_as_float(R.raw[u][3])));
-                        hi4 = make_float4(elu_tf32(__uint_as_float(R.raw[u][4])), elu_tf32(__uint_as_float(R.raw[u][5])),
-                                          elu_tf32(__uint_as_float(R.raw[u][6])), elu_tf32(__uint_as_float(R.raw[u][7])));
-                    }
-                    *reinterpret_cast<float4 *>(row + (2 * jj) * kIcPlane + p * 16) = lo4;
-                    *reinterpret_cast<float4 *>(row + (2 * jj + 1) * kIcPlane + p * 16) = hi4;
+            for (int idx = ptid; idx < CU * 128; idx += NP) {         // consecutive lanes: consecutive positions of one plane
+                const int cc = idx >> 7, pp = idx & 127;
+                if (pp < npos) {
+                    float4 *q4 = reinterpret_cast<float4 *>(row + cc * kIcPlane + pp * 16);
+                    float4 v = *q4;
+                    v.x = elu_tf32(v.x); v.y = elu_tf32(v.y); v.z = elu_tf32(v.z); v.w = elu_tf32(v.w);
+                    *q4 = v;
                 }
+            }
+            if (ptid < npos) {
+                float4 *q4 = reinterpret_cast<float4 *>(row + Cfg::kPlaneChunk * kIcPlane + ptid * 16);
+                float4 v = *q4;
+                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z);
+                *q4 = v;
             }
         };
 
-        Cursor c0, c1;
-        cur_init(c0);
-        RowRegs ra, rb;
-        if (c0.valid) row_load(c0, ra);
-        uint32_t seq = 0;
-        while (c0.valid) {                                            // two rows per trip: the buffers alternate without copies
-            c1 = c0;
-            cur_next(c1);
-            if (c1.valid) row_load(c1, rb);
-            {
-                const uint32_t slot = seq % kIcRing;
-                if (seq >= kIcRing) mbar_wait(&bar_empty[slot], ((seq / kIcRing) + 1) & 1);
-                row_store(c0, ra, ring + slot * Cfg::kRowBytes);
-                fence_proxy_async();                                   // this thread's stores -> visible to the async proxy (tensor core)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[slot]);
-                ++seq;
+        Cursor ci, ca;
+        cur_init(ci);
+        ca = ci;
+        uint32_t seq_i = 0, seq_a = 0;
+#pragma unroll 1
+        for (int d = 0; d < kIcAhead; ++d) {                          // prime: kIcAhead rows in flight (the ring is empty: no waits)
+            if (ci.valid) {
+                row_issue(ci, ring_addr + (seq_i % kIcRing) * Cfg::kRowBytes);
+                ++seq_i;
+                cur_next(ci);
             }
-            if (!c1.valid) break;
-            c0 = c1;
-            cur_next(c0);
-            if (c0.valid) row_load(c0, ra);
-            {
-                const uint32_t slot = seq % kIcRing;
-                if (seq >= kIcRing) mbar_wait(&bar_empty[slot], ((seq / kIcRing) + 1) & 1);
-                row_store(c1, rb, ring + slot * Cfg::kRowBytes);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[slot]);
-                ++seq;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        while (ca.valid) {
+            if (ci.valid) {
+                const uint32_t slot = seq_i % kIcRing;
+                if (seq_i >= kIcRing) mbar_wait(&bar_empty[slot], ((seq_i / kIcRing) + 1) & 1);
+                row_issue(ci, ring_addr + slot * Cfg::kRowBytes);
+                ++seq_i;
+                cur_next(ci);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kIcAhead) : "memory");        // this thread's copies of row seq_a have landed
+            asm volatile("bar.sync 1, %0;" ::"n"(kIcProdWarps * 32) : "memory");       // ... and every other producer's
+            const uint32_t slot = seq_a % kIcRing;
+            row_activate(ca, ring + slot * Cfg::kRowBytes);
+            fence_proxy_async();                                       // this thread's stores -> visible to the async proxy (tensor core)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[slot]);
+            ++seq_a;
+            cur_next(ca);
         }
     } else {
         // ================= epilogue: TMEM -> registers -> NHWC rows =================
@@ -336,9 +352,17 @@ __global__ void __launch_bounds__(kIcThreads, 1) iconv1_fwd_kernel(const __grid_
                 const uint32_t buf = g & 1;
                 mbar_wait(&bar_accf[buf], (g >> 1) & 1);
                 tc_fence_after();
-                uint32_t r[NF];
-                tmem_ld_row<NF>(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * NF, r);
+                uint32_t r[NF], s[NF];
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * Cfg::kBufCols;
+                tmem_ld_row<NF>(taddr, r);
+                tmem_ld_row<NF>(taddr + NF, s);
                 tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < NF; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(s[e]));     // (ky0 + ky1) + ky2: fixed order
+                tmem_ld_row<NF>(taddr + 2 * NF, s);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < NF; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(s[e]));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_acce[buf]);            // the MMA warp may overwrite this buffer
