@@ -5,7 +5,16 @@
 using namespace btslpg;
 using namespace btslpg_api;
 
+namespace {
+std::atomic<unsigned long long *> g_iconv_prof{nullptr};
+}
+
 extern "C" {
+
+// tools only (not in include/btslpg.h): device buffer of >= 16 uint64 that subsequent launches add their roles' wait cycles to
+__attribute__((visibility("default"))) void btslpg_debug_iconv1_profile(void *device_u64) {
+    g_iconv_prof.store(static_cast<unsigned long long *>(device_u64));
+}
 
 int btslpg_iconv1_forward(const BtsTensor *a, int a_subpixel, const BtsTensor *const *planes, const BtsTensor *kernel, int act_out,
                           BtsTensor *out, void *stream) {
@@ -56,6 +65,7 @@ int btslpg_iconv1_forward(const BtsTensor *a, int a_subpixel, const BtsTensor *c
     const int64_t items = (int64_t)p.B * p.nseg * p.nstrips;
     if (items >= ((int64_t)1 << 31)) return fail(BTSLPG_ESHAPE, "out: too many work items");
     p.items = (uint32_t)items;
+    p.prof = g_iconv_prof.load();
 
     DeviceGuard guard(ov.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", ov.dev, cudaGetErrorString(guard.err));

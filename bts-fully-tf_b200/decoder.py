@@ -157,6 +157,7 @@ class BtsDecoder(nn.Module):
         self.iconv1 = _conv(nf + 3, nf)
         self.depth_conv = _conv(nf, 1)
         self.intermediates = {}
+        self.tensor_core_iconv1 = True          # inference: iconv1 on the tcgen05 kernel (TF32) while torch's cuDNN TF32 switch is on
         self._loss_ws = None
         self.reset_parameters_keras()
 
@@ -260,6 +261,19 @@ class BtsDecoder(nn.Module):
         # addressing.  cuDNN: forward 0.77 -> 0.48 ms, forward+backward 3.0 -> 1.7 ms (B = 16, 352x1216).
         nf1 = self.upconv1.weight.shape[0]
         pad1 = ops.pad_to(nf1 + 3)                                         # 35 -> 36 channels
+        self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
+                              "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
+        if (not torch.is_grad_enabled() and nf1 in (16, 32) and self.tensor_core_iconv1 and torch.backends.cudnn.allow_tf32
+                and iconv2.dtype == torch.float32):
+            # bts_decoder.py:98-103, inference, WITHOUT concat1: iconv1's convolution is a tcgen05 implicit GEMM that stages
+            # elu(upconv1) and the three LPG planes from their own buffers (ops.iconv1_forward), followed by the fused last
+            # convolution.  TF32 operands like the library convolution it replaces -- hence only while the framework's own
+            # TF32 switch (torch.backends.cudnn.allow_tf32, on by default) is on; with it off the float32 path below runs.
+            up4 = F.conv2d(iconv2, ops.subpixel_kernel(self.upconv1.weight), padding=1)       # (B, 4*nf1, H/2, W/2)
+            up4_nhwc = _nhwc_view(up4.contiguous(memory_format=torch.channels_last))
+            x = ops.iconv1_forward(up4_nhwc, [d2, d4, d8], ops.kernel_hwio(self.iconv1.weight), a_subpixel=True)
+            return ops.depthconv_forward(x, ops.kernel9c(self.depth_conv.weight), act_in=True,
+                                         sigmoid_scale=None if return_logit else self.max_depth)
         if nf1 % 4 == 0:
             up4 = F.conv2d(iconv2, ops.subpixel_kernel(self.upconv1.weight), padding=1)       # (B, 4*nf1, H/2, W/2)
             up4_nhwc = _nhwc_view(up4.contiguous(memory_format=torch.channels_last))
@@ -269,8 +283,6 @@ class BtsDecoder(nn.Module):
             up1_nhwc = _nhwc_view(up1_raw.contiguous(memory_format=torch.channels_last))
             concat1 = _to_nchw(ops.concat_nhwc(up1_nhwc, [d2, d4, d8], act=True, pad=pad1))
         iconv1_raw = _conv_padded_input(self.iconv1, concat1, pad1)
-        self.intermediates = {"reduction_8x8": red8, "reduction_4x4": red4, "reduction_2x2": red2,
-                              "depth_8x8_scaled": d8, "depth_4x4_scaled": d4, "depth_2x2_scaled": d2}
         fused_tail = iconv1_raw.shape[1] in (16, 32)
         if fused_tail and not torch.is_grad_enabled():
             # bts_decoder.py:100-103 in ONE pass over the raw conv output: iconv1's ELU, the last Conv2D(1, 3x3) and,

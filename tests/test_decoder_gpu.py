@@ -151,3 +151,36 @@ def test_inference_fast_path_equals_eval_path():
     assert ops.launch_count() >= 3 + 5 + 5               # heads, up-samplings, concats
     slow = dec(feats)                                    # grad enabled: unfused BatchNorm path
     np.testing.assert_allclose(fast.cpu().numpy(), slow.detach().cpu().numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_inference_with_tcgen05_iconv1_matches_reference_fixture(golden_dir):
+    """With the framework's TF32 switch on (its default), inference runs iconv1 as the tcgen05 implicit GEMM over the concat's
+    sources (no concat1).  TF32 operands: the depth map agrees with the float64 reference run of the UNMODIFIED bts_decoder.py to
+    the tolerance of a TF32 convolution chain (5e-3), and with this repo's own float32 path to the same."""
+    from oracle import decoder_fixture
+    z = np.load(os.path.join(golden_dir, "decoder_f256.npz"))
+    feats = [torch.from_numpy(z["feat_" + k]).float().to(DEV) for k in ("dense", "s2", "s4", "s8", "s16")]
+    dec = BtsDecoder([f.shape[-1] for f in feats], 10.0, num_filters=int(z["num_filters"])).to(DEV).eval()
+    dec.load_keras_kernels([k.float() for k in decoder_fixture.regen_kernels([tuple(s) for s in z["kernel_shapes"]], int(z["seed"]))])
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            exact = dec(feats)
+        torch.backends.cudnn.allow_tf32 = True
+        ops.reset_launch_count()
+        with torch.no_grad():
+            fast = dec(feats)
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    np.testing.assert_allclose(exact.cpu().numpy(), z["infer_depth_est"], rtol=5e-4, atol=1e-5)
+    np.testing.assert_allclose(fast.cpu().numpy(), z["infer_depth_est"], rtol=5e-3, atol=1e-4)
+    dec.tensor_core_iconv1 = False
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        with torch.no_grad():
+            lib = dec(feats)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old[0]
+    np.testing.assert_allclose(fast.cpu().numpy(), lib.cpu().numpy(), rtol=5e-3, atol=1e-4)
