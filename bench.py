@@ -39,7 +39,9 @@ UNIT = "GB/s"
 
 
 def parse_args():
-    ap = argparse.ArgumentParser()
+    # `@file` arguments as in the reference's scripts (bts_train.py:45-53: one or more whitespace-separated options per line)
+    ap = argparse.ArgumentParser(fromfile_prefix_chars="@")
+    ap.convert_arg_line_to_args = lambda line: [a for a in line.split() if a.strip()]
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
@@ -273,6 +275,13 @@ def heads_context(peak):
     fr = [p["frac"] for p in pts]
     return {"points": pts, "min_frac": min(fr), "max_frac": max(fr), "peak": out["peak"],
             "note": "B=32, 480x640; densenet161 C=128/128/64, resnet50 C=64/64/32; algorithmic bytes per BASELINE.md section 3"}
+
+
+def iconv_context():
+    """iconv1 without concat1 (tcgen05 implicit GEMM, bts_decoder.py:98-100) against the fused concat kernel + cuDNN convolution."""
+    _tools()
+    import bench_iconv
+    return bench_iconv.collect()
 
 
 def tail_context():
@@ -534,7 +543,7 @@ def main():
 
     # ---- the kernels the decoder actually launches (fused heads) and the decoder-tail kernels, same hygiene (N = 1 only)
     if not a.skip_extras and world == 1 and a.dtype == "f32":
-        for key, fn in (("heads", lambda: heads_context(peak)), ("tail", tail_context)):
+        for key, fn in (("heads", lambda: heads_context(peak)), ("tail", tail_context), ("iconv1_tcgen05", iconv_context)):
             try:
                 extras[key] = fn()
             except Exception as exc:  # noqa: BLE001

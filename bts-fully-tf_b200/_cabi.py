@@ -120,8 +120,39 @@ def load():
                     fn = getattr(lib, name)      # AttributeError if the ABI is incomplete
                     fn.restype = res
                     fn.argtypes = args
+                if os.environ.get("BTSLPG_NVTX"):
+                    lib = _NvtxProxy(lib)
                 _lib = lib
     return _lib
+
+
+class _NvtxProxy:
+    """BTSLPG_NVTX=1: every launch through the ABI sits in an NVTX range named after its entry point (nsys / ncu --nvtx
+    timelines; the reference's counterpart is the TensorBoard profiler of custom_callbacks.py).  Off by default: no overhead."""
+    _QUIET = ("btslpg_version", "btslpg_last_error", "btslpg_status_string", "btslpg_launch_count", "btslpg_reset_launch_count",
+              "btslpg_last_kernel")
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._lib, name)
+            if name in self._QUIET or name.endswith("_workspace_bytes"):
+                fn = raw
+            else:
+                import torch
+
+                def fn(*a, _raw=raw, _name=name):
+                    torch.cuda.nvtx.range_push(_name)
+                    try:
+                        return _raw(*a)
+                    finally:
+                        torch.cuda.nvtx.range_pop()
+            self._cache[name] = fn
+        return fn
 
 
 _VALUE_ERRORS = (-1, -2, -3, -4, -5)

@@ -17,6 +17,7 @@ Files written
                       float32-representable inputs/weights, inference BN and training BN
   decoder_f256.npz    the same at num_filters=256 (the channel counts of the fused fast paths); kernels are redrawn by
                       oracle/decoder_fixture.regen_kernels (checked bit for bit here), gradients of large kernels sampled
+  lpg_full_size_samples_shapes.npz   the same at 2 x 352 x 1216 (KITTI Eigen) and 2 x 416 x 544 (NYU training crop)
   lpg_full_size_samples.npz   the layer at FULL size (2 x 480 x 640, r = 8/4/2, seeded numpy inputs): 4096 sampled
                       outputs per scale instead of the 2.4 MB maps (the "full-size" pin of SURVEY 8(c))
   tail_silog.npz      bts.py:27-41 si_log_loss (nyu and kitti thresholds) on depth_est =
@@ -183,7 +184,7 @@ def golden_decoder_f256():
 
 def full_size_inputs(r, B=2, H=480, W=640):
     """Seeded inputs of the full-size pin (numpy Generator streams are stable across platforms)."""
-    rng = np.random.default_rng(4000 + r)
+    rng = np.random.default_rng(4000 + r + (0 if (H, W) == (480, 640) else H * 10000 + W))
     z = rng.standard_normal((B, H // r, W // r, 3)).astype(np.float32)
     coef = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
     idx = np.sort(rng.choice(B * H * W, size=4096, replace=False))
@@ -203,6 +204,24 @@ def golden_full_size():
         out["r%d_n_negative" % r] = int((y64 < 0).sum())
         print("lpg_full_size r=%d: sample mean %.6f, negatives %d" % (r, float(y64[idx].mean()), int((y64 < 0).sum())))
     np.savez_compressed(os.path.join(HERE, "lpg_full_size_samples.npz"), **out)
+
+
+def golden_full_size_shapes():
+    """The same pin at the reference's other two input sizes: KITTI Eigen 352 x 1216 (args/test_eigen.txt:8-9) and the NYU
+    training crop 416 x 544 (args/train_nyu.txt:13-14).  A separate file: lpg_full_size_samples.npz stays bit-identical."""
+    out = {}
+    for H, W in ((352, 1216), (416, 544)):
+        for r in (8, 4, 2):
+            coef, idx = full_size_inputs(r, 2, H, W)
+            y = custom_layers.LocalPlanarGuidance(upratio=r)(torch.from_numpy(coef)).numpy().reshape(-1)
+            y64 = custom_layers.LocalPlanarGuidance(upratio=r)(torch.from_numpy(coef).double()).numpy().reshape(-1)
+            key = "h%dw%d_r%d" % (H, W, r)
+            out[key + "_idx"] = idx
+            out[key + "_out"] = y[idx]
+            out[key + "_out64"] = y64[idx]
+            out[key + "_n_negative"] = int((y64 < 0).sum())
+            print("lpg_full_size %dx%d r=%d: sample mean %.6f, negatives %d" % (H, W, r, float(y64[idx].mean()), int((y64 < 0).sum())))
+    np.savez_compressed(os.path.join(HERE, "lpg_full_size_samples_shapes.npz"), **out)
 
 
 def golden_tail():
@@ -254,6 +273,7 @@ def golden_tail():
 
 if __name__ == "__main__":
     golden_full_size()
+    golden_full_size_shapes()
     golden_tail()
     golden_lpg()
     golden_pole()

@@ -320,6 +320,31 @@ def test_full_size_pin(golden_dir, r, d):
     parity.check_forward(npf(full), coef, r, what="full-size pin r=%d" % r)
 
 
+@pytest.mark.parametrize("H,W", [(352, 1216), (416, 544)])
+@pytest.mark.parametrize("r,d", RS)
+def test_full_size_pin_other_shapes(golden_dir, r, d, H, W):
+    """The same pin at KITTI Eigen 352 x 1216 and the NYU training crop 416 x 544: forward against sampled outputs of the
+    UNMODIFIED reference layer, backward against the float64 oracle."""
+    from test_oracle import full_size_inputs
+    z = np.load(os.path.join(golden_dir, "lpg_full_size_samples_shapes.npz"))
+    key = "h%dw%d_r%d" % (H, W, r)
+    coef, idx = full_size_inputs(r, 2, H, W)
+    full, ds = ops.lpg_forward(torch.from_numpy(coef).to(DEV), r, d)
+    assert ops.last_kernel().startswith("lpg_fwd_vec<f32,r%d" % r)
+    _, den = c_oracle.lpg_forward_f64(coef, r, return_den=True)
+    good = den.reshape(-1)[idx] >= parity.DEN_OK
+    got = npf(full).reshape(-1)[idx]
+    np.testing.assert_allclose(got[good], z[key + "_out64"][good], rtol=1e-5)
+    np.testing.assert_allclose(got[good], z[key + "_out"][good], rtol=1e-5)
+    assert int((full < 0).sum()) == int(z[key + "_n_negative"])
+    if d:
+        assert torch.equal(ds, full[:, ::d, ::d])
+    g = torch.Generator().manual_seed(H + r)
+    g_full = torch.randn(2, H, W, 1, generator=g)
+    gc = ops.lpg_backward(torch.from_numpy(coef).to(DEV), g_full.to(DEV), None, r, 0)
+    parity.check_backward(npf(gc), coef, g_full.numpy(), r, what="full-size bwd %dx%d r=%d" % (H, W, r))
+
+
 # ------------------------------------------------------------------------------------------------
 # errors and edge cases through the ABI
 # ------------------------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ def test_decoder_fixture_wiring(golden_dir):
 
 def full_size_inputs(r, B=2, H=480, W=640):
     """Same seeded inputs as tests/golden/make_golden.py:full_size_inputs (numpy Generator streams are stable)."""
-    rng = np.random.default_rng(4000 + r)
+    rng = np.random.default_rng(4000 + r + (0 if (H, W) == (480, 640) else H * 10000 + W))
     z = rng.standard_normal((B, H // r, W // r, 3)).astype(np.float32)
     coef = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
     idx = np.sort(rng.choice(B * H * W, size=4096, replace=False))
@@ -189,6 +189,23 @@ def test_full_size_pin(golden_dir, r):
     out32 = c_oracle.lpg_forward_f32(coef, r)
     np.testing.assert_allclose(out32.reshape(-1)[idx][good], z["r%d_out" % r][good], rtol=2e-6)
     assert int((out64 < 0).sum()) == int(z["r%d_n_negative" % r])      # the pole is crossed in the same places
+
+
+@pytest.mark.parametrize("H,W", [(352, 1216), (416, 544)])
+@pytest.mark.parametrize("r", [8, 4, 2])
+def test_full_size_pin_other_shapes(golden_dir, r, H, W):
+    """The same pin at KITTI Eigen 352 x 1216 and the NYU training crop 416 x 544 (tests/golden/lpg_full_size_samples_shapes.npz)."""
+    z = np.load(os.path.join(golden_dir, "lpg_full_size_samples_shapes.npz"))
+    key = "h%dw%d_r%d" % (H, W, r)
+    coef, idx = full_size_inputs(r, 2, H, W)
+    assert np.array_equal(idx, z[key + "_idx"])
+    out64, den = c_oracle.lpg_forward_f64(coef, r, return_den=True)
+    good = den.reshape(-1)[idx] >= 0.05
+    assert good.sum() > 4000
+    np.testing.assert_allclose(out64.reshape(-1)[idx][good], z[key + "_out64"][good], rtol=5e-7)
+    out32 = c_oracle.lpg_forward_f32(coef, r)
+    np.testing.assert_allclose(out32.reshape(-1)[idx][good], z[key + "_out"][good], rtol=2e-6)
+    assert int((out64 < 0).sum()) == int(z[key + "_n_negative"])
 
 
 def test_decoder_f256_fixture_kernels_regenerate(golden_dir):

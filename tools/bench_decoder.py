@@ -210,7 +210,9 @@ def run(cfg_id, a, rank, local_rank, world):
 
 
 def main():
-    ap = argparse.ArgumentParser()
+    # `@file` arguments as in the reference's scripts (bts_train.py:45-53: one or more whitespace-separated options per line)
+    ap = argparse.ArgumentParser(fromfile_prefix_chars="@")
+    ap.convert_arg_line_to_args = lambda line: [a for a in line.split() if a.strip()]
     ap.add_argument("--config", type=int, nargs="*", default=[3, 4, 5])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
