@@ -60,14 +60,15 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
         p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
         p.div_cb = FastDiv(p.col_blocks);
         p.div_h = FastDiv(p.H);
-        static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads); });
+        constexpr int smem = depthconv_bwd_smem_bytes<T, CC>();
+        static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads, smem); });
         uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;
         if (blocks > (uint32_t)kDcMaxBlocks) blocks = kDcMaxBlocks;
         if (gw) {
             const size_t fit = (workspace_bytes - kDcHeaderBytes) / ((size_t)9 * CC * sizeof(float));
             if (fit < blocks) blocks = (uint32_t)fit;
         }
-        depthconv_bwd_kernel<T, CC, ELU><<<blocks, kDcThreads, 0, st>>>(p);
+        depthconv_bwd_kernel<T, CC, ELU><<<blocks, kDcThreads, smem, st>>>(p);
         snprintf(tl_kernel, sizeof(tl_kernel), ELU ? "depthconv_bwd<%s,C%d,elu>" : "depthconv_bwd<%s,C%d>", ElemTraits<T>::kName, CC);
         return check_launch("btslpg_depthconv_backward");
     };

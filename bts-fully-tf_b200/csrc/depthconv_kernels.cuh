@@ -22,6 +22,9 @@
 
 namespace btslpg {
 
+__device__ __forceinline__ float load_smem1(const float *p) { return *p; }
+__device__ __forceinline__ float load_smem1(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
 constexpr int kDcThreads = 256;
 constexpr int kDcTileW = 128;            // pixels of one image row per work item
 constexpr int kDcHeaderBytes = 256;
@@ -72,12 +75,25 @@ __device__ __forceinline__ void dc_reduce_partials(const float *partial, uint32_
     }
 }
 
+// Two stages of (x tile, 3-row strip of g) in shared memory, filled with cp.async one work item ahead of the arithmetic.
+// The first version loaded the g strip, synchronised, loaded x into registers and only then computed: two exposed DRAM round
+// trips per 128-pixel item and CTA (0.45 of the HBM peak at C = 32, 0.34 at C = 16, profiles/r02 bench extras.tail).
+template <typename T, int C> struct DcBwdStage {
+    static constexpr int kXBytes = kDcTileW * C * (int)sizeof(T);             // 16 KB (float32, C = 32)
+    static constexpr int kGFloats = 3 * (kDcTileW + 2);
+    static constexpr int kGBytes = (kGFloats * (int)sizeof(T) + 15) / 16 * 16;
+    static constexpr int kBytes = kXBytes + kGBytes;
+};
+template <typename T, int C> __host__ __device__ constexpr int depthconv_bwd_smem_bytes() { return 2 * DcBwdStage<T, C>::kBytes; }
+
 template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThreads, 2) depthconv_bwd_kernel(const __grid_constant__ DepthConvBwdParams<T> prm) {
+    using St = DcBwdStage<T, C>;
     constexpr int LPP = C / 4;                 // lanes per pixel
     constexpr int PPW = 32 / LPP;              // pixels per warp pass
     constexpr int NW = kDcThreads / 32;
     constexpr int NCOL4 = 9 * C / 4;           // float4 columns of g_w: 72 (C = 32) or 36 (C = 16)
-    __shared__ float gs[3][kDcTileW + 2];
+    constexpr int EPV = 16 / (int)sizeof(T);   // elements per 16-byte copy
+    extern __shared__ __align__(16) unsigned char dcb_smem[];
     __shared__ __align__(16) float red[NW][9 * C];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -92,70 +108,83 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
             acc[t][e] = 0.0f;
         }
 
-    for (uint32_t item = blockIdx.x; item < prm.items; item += gridDim.x) {
+    // copies of one work item into a stage: the x tile (16-byte pieces) and the 3-row strip of g with its one-pixel halo
+    // (element-wise, zero-filled outside the image: padding='same')
+    auto prefetch = [&](uint32_t item, int stage) {
         uint32_t rowi, xb, b, y;
         prm.div_cb.divmod(item, rowi, xb);     // rowi = b * H + y
         prm.div_h.divmod(rowi, b, y);
         const uint32_t x0 = xb * kDcTileW;
         const uint32_t npx = min((uint32_t)kDcTileW, prm.W - x0);
-        // 3-row strip of g with a one-pixel halo, zeros outside the image (padding='same')
+        const uint32_t sbase = smem_u32(dcb_smem) + stage * St::kBytes;
+        const T *xsrc = prm.x + ((size_t)rowi * prm.W + x0) * C;
+        for (uint32_t i = threadIdx.x; i < npx * C / EPV; i += kDcThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(xsrc + (size_t)i * EPV) : "memory");
         for (uint32_t i = threadIdx.x; i < 3 * (kDcTileW + 2); i += kDcThreads) {
             const uint32_t r = i / (kDcTileW + 2), j = i % (kDcTileW + 2);
             const int yy = (int)y + (int)r - 1, xx = (int)x0 + (int)j - 1;
-            float v = 0.0f;
-            if (yy >= 0 && yy < (int)prm.H && xx >= 0 && xx < (int)prm.W && j <= npx + 1)
-                v = load1(prm.g + ((size_t)b * prm.H + yy) * prm.W + xx);
-            gs[r][j] = v;
+            const bool in = yy >= 0 && yy < (int)prm.H && xx >= 0 && xx < (int)prm.W && j <= npx + 1;
+            const T *gsrc = in ? prm.g + ((size_t)b * prm.H + yy) * prm.W + xx : prm.g;
+            if constexpr (sizeof(T) == 4) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + St::kXBytes + i * 4), "l"(gsrc), "r"(in ? 4 : 0) : "memory");
+            } else {                            // 2-byte elements: below cp.async's granularity, a plain store of the loaded value
+                reinterpret_cast<T *>(dcb_smem + stage * St::kBytes + St::kXBytes)[i] = in ? *gsrc : T(0.0f);
+            }
         }
+    };
+
+    uint32_t item = blockIdx.x;
+    if (item < prm.items) prefetch(item, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int k = 0; item < prm.items; item += gridDim.x, ++k) {
+        const int stage = k & 1;
+        if (item + gridDim.x < prm.items) prefetch(item + gridDim.x, stage ^ 1);       // the next item flies during this one's arithmetic
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
+        uint32_t rowi, xb;
+        prm.div_cb.divmod(item, rowi, xb);
+        const uint32_t x0 = xb * kDcTileW;
+        const uint32_t npx = min((uint32_t)kDcTileW, prm.W - x0);
+        const T *xs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes);
+        const T *gs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes + St::kXBytes);       // [3][kDcTileW + 2]
         const size_t row0 = ((size_t)rowi * prm.W + x0);
-        // U pixels per thread and iteration: all U loads of x are issued before the first use (the kernel holds ~110
-        // registers, i.e. 16 resident warps per SM -- one 16-byte load per thread in flight is latency-bound at 2.6 TB/s)
-        constexpr int U = kDcTileW / (NW * PPW) > 4 ? 4 : kDcTileW / (NW * PPW);
-        for (uint32_t base = wid * PPW + pl; base < npx; base += U * NW * PPW) {
-            float xv[U][4];
+        for (uint32_t px = wid * PPW + pl; px < npx; px += NW * PPW) {
+            float xv[4];
+            lds_elems<T, 4>(xs + (size_t)px * C + 4 * cg, xv);
+            float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float dact[4];
+            if constexpr (ELU) {
+                // x is the PRE-activation of iconv1 (bts_decoder.py:100): the layer input is elu(x), d elu / d x = x > 0 ? 1 : exp(x)
+                // (the same 4-instruction ELU as the forward, so that forward and backward see one function)
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t px = base + u * NW * PPW;
-                if (px < npx) load_elems<T, 4>(prm.x + (row0 + px) * C + 4 * cg, xv[u]);
+                for (int e = 0; e < 4; ++e) {
+                    const float ex = ex2_sfu(xv[e] * kLog2e);
+                    dact[e] = xv[e] > 0.0f ? 1.0f : ex;
+                    xv[e] = xv[e] > 0.0f ? xv[e] : ex - 1.0f;
+                }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t px = base + u * NW * PPW;
-                if (px >= npx) break;
-                float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                float dact[4];
-                if constexpr (ELU) {
-                    // x is the PRE-activation of iconv1 (bts_decoder.py:100): the layer input is elu(x), d elu / d x = x > 0 ? 1 : exp(x)
-                    // (the same 4-instruction ELU as the forward, so that forward and backward see one function)
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int tp = (dy + 1) * 3 + (dx + 1);
+                    const float gv = load_smem1(gs + (1 - dy) * (kDcTileW + 2) + px + 1 - dx);          // g at pixel q - (dy, dx)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float ex = ex2_sfu(xv[u][e] * kLog2e);
-                        dact[e] = xv[u][e] > 0.0f ? 1.0f : ex;
-                        xv[u][e] = xv[u][e] > 0.0f ? xv[u][e] : ex - 1.0f;
+                        out[e] = fmaf(gv, wr[tp][e], out[e]);
+                        acc[tp][e] = fmaf(gv, xv[e], acc[tp][e]);
                     }
                 }
+            if constexpr (ELU) {
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int t = (dy + 1) * 3 + (dx + 1);
-                        const float gv = gs[1 - dy][px + 1 - dx];          // g at pixel q - (dy, dx)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            out[e] = fmaf(gv, wr[t][e], out[e]);
-                            acc[t][e] = fmaf(gv, xv[u][e], acc[t][e]);
-                        }
-                    }
-                if constexpr (ELU) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) out[e] *= dact[e];
-                }
-                if (prm.g_x) store_elems<T, 4>(prm.g_x + (row0 + px) * C + 4 * cg, out);
+                for (int e = 0; e < 4; ++e) out[e] *= dact[e];
             }
+            if (prm.g_x) store_elems<T, 4>(prm.g_x + (row0 + px) * C + 4 * cg, out);
         }
-        __syncthreads();
+        __syncthreads();                        // the stage is refilled by the prefetch of the next iteration
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     if (!prm.g_w) return;     // uniform across the grid
     // lanes that share a channel group (fixed xor tree over the pixel slots), then warps, then CTAs
