@@ -84,6 +84,12 @@ SYMBOLS = {
     "btslpg_concat_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int,
                                               ctypes.c_int, ctypes.c_void_p]),
     "btslpg_iconv1_forward": (ctypes.c_int, [_TP, ctypes.c_int, ctypes.POINTER(_TP), _TP, ctypes.c_int, _TP, ctypes.c_void_p]),
+    "btslpg_bn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "btslpg_bn_elu_stats": (ctypes.c_int, [_TP, ctypes.c_int, _TP, _TP, _TP, _TP, ctypes.c_float, ctypes.c_float, _TP, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_void_p]),
+    "btslpg_bn_elu_backward_stats": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, _TP, _TP, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "btslpg_concat_backward_bn": (ctypes.c_int, [_TP, _TP, ctypes.c_int, _TP, _TP, ctypes.c_int, _TP, ctypes.POINTER(_TP), ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_void_p]),
     "btslpg_upsample2x_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_upsample2x_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_affine_act": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_void_p]),

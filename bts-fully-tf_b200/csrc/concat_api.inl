@@ -170,9 +170,10 @@ int btslpg_concat_forward(const BtsTensor *a, int a_subpixel, int act, const Bts
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
 }
 
-int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, int a_subpixel, BtsTensor *g_b,
-                           BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream) {
+int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor *y, int act, const BtsTensor *bn_pack, BtsTensor *g_a, int a_subpixel,
+                              BtsTensor *g_b, BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream) {
     if (!g_a) return fail(BTSLPG_EINVAL, "g_a: tensor is NULL");
+    const bool need_y = act != 0 || bn_pack != nullptr;
     if (act != 0 && act != 1) return fail(BTSLPG_EINVAL, "act must be 0 (none) or 1 (elu)");
     if (pad_channels < 0 || pad_channels > 7) return fail(BTSLPG_EINVAL, "pad_channels must be in [0, 7]");
     ConcatGeom g;
@@ -180,8 +181,14 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
     const int64_t ct = g.a.C + (g.has_b ? g.b.C : 0) + n_planes + pad_channels;
     if (g.out.C != ct) return fail(BTSLPG_ESHAPE, "g_out: last dimension must be %lld (= CA + CB + n_planes + pad_channels), got %lld", (long long)ct, (long long)g.out.C);
     View yv;
-    if (act) {
-        if (!y) return fail(BTSLPG_EINVAL, "y: the saved forward output is required when act != 0");
+    float *bn = nullptr;
+    if (bn_pack) {
+        if (a_subpixel) return fail(BTSLPG_EINVAL, "bn_pack: not available for the sub-pixel source");
+        if (g.out.dtype != kF32) return fail(BTSLPG_EDTYPE, "bn_pack: float32 tensors only");
+        if (int e = parse_f32_vec(bn_pack, "bn_pack", 8 * g.a.C, g.out.dev, bn)) return e;
+    }
+    if (need_y) {
+        if (!y) return fail(BTSLPG_EINVAL, "y: the saved forward output is required when act != 0 or a BatchNorm pack is given");
         if (int e = parse_nhwc(y, "y", yv)) return e;
         if (yv.B != g.out.B || yv.H != g.out.H || yv.W != g.out.W || yv.C != g.out.C) return fail(BTSLPG_ESHAPE, "y: shape differs from g_out");
         if (yv.dtype != g.out.dtype) return fail(BTSLPG_EDTYPE, "y: dtype differs from g_out");
@@ -195,12 +202,13 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
-        const int P = concat_tile_px<T>(ct, act ? 2 : 1);
+        const int P = concat_tile_px<T>(ct, need_y ? 2 : 1);
         if (P < 8) return fail(BTSLPG_ESHAPE, "concat: %lld channels do not fit the staging buffer", (long long)ct);
         ConcatParams<T> p;
         memset(&p, 0, sizeof(p));
         p.g_out = reinterpret_cast<const T *>(g.out.ptr);
-        p.y = act ? reinterpret_cast<const T *>(yv.ptr) : nullptr;
+        p.y = need_y ? reinterpret_cast<const T *>(yv.ptr) : nullptr;
+        p.bn = bn;
         p.g_a = reinterpret_cast<T *>(g.a.ptr);
         p.g_b = g.has_b ? reinterpret_cast<T *>(g.b.ptr) : nullptr;
         for (int k = 0; k < n_planes; ++k) p.g_plane[k] = g_planes[k] ? reinterpret_cast<T *>(g.plane[k].ptr) : nullptr;
@@ -213,14 +221,20 @@ int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, 
         p.div_cb = FastDiv(p.cb ? p.cb : 1);
         p.act = act;
         p.vec = (p.ca % (16 / sizeof(T)) == 0) && (p.cb % (16 / sizeof(T)) == 0);
-        const int smem = (act ? 2 : 1) * P * (int)ct * (int)sizeof(T);
+        const int smem = (need_y ? 2 : 1) * P * (int)ct * (int)sizeof(T);
         const uint64_t ntiles = ((uint64_t)g.npix + P - 1) / P;
         concat_allow_smem(concat_bwd_kernel<T>, smem);
         concat_bwd_kernel<T><<<concat_blocks(concat_bwd_kernel<T>, smem, ntiles), kConcatThreads, smem, st>>>(p);
-        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", p.sub_w ? "+subpixel" : "", p.ca, p.cb, p.np, p.pad);
+        snprintf(tl_kernel, sizeof(tl_kernel), "concat_bwd<%s,%s%s%s,C%u+%u+%u+%u>", ElemTraits<T>::kName, act ? "elu" : "id", bn ? "+bn" : "",
+                 p.sub_w ? "+subpixel" : "", p.ca, p.cb, p.np, p.pad);
         return check_launch("btslpg_concat_backward");
     };
     return g.out.dtype == kF32 ? go(float{}) : go(__nv_bfloat16{});
+}
+
+int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y, int act, BtsTensor *g_a, int a_subpixel, BtsTensor *g_b,
+                           BtsTensor *const *g_planes, int n_planes, int pad_channels, void *stream) {
+    return btslpg_concat_backward_bn(g_out, y, act, nullptr, g_a, a_subpixel, g_b, g_planes, n_planes, pad_channels, stream);
 }
 
 }  // extern "C"

@@ -43,6 +43,10 @@ template <typename T> struct ConcatParams {
     // BatchNormalization folded in: scale = gamma / sqrt(var + eps), shift = beta - mean * scale (bts_decoder.py:33-34, :41)
     const float *scale;
     const float *shift;
+    // backward only, optional: training-mode BatchNormalization between the activation and the concat (bnstat_kernels.cuh): the
+    // float32 [8][CA] pack {scale, shift, mean, std, 1/gamma, beta, c1 = mean(g), c2 = mean(g * xhat)};
+    // g_a = scale * (g - c1 - xhat * c2) * elu'(elu), xhat = (y - beta) / gamma and elu = mean + xhat * std recovered from the output y
+    const float *bn;
     uint64_t npix;
     uint32_t ca, cb, np, pad, ct;       // ct = ca + cb + np + pad; the pad channels are written as zeros (and ignored backward)
     uint32_t tile_px;                   // P: pixels per CTA iteration (multiple of 8)
@@ -306,6 +310,18 @@ template <typename T, bool ACT> __global__ void __launch_bounds__(kConcatThreads
     }
 }
 
+// gradient of source a for one element of channel c: plain slice, ELU' from the output, or the training-mode BatchNorm form
+template <typename T> __device__ __forceinline__ float concat_ga(const ConcatParams<T> &prm, float g, float y, uint32_t c) {
+    if (prm.bn) {
+        const uint32_t ca = prm.ca;
+        const float xhat = (y - __ldg(prm.bn + 5 * ca + c)) * __ldg(prm.bn + 4 * ca + c);
+        const float elu = fmaf(xhat, __ldg(prm.bn + 3 * ca + c), __ldg(prm.bn + 2 * ca + c));
+        const float d = __ldg(prm.bn + c) * (g - __ldg(prm.bn + 6 * ca + c) - xhat * __ldg(prm.bn + 7 * ca + c));
+        return prm.act ? d * elu_grad_from_output(elu) : d;
+    }
+    return prm.act ? g * elu_grad_from_output(y) : g;
+}
+
 template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_bwd_kernel(const __grid_constant__ ConcatParams<T> prm) {
     extern __shared__ __align__(16) unsigned char concat_smem[];
     const uint32_t P = prm.tile_px, ct = prm.ct;
@@ -320,12 +336,12 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_b
         const bool full = full_in && prm.vec;
         if (full_in) {
             flat_g2s_async<T>(prm.g_out + p0 * ct, gimg, npx * ct);
-            if (prm.act) flat_g2s_async<T>(prm.y + p0 * ct, yimg, npx * ct);
+            if (prm.act || prm.bn) flat_g2s_async<T>(prm.y + p0 * ct, yimg, npx * ct);
             flat_g2s_wait();
         } else {
             for (uint32_t i = threadIdx.x; i < npx * ct; i += kConcatThreads) {
                 gimg[i] = prm.g_out[p0 * ct + i];
-                if (prm.act) yimg[i] = prm.y[p0 * ct + i];
+                if (prm.act || prm.bn) yimg[i] = prm.y[p0 * ct + i];
             }
         }
         __syncthreads();
@@ -352,7 +368,7 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_b
 #pragma unroll
                     for (int e = 0; e < V; ++e) {
                         const float g = smem_get<T>(gimg, p * ct + c + e);
-                        v[e] = prm.act ? g * elu_grad_from_output(smem_get<T>(yimg, p * ct + c + e)) : g;
+                        v[e] = concat_ga<T>(prm, g, (prm.act || prm.bn) ? smem_get<T>(yimg, p * ct + c + e) : 0.0f, c + e);
                     }
                     store_elems<T, V, 4>(prm.g_a + p0 * prm.ca + i, v);
                 }
@@ -361,7 +377,7 @@ template <typename T> __global__ void __launch_bounds__(kConcatThreads) concat_b
                     uint32_t p, c;
                     prm.div_ca.divmod(i, p, c);
                     const float g = smem_get<T>(gimg, p * ct + c);
-                    store1(prm.g_a + p0 * prm.ca + i, prm.act ? g * elu_grad_from_output(smem_get<T>(yimg, p * ct + c)) : g);
+                    store1(prm.g_a + p0 * prm.ca + i, concat_ga<T>(prm, g, (prm.act || prm.bn) ? smem_get<T>(yimg, p * ct + c) : 0.0f, c));
                 }
             }
         }

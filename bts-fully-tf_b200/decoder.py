@@ -79,6 +79,7 @@ class _ConvBlock(nn.Module):
         self.pad = ops.pad_to(nf + cskip + clpg)
         # inference: evaluate the upconv on the low-res input (ops.subpixel_kernel) where cuDNN gains from it (block2: 0.76 -> 0.57 ms)
         self.subpixel_inference = bool(subpixel_inference) and nf % 4 == 0
+        self.fused_training_glue = True     # training: ELU + BatchNorm (batch statistics) + concat on the hand-written kernels
 
     def forward(self, x, skip_nhwc, lpg_nhwc=None):
         planes = [lpg_nhwc] if lpg_nhwc is not None else []            # order is load-bearing (bts_decoder.py:42)
@@ -91,8 +92,17 @@ class _ConvBlock(nn.Module):
             cat = ops.concat_forward(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, skip_nhwc.contiguous(), act=True,
                                      pad=self.pad, scale=scale, shift=shift, a_subpixel=self.subpixel_inference)
             return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
-        up = self.bn(F.elu(self.upconv(_upsample2x(x))))               # training / autograd: BatchNorm needs its batch statistics
-        cat = ops.concat_nhwc(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, b=skip_nhwc, act=False, pad=self.pad)
+        raw = self.upconv(_upsample2x(x))
+        nf = raw.shape[1]
+        if self.training and self.fused_training_glue and ops.bn_glue_supported(nf, nf + skip_nhwc.shape[-1] + len(planes) + self.pad, raw.dtype):
+            # training: ELU + BatchNormalization (batch statistics, moving averages) + concat as a statistics pass and ONE fused pass,
+            # forward and backward (ops.conv_block_glue); the framework runs three read+write passes each way
+            cat = ops.conv_block_glue(_nhwc_view(raw.contiguous(memory_format=torch.channels_last)), skip_nhwc, planes, self.bn, pad=self.pad)
+            if self.bn.num_batches_tracked is not None:
+                self.bn.num_batches_tracked.add_(1)
+        else:
+            up = self.bn(F.elu(raw))                                    # autograd in eval mode / unsupported channel counts: the framework's BatchNorm
+            cat = ops.concat_nhwc(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, b=skip_nhwc, act=False, pad=self.pad)
         return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
 
 

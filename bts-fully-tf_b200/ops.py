@@ -489,6 +489,73 @@ def concat_nhwc(a, planes=(), b=None, act=False, pad=0, a_subpixel=False):
     return ConcatFunction.apply(a, b, bool(act), int(pad), bool(a_subpixel), *planes)
 
 
+# ---------------------------------------------------------------------------------------------
+# training-mode conv block glue: ELU + BatchNormalization (batch statistics) + concat (bts_decoder.py:30-44)
+# ---------------------------------------------------------------------------------------------
+def bn_glue_supported(ca, ct, dtype):
+    """The fused training glue takes float32, a power-of-two channel count in [4, 1024] and a concat width that is a multiple of 4."""
+    return dtype == torch.float32 and 4 <= ca <= 1024 and (ca & (ca - 1)) == 0 and ct % 4 == 0
+
+
+def bn_elu_stats(raw, gamma, beta, running_mean, running_var, momentum, eps, pack=None, act=True):
+    """Batch statistics of elu(raw) per channel -> pack [8][C] (scale, shift, mean, std, 1/gamma, beta, -, -); updates the moving
+    averages in place when given.  One read of `raw`, deterministic."""
+    lib = load()
+    C = raw.shape[-1]
+    if pack is None:
+        pack = torch.empty((8, C), dtype=torch.float32, device=raw.device)
+    ws = _workspace(raw.device, int(lib.btslpg_bn_workspace_bytes(C)))
+    rr, rg, rb, rp = as_ref(raw), as_ref(gamma), as_ref(beta), as_ref(pack)
+    rm, rv = as_ref(running_mean), as_ref(running_var)
+    check(lib.btslpg_bn_elu_stats(rr.ptr, 1 if act else 0, rg.ptr, rb.ptr, ptr_or_null(rm), ptr_or_null(rv), float(momentum), float(eps),
+                                  rp.ptr, ctypes.c_void_p(ws.data_ptr()), ws.numel(), current_stream_ptr(raw.device)))
+    return pack
+
+
+class ConvBlockGlueFunction(torch.autograd.Function):
+    """(raw upconv output, skip, gamma, beta, planes...) -> concat [BN(elu(raw)), skip, planes..., zero pad] in training mode, as one
+    statistics pass + one fused concat pass forward and the same backward (csrc/bnstat_kernels.cuh, csrc/concat_kernels.cuh)."""
+
+    @staticmethod
+    def forward(ctx, raw, skip, gamma, beta, running_mean, running_var, momentum, eps, pad, *planes):
+        raw_c, skip_c = raw.contiguous(), skip.contiguous()
+        pack = bn_elu_stats(raw_c, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), running_mean, running_var, momentum, eps)
+        out = concat_forward(raw_c, [p.contiguous() for p in planes], skip_c, act=True, pad=pad, scale=pack[0], shift=pack[1])
+        ctx.save_for_backward(out, pack)
+        ctx.ca, ctx.cb, ctx.np, ctx.pad = raw_c.shape[-1], skip_c.shape[-1], len(planes), pad
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        out, pack = ctx.saved_tensors
+        lib = load()
+        g_out = g_out.contiguous()
+        B, H, W, _ = g_out.shape
+        g_gamma = torch.empty(ctx.ca, dtype=torch.float32, device=g_out.device)
+        g_beta = torch.empty(ctx.ca, dtype=torch.float32, device=g_out.device)
+        ws = _workspace(g_out.device, int(lib.btslpg_bn_workspace_bytes(ctx.ca)))
+        rg, ry, rp, rgg, rgb = as_ref(g_out), as_ref(out), as_ref(pack), as_ref(g_gamma), as_ref(g_beta)
+        check(lib.btslpg_bn_elu_backward_stats(rg.ptr, ry.ptr, int(ctx.ca), rp.ptr, rgg.ptr, rgb.ptr, ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                               current_stream_ptr(g_out.device)))
+        g_a = torch.empty((B, H, W, ctx.ca), dtype=g_out.dtype, device=g_out.device)
+        g_b = torch.empty((B, H, W, ctx.cb), dtype=g_out.dtype, device=g_out.device)
+        need_planes = [ctx.needs_input_grad[9 + k] for k in range(ctx.np)]
+        g_p = [torch.empty((B, H, W, 1), dtype=g_out.dtype, device=g_out.device) if need_planes[k] else None for k in range(ctx.np)]
+        ra, rb = as_ref(g_a), as_ref(g_b)
+        rpl = [as_ref(p) for p in g_p]
+        check(lib.btslpg_concat_backward_bn(rg.ptr, ry.ptr, 1, rp.ptr, ra.ptr, 0, rb.ptr, _tensor_ptr_array(rpl), ctx.np, int(ctx.pad),
+                                            current_stream_ptr(g_out.device)))
+        return (g_a, g_b, g_gamma, g_beta, None, None, None, None, None) + tuple(g_p)
+
+
+def conv_block_glue(raw, skip, planes, bn, pad=0):
+    """bts_decoder.py:32-42 in TRAINING mode for a torch BatchNorm2d `bn` (its weight / bias / running statistics are used and
+    updated): concat [bn(elu(raw)), skip, *planes] (+ `pad` zero channels), NHWC."""
+    return ConvBlockGlueFunction.apply(raw, skip, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps),
+                                       int(pad), *planes)
+
+
 _subpixel_R = {}
 
 

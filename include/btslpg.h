@@ -249,6 +249,35 @@ BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y
                                       void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * TRAINING-mode conv block glue -- bts_decoder.py:30-44:
+ *     upconv = Conv2D(nf, 3, activation='elu')(upsample) ; upconv = BatchNormalization(momentum=0.99, epsilon=1.1e-5)(upconv, training)
+ *     concat = Concatenate(axis=3)([upconv, skip(, lpg)])
+ * as a statistics pass plus the fused concat pass, forward and backward (the framework: ELU, BatchNorm, cat = three read+write
+ * passes each way).  `pack` is a float32 [8][C] device buffer owned by the caller and shared by the four calls of a block:
+ * {scale, shift, mean, std, 1/gamma, beta, c1, c2}.
+ *   btslpg_bn_elu_stats            raw (B,H,W,C) = the convolution's LINEAR output; act = 1: statistics of elu(raw).  Writes
+ *                                  pack[0..5] (scale = gamma / sqrt(var + eps) with the BIASED batch variance, shift = beta - mean * scale)
+ *                                  and, when given, the moving averages: running = (1 - momentum) * running + momentum * batch value
+ *                                  (momentum = 1 - Keras' 0.99; unbiased variance, as fused batch norm does).  Feed pack[0], pack[1]
+ *                                  to btslpg_concat_forward as scale / shift.
+ *   btslpg_bn_elu_backward_stats   g_out, y: gradient and saved output of the concat (B,H,W,CT), the block's `channels` first.
+ *                                  Writes g_gamma = sum g * xhat, g_beta = sum g (xhat = (y - beta) / gamma: recovered from the output,
+ *                                  nothing else is kept alive) and pack[6..7] = their means.
+ *   btslpg_concat_backward_bn      btslpg_concat_backward with the pack: g_a = scale * (g - c1 - xhat * c2) * elu'(elu).
+ * float32, C a power of two in [4, 1024], CT a multiple of 4.  Deterministic (fixed-order sums, no atomics).
+ * workspace: btslpg_bn_workspace_bytes(C) bytes, 16-byte aligned, no initialisation needed.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API size_t btslpg_bn_workspace_bytes(int channels);
+BTSLPG_API int btslpg_bn_elu_stats(const BtsTensor *raw, int act, const BtsTensor *gamma, const BtsTensor *beta, BtsTensor *running_mean,
+                                   BtsTensor *running_var, float momentum, float eps, BtsTensor *pack, void *workspace,
+                                   size_t workspace_bytes, void *stream);
+BTSLPG_API int btslpg_bn_elu_backward_stats(const BtsTensor *g_out, const BtsTensor *y, int channels, BtsTensor *pack, BtsTensor *g_gamma,
+                                            BtsTensor *g_beta, void *workspace, size_t workspace_bytes, void *stream);
+BTSLPG_API int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor *y, int act, const BtsTensor *bn_pack, BtsTensor *g_a,
+                                         int a_subpixel, BtsTensor *g_b, BtsTensor *const *g_planes, int n_planes, int pad_channels,
+                                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the
  * `layers.UpSampling2D(size=2, interpolation='nearest')` in front of every upconv of the decoder
  * (bts_decoder.py:31, :38, :97): out[b, y, x, :] = in[b, y/2, x/2, :].

@@ -197,3 +197,17 @@ def iconv1_forward(a_raw, planes, hwio, act_out=False):
     if act_out:
         y = np.where(y > 0, y, np.expm1(np.minimum(y, 0)))
     return y
+
+
+def conv_block_glue(raw, skip, planes, gamma, beta, eps, pad=0):
+    """bts_decoder.py:32-42 in TRAINING mode, float64: elu -> BatchNormalization with the batch's own (biased) statistics ->
+    Concatenate([., skip, *planes]) (+ zero pad channels).  Returns (concat, mean, biased variance)."""
+    x = np.asarray(raw, np.float64)
+    e = np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    mean = e.mean(axis=(0, 1, 2))
+    var = e.var(axis=(0, 1, 2))
+    up = (e - mean) / np.sqrt(var + eps) * np.asarray(gamma, np.float64) + np.asarray(beta, np.float64)
+    parts = [up, np.asarray(skip, np.float64)] + [np.asarray(p, np.float64).reshape(x.shape[:3] + (1,)) for p in planes]
+    if pad:
+        parts.append(np.zeros(x.shape[:3] + (pad,)))
+    return np.concatenate(parts, axis=3), mean, var
