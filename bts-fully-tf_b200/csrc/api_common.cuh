@@ -93,6 +93,18 @@ inline bool is_contig_nhwc(const View &v) {
     return v.sC == 1 && v.sW == v.C && v.sH == v.W * v.C && v.sB == v.H * v.W * v.C;
 }
 
+// (B,H,W,C) NHWC view whose pixels are uniformly strided (e.g. a channel slice of a wider NHWC buffer)
+inline int parse_pixel_strided(const BtsTensor *t, const char *name, View &v) {
+    if (int e = parse_nhwc(t, name, v)) return e;
+    const int64_t npix = v.B * v.H * v.W;
+    if (npix * v.C == 0) return 0;
+    if (v.C > 1 && v.sC != 1) return fail(BTSLPG_ELAYOUT, "%s: channel stride must be 1", name);
+    const bool uniform = (v.H == 1 || v.sH == v.W * v.sW) && (v.B == 1 || v.sB == v.H * v.sH);
+    if (!uniform) return fail(BTSLPG_ELAYOUT, "%s: pixels must be uniformly strided (a channel slice of a contiguous NHWC tensor)", name);
+    if (v.sW < v.C) return fail(BTSLPG_ELAYOUT, "%s: pixel stride %lld is smaller than the channel count %lld", name, (long long)v.sW, (long long)v.C);
+    return 0;
+}
+
 // flat (B,H,W[,1]) map: contiguous, 16-byte aligned
 inline int parse_flat(const BtsTensor *t, const char *name, View &v, int64_t &n) {
     if (int e = parse_map(t, name, v)) return e;

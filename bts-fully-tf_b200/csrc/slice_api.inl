@@ -1,21 +1,5 @@
 // slice_api.inl -- C ABI for the strided affine + activation copy (DenseASPP glue, bts_decoder.py:46-76); included by its own .cu translation unit.
 
-namespace {
-
-// (B,H,W,C) NHWC view whose pixels are uniformly strided (e.g. a channel slice of a wider NHWC buffer)
-int parse_pixel_strided(const BtsTensor *t, const char *name, View &v) {
-    if (int e = parse_nhwc(t, name, v)) return e;
-    const int64_t npix = v.B * v.H * v.W;
-    if (npix * v.C == 0) return 0;
-    if (v.C > 1 && v.sC != 1) return fail(BTSLPG_ELAYOUT, "%s: channel stride must be 1", name);
-    const bool uniform = (v.H == 1 || v.sH == v.W * v.sW) && (v.B == 1 || v.sB == v.H * v.sH);
-    if (!uniform) return fail(BTSLPG_ELAYOUT, "%s: pixels must be uniformly strided (a channel slice of a contiguous NHWC tensor)", name);
-    if (v.sW < v.C) return fail(BTSLPG_ELAYOUT, "%s: pixel stride %lld is smaller than the channel count %lld", name, (long long)v.sW, (long long)v.C);
-    return 0;
-}
-
-}  // namespace
-
 extern "C" {
 
 int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, const BtsTensor *shift, int act, BtsTensor *dst, void *stream) {

@@ -133,6 +133,124 @@ class _DenseAspp(nn.Module):
         return self.conv2(x)
 
 
+def _conv_backward(g_nhwc, x_nhwc, conv):
+    """(d input, d weight) of a bias-free stride-1 convolution, NHWC tensors in and out (cuDNN through the framework's own entry)."""
+    g_in, g_w, _ = torch.ops.aten.convolution_backward(_to_nchw(g_nhwc), _to_nchw(x_nhwc), conv.weight, None, [1, 1], list(conv.padding),
+                                                       list(conv.dilation), False, [0, 0], 1, [True, True, False])
+    return _nhwc_view(g_in.contiguous(memory_format=torch.channels_last)), g_w
+
+
+def _conv_nhwc(x_nhwc, conv):
+    return _nhwc_view(F.conv2d(_to_nchw(x_nhwc), conv.weight, None, 1, conv.padding, conv.dilation).contiguous(memory_format=torch.channels_last))
+
+
+class DenseAsppTrainFunction(torch.autograd.Function):
+    """The DenseASPP of bts_decoder.py:46-76 in TRAINING mode, iconv4 -> concat4_daspp, on ONE (B,h,w,nf + 5 nf/2) buffer the blocks
+    append to.  The convolutions are cuDNN; everything between them is the hand-written glue of csrc/bnrelu_kernels.cuh and
+    csrc/slice_kernels.cuh:
+      forward   per-channel batch moments are taken once per appended piece and shared by every BatchNormalization over a concat that
+                contains it; Concatenate + BatchNormalization + ReLU in front of a 1x1 conv = one affine_act pass over a channel slice
+      backward  ReLU' + BatchNormalization' = a statistics pass and an apply pass that ADDS into the slice of the shared gradient
+                buffer (the Concatenates' backward).
+    Inputs: iconv4 (NCHW), the decoder (for the layers' hyper-parameters and moving averages), then the parameters in
+    BtsDecoder._daspp_params() order (so that their gradients come back through autograd)."""
+
+    @staticmethod
+    def forward(ctx, iconv4, dec, *params):
+        blocks = dec._daspp_blocks()
+        B, nf, h, w = iconv4.shape
+        half, n = nf // 2, B * h * w
+        CT = nf + 5 * half
+        dev = iconv4.device
+        x4 = _nhwc_view(iconv4.contiguous(memory_format=torch.channels_last))
+        buf = torch.empty((B, h, w, CT), dtype=torch.float32, device=dev)          # [iconv4 | d3 | d6 | d12 | d18 | d24]
+        mean, var = torch.empty(CT, dtype=torch.float32, device=dev), torch.empty(CT, dtype=torch.float32, device=dev)
+        ops.affine_act(x4, dst=buf[..., :nf])
+        ops.bn_moments(x4, mean[:nf], var[:nf])
+
+        def fold(bn, m, v):
+            return ops.bn_fold(m, v, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.momentum, bn.eps, n)
+
+        vec4 = fold(dec.bn4, mean[:nf], var[:nf])
+        saved = [x4, buf, *vec4]
+        for k, blk in enumerate(blocks):
+            ck = nf + half * k
+            if k == 0:
+                vk = vec4
+                xk = ops.affine_act(x4, scale=vec4[0], shift=vec4[1], act=ops.ACT_RELU)              # relu(iconv4_bn)
+            else:
+                vk = fold(blk.bn_first, mean[:ck], var[:ck])
+                xk = ops.affine_act(buf[..., :ck], scale=vk[0], shift=vk[1], act=ops.ACT_RELU)       # relu(BN(concat4_k)), contiguous
+            t = _conv_nhwc(xk, blk.conv1)
+            m2, v2 = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
+            ops.bn_moments(t, m2, v2)
+            v2k = fold(blk.bn2, m2, v2)
+            r2 = ops.affine_act(t, scale=v2k[0], shift=v2k[1], act=ops.ACT_RELU)
+            d = _conv_nhwc(r2, blk.conv2)
+            ops.affine_act(d, dst=buf[..., ck:ck + half])
+            if k + 1 < len(blocks):
+                ops.bn_moments(d, mean[ck:ck + half], var[ck:ck + half])
+            saved += [xk, t, r2, *v2k] + ([] if k == 0 else list(vk))
+        ops.affine_act(x4, dst=buf[..., :nf], scale=vec4[0], shift=vec4[1])                          # concat4_daspp starts with iconv4_bn (:75)
+        ctx.save_for_backward(*saved)
+        ctx.dec = dec
+        return buf
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        dec = ctx.dec
+        blocks = dec._daspp_blocks()
+        sv = list(ctx.saved_tensors)
+        x4, buf, vec4 = sv[0], sv[1], tuple(sv[2:6])
+        pos = 6
+        per_block = []
+        for k in range(len(blocks)):
+            xk, t, r2 = sv[pos:pos + 3]
+            v2k = tuple(sv[pos + 3:pos + 7])
+            pos += 7
+            vk = vec4
+            if k > 0:
+                vk = tuple(sv[pos:pos + 4])
+                pos += 4
+            per_block.append((xk, t, r2, v2k, vk))
+        B, h, w, CT = buf.shape
+        nf = x4.shape[-1]
+        half = nf // 2
+        dev = buf.device
+        gbuf = g_out.contiguous().clone()              # gradient of concat4_daspp; the blocks' contributions are added into its slices
+        g4 = torch.empty_like(x4)                      # d loss / d iconv4
+        g4_written = False
+        grads = {}
+
+        def vec_slice(v, a, b):
+            return tuple(u[a:b] for u in v)
+
+        for k in range(len(blocks) - 1, -1, -1):
+            blk = blocks[k]
+            xk, t, r2, v2k, vk = per_block[k]
+            ck = nf + half * k
+            g_d = ops.affine_act(gbuf[..., ck:ck + half])                               # contiguous copy of the block's complete gradient
+            g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2)
+            gg2, gb2 = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
+            g_t = ops.bn_act_backward(g_r2, t, v2k, gg2, gb2, torch.empty_like(t))
+            grads[blk.bn2.weight], grads[blk.bn2.bias] = gg2, gb2
+            g_xk, grads[blk.conv1.weight] = _conv_backward(g_t, xk, blk.conv1)
+            if k == 0:
+                # iconv4_bn feeds relu -> conv1 of daspp_3 AND concat4_daspp directly (:58-59, :75): one BatchNormalization backward
+                gg, gb = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
+                ops.bn_act_backward(g_xk, x4, vec4, gg, gb, g4, accumulate=g4_written, g2=gbuf[..., :nf])
+                grads[dec.bn4.weight], grads[dec.bn4.bias] = gg, gb
+            else:
+                gg, gb = torch.empty(ck, dtype=torch.float32, device=dev), torch.empty(ck, dtype=torch.float32, device=dev)
+                ops.bn_act_backward(g_xk[..., :nf], x4, vec_slice(vk, 0, nf), gg[:nf], gb[:nf], g4, accumulate=g4_written)
+                g4_written = True
+                ops.bn_act_backward(g_xk[..., nf:], buf[..., nf:ck], vec_slice(vk, nf, ck), gg[nf:], gb[nf:], gbuf[..., nf:ck], accumulate=True)
+                grads[blk.bn_first.weight], grads[blk.bn_first.bias] = gg, gb
+        g_iconv4 = _to_nchw(g4) if ctx.needs_input_grad[0] else None
+        return (g_iconv4, None) + tuple(grads[p] for p in dec._daspp_params())
+
+
 class BtsDecoder(nn.Module):
     """The decoder graph of bts_decoder.py with the three LPG heads fused.  Sub-modules are created in
     the reference's layer-creation order, so `conv_kernels()` lines up with a Keras weight list."""
@@ -167,6 +285,7 @@ class BtsDecoder(nn.Module):
         self.iconv1 = _conv(nf + 3, nf)
         self.depth_conv = _conv(nf, 1)
         self.intermediates = {}
+        self.fused_training_glue = True         # training: DenseASPP BatchNorm / ReLU / concat glue on the hand-written kernels
         self.tensor_core_iconv1 = True          # inference: iconv1 on the tcgen05 kernel (TF32) while torch's cuDNN TF32 switch is on
         self._loss_ws = None
         self.reset_parameters_keras()
@@ -243,7 +362,29 @@ class BtsDecoder(nn.Module):
         ops.affine_act(buf[..., :nf], dst=buf[..., :nf], scale=s4_, shift=t4_)                       # concat4_daspp starts with iconv4_bn (:75)
         return F.elu(self.daspp_feat(_to_nchw(buf)))
 
+    def _daspp_blocks(self):
+        return (self.daspp_3, self.daspp_6, self.daspp_12, self.daspp_18, self.daspp_24)
+
+    def _daspp_bns(self):
+        out = [self.bn4]
+        for blk in self._daspp_blocks():
+            out += ([blk.bn_first] if blk.bn_first is not None else []) + [blk.bn2]
+        return out
+
+    def _daspp_params(self):
+        """Parameters DenseAsppTrainFunction differentiates, in the order it returns their gradients."""
+        out = [self.bn4.weight, self.bn4.bias]
+        for blk in self._daspp_blocks():
+            if blk.bn_first is not None:
+                out += [blk.bn_first.weight, blk.bn_first.bias]
+            out += [blk.conv1.weight, blk.bn2.weight, blk.bn2.bias, blk.conv2.weight]
+        return out
+
     def _daspp(self, iconv4):
+        if self.training and self.fused_training_glue and ops.bn_slices_supported(iconv4.shape[1], iconv4.dtype):
+            buf = DenseAsppTrainFunction.apply(iconv4, self, *self._daspp_params())
+            torch._foreach_add_([bn.num_batches_tracked for bn in self._daspp_bns()], 1)
+            return F.elu(self.daspp_feat(_to_nchw(buf)))
         iconv4_bn = self.bn4(iconv4)
         d3 = self.daspp_3(iconv4_bn)
         c2 = torch.cat([iconv4, d3], 1)

@@ -636,6 +636,56 @@ def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
 
 
 # ---------------------------------------------------------------------------------------------
+# training-mode BatchNormalization (+ ReLU) over channel slices (DenseASPP glue, bts_decoder.py:46-54, :61-76); csrc/bnrelu_kernels.cuh
+# ---------------------------------------------------------------------------------------------
+def bn_slices_supported(nf, dtype):
+    """DenseASPP widths the training glue takes: float32, nf a multiple of 8 (half-width pieces of whole 16-byte vectors), slices of
+    at most 1024 channels (the widest is 2 * nf)."""
+    return dtype == torch.float32 and nf % 8 == 0 and 8 <= nf <= 512
+
+
+def _bn_ws(device, channels):
+    lib = load()
+    ws = _workspace(device, int(lib.btslpg_bn_workspace_bytes(int(channels))))
+    return ctypes.c_void_p(ws.data_ptr()), ws.numel()
+
+
+def bn_moments(x, mean, var):
+    """Per-channel mean and biased variance of the (B,H,W,C) channel slice `x` into the float32 [C] vectors `mean`, `var`."""
+    lib = load()
+    wp, wn = _bn_ws(x.device, x.shape[-1])
+    rx, rm, rv = as_ref(x), as_ref(mean), as_ref(var)
+    check(lib.btslpg_bn_moments(rx.ptr, rm.ptr, rv.ptr, wp, wn, current_stream_ptr(x.device)))
+
+
+def bn_fold(mean, var, gamma, beta, running_mean, running_var, momentum, eps, count):
+    """Batch moments + gamma / beta -> (scale, shift, mean, rstd), the vectors the forward (affine_act) and the backward take; updates
+    the moving averages in place when given."""
+    lib = load()
+    scale, shift, rstd = (torch.empty_like(mean) for _ in range(3))
+    refs = [as_ref(t) for t in (mean, var, gamma, beta, running_mean, running_var, scale, shift, rstd)]
+    check(lib.btslpg_bn_fold(refs[0].ptr, refs[1].ptr, refs[2].ptr, refs[3].ptr, ptr_or_null(refs[4]), ptr_or_null(refs[5]), float(momentum),
+                             float(eps), int(count), refs[6].ptr, refs[7].ptr, refs[8].ptr, current_stream_ptr(mean.device)))
+    return scale, shift, mean, rstd
+
+
+def bn_act_backward(g, x, vecs, g_gamma, g_beta, dst, relu=True, accumulate=False, g2=None):
+    """Backward of y = act(x * scale + shift) with batch statistics, over one channel slice: fills g_gamma / g_beta [C] and writes or
+    adds d loss / d x into `dst`.  vecs = (scale, shift, mean, rstd) slices; g2: gradient reaching the normalised value directly."""
+    lib = load()
+    wp, wn = _bn_ws(g.device, g.shape[-1])
+    rg, rh, rx, rd = as_ref(g), as_ref(g2), as_ref(x), as_ref(dst)
+    rv = [as_ref(v) for v in vecs]
+    rgg, rgb = as_ref(g_gamma), as_ref(g_beta)
+    st = current_stream_ptr(g.device)
+    check(lib.btslpg_bn_act_backward_stats(rg.ptr, ptr_or_null(rh), rx.ptr, rv[0].ptr, rv[1].ptr, rv[2].ptr, rv[3].ptr, 1 if relu else 0,
+                                           rgg.ptr, rgb.ptr, wp, wn, st))
+    check(lib.btslpg_bn_act_backward(rg.ptr, ptr_or_null(rh), rx.ptr, rv[0].ptr, rv[1].ptr, rv[2].ptr, rv[3].ptr, rgg.ptr, rgb.ptr,
+                                     1 if relu else 0, rd.ptr, 1 if accumulate else 0, st))
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------
 # last convolution Conv2D(1, 3x3, 'same'): hand-written forward (with the neighbouring ELU / sigmoid folded in) and backward
 # ---------------------------------------------------------------------------------------------
 def depthconv_backward(x, kernel9c, g_out, need_g_x=True, need_g_kernel=True, act_in=False):

@@ -278,6 +278,34 @@ BTSLPG_API int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor
                                          void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * TRAINING-mode BatchNormalization (+ ReLU) over channel slices of NHWC buffers -- the glue of the DenseASPP
+ * (bts_decoder.py:46-54 dense_aspp_block, :61-76) when is_training: [Concatenate ->] BatchNormalization(training) -> ReLU in front of
+ * every convolution, on one (B,h,w,896) buffer that the blocks append to.  Batch statistics are per channel, so the moments of a
+ * channel are taken ONCE when it is appended and shared by every later BatchNormalization over a concat that contains it.
+ *   btslpg_bn_moments             x (B,H,W,C) channel slice -> mean[C], var[C] (biased), float32
+ *   btslpg_bn_fold                moments + gamma / beta -> scale = gamma * rstd, shift = beta - mean * scale, rstd = 1/sqrt(var + eps);
+ *                                 updates the moving averages when given (torch momentum = 1 - Keras' 0.99; unbiased variance,
+ *                                 `count` values per channel).  The forward is then btslpg_affine_act(src, scale, shift, ReLU, dst).
+ *   btslpg_bn_act_backward_stats  y = act(x * scale + shift); gm = g * [y > 0] (relu) (+ g2, nullable: a gradient that reaches the
+ *                                 NORMALISED value directly): g_beta = sum gm, g_gamma = sum gm * xhat, xhat = (x - mean) * rstd
+ *   btslpg_bn_act_backward        dst (+)= scale * (gm - g_beta / n - xhat * g_gamma / n): d loss / d x, written or ACCUMULATED into a
+ *                                 slice of the shared gradient buffer (the concat's backward is that accumulation)
+ * Every tensor argument is float32, channel stride 1, uniformly strided 16-byte aligned pixels, C a multiple of 4 in [4, 1024];
+ * per-channel vectors are contiguous float32 [C], 16-byte aligned.  Deterministic (fixed-order sums, no atomics).
+ * workspace: btslpg_bn_workspace_bytes(C) bytes, 16-byte aligned, no initialisation needed.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API int btslpg_bn_moments(const BtsTensor *x, BtsTensor *mean, BtsTensor *var, void *workspace, size_t workspace_bytes, void *stream);
+BTSLPG_API int btslpg_bn_fold(const BtsTensor *mean, const BtsTensor *var, const BtsTensor *gamma, const BtsTensor *beta,
+                              BtsTensor *running_mean, BtsTensor *running_var, float momentum, float eps, int64_t count, BtsTensor *scale,
+                              BtsTensor *shift, BtsTensor *rstd, void *stream);
+BTSLPG_API int btslpg_bn_act_backward_stats(const BtsTensor *g, const BtsTensor *g2, const BtsTensor *x, const BtsTensor *scale,
+                                            const BtsTensor *shift, const BtsTensor *mean, const BtsTensor *rstd, int relu,
+                                            BtsTensor *g_gamma, BtsTensor *g_beta, void *workspace, size_t workspace_bytes, void *stream);
+BTSLPG_API int btslpg_bn_act_backward(const BtsTensor *g, const BtsTensor *g2, const BtsTensor *x, const BtsTensor *scale,
+                                      const BtsTensor *shift, const BtsTensor *mean, const BtsTensor *rstd, const BtsTensor *g_gamma,
+                                      const BtsTensor *g_beta, int relu, BtsTensor *dst, int accumulate, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the
  * `layers.UpSampling2D(size=2, interpolation='nearest')` in front of every upconv of the decoder
  * (bts_decoder.py:31, :38, :97): out[b, y, x, :] = in[b, y/2, x/2, :].
