@@ -753,6 +753,19 @@ def depth_conv(x_nhwc, weight, act_in=False):
 # ---------------------------------------------------------------------------------------------
 # iconv1 as a tcgen05 implicit GEMM over the concat's sources (inference)
 # ---------------------------------------------------------------------------------------------
+def conv3x3_wgrad(x, g, out=None):
+    """d kernel (HWIO, float32 [3,3,Cin,Cout]) of a stride-1 'same' 3x3 convolution from its NHWC input `x` and the gradient `g` of
+    its output, on the tcgen05 tensor cores (TF32 operands, float32 accumulation; csrc/wgrad_kernels.cuh)."""
+    lib = load()
+    cin, cout = x.shape[-1], g.shape[-1]
+    if out is None:
+        out = torch.empty((3, 3, cin, cout), dtype=torch.float32, device=x.device)
+    ws = _workspace(x.device, int(lib.btslpg_conv3x3_wgrad_workspace_bytes(int(cin), int(cout))))
+    rx, rg, ro = as_ref(x), as_ref(g), as_ref(out)
+    check(lib.btslpg_conv3x3_wgrad(rx.ptr, rg.ptr, ro.ptr, ctypes.c_void_p(ws.data_ptr()), ws.numel(), current_stream_ptr(x.device)))
+    return out
+
+
 def kernel_hwio(weight):
     """torch OIHW (O,I,3,3) conv weight -> float32 Keras HWIO (3,3,I,O) contiguous."""
     return weight.detach().permute(2, 3, 1, 0).float().contiguous()

@@ -278,6 +278,21 @@ BTSLPG_API int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor
                                          void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weight gradient of a full-resolution 3x3 convolution (stride 1, padding='same', no bias) on the tcgen05 tensor cores
+ *  -- the d kernel of upconv1 / iconv1 (bts_decoder.py:98, :100), the part of their backward the library runs at 4-9
+ * times its traffic floor:
+ *     g_kernel[ky][kx][ci][co] = sum_{b,y,x} x[b, y+ky-1, x+kx-1, ci] * g[b, y, x, co]          (x = 0 outside the image)
+ *   x         (B,H,W,Cin)  float32 contiguous NHWC, Cin a multiple of 4 in [4, 64]: the convolution's INPUT
+ *   g         (B,H,W,Cout) float32 contiguous NHWC, Cout a multiple of 4 in [4, 32]: gradient of its (linear) output
+ *   g_kernel  float32 [3][3][Cin][Cout], the Keras HWIO layout of layer.kernel
+ * TF32 operands (the tensor core ignores the low 13 mantissa bits of the float32 inputs), float32 accumulation; deterministic
+ * (per-CTA partials summed in a fixed order).  workspace: btslpg_conv3x3_wgrad_workspace_bytes(Cin, Cout) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+BTSLPG_API size_t btslpg_conv3x3_wgrad_workspace_bytes(int cin, int cout);
+BTSLPG_API int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_kernel, void *workspace, size_t workspace_bytes,
+                                    void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * TRAINING-mode BatchNormalization (+ ReLU) over channel slices of NHWC buffers -- the glue of the DenseASPP
  * (bts_decoder.py:46-54 dense_aspp_block, :61-76) when is_training: [Concatenate ->] BatchNormalization(training) -> ReLU in front of
  * every convolution, on one (B,h,w,896) buffer that the blocks append to.  Batch statistics are per channel, so the moments of a

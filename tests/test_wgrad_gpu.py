@@ -1,0 +1,77 @@
+"""GPU parity of the tcgen05 weight gradient of the full-resolution 3x3 convolutions (bts_decoder.py:98, :100) against the float64
+definition (and, structurally, against one-hot inputs that isolate single taps)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from bts_fully_tf_b200 import ops
+
+import os
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True, params=[0, 1], ids=["one-copy", "three-copies"])
+def _variant(request):
+    """Both operand-staging variants of the kernel (tuning key 11)."""
+    ops.set_tuning(11, request.param)
+    yield
+    ops.set_tuning(11, 0)
+
+
+def _ref_wgrad(x, g):
+    """HWIO d kernel in float64: conv2d's own autograd on the CPU."""
+    xd = x.double().permute(0, 3, 1, 2).contiguous()
+    w = torch.zeros(g.shape[-1], x.shape[-1], 3, 3, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xd, w, padding=1)
+    y.backward(g.double().permute(0, 3, 1, 2).contiguous())
+    return w.grad.permute(2, 3, 1, 0).contiguous()           # OIHW -> HWIO
+
+
+def _tf32(t):
+    """Truncate to TF32 (what the tensor core reads)."""
+    return (t.view(torch.int32) & -8192).view(torch.float32)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 32, 32), (2, 11, 37, 32, 16), (1, 16, 48, 20, 16), (2, 9, 33, 64, 32), (1, 24, 40, 36, 32),
+                                            (3, 5, 7, 8, 4), (1, 1, 1, 4, 4)])
+def test_wgrad_matches_float64_definition(B, H, W, Cin, Cout):
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, H, W, Cin, generator=gen)
+    g = torch.randn(B, H, W, Cout, generator=gen)
+    out = ops.conv3x3_wgrad(x.to(DEV), g.to(DEV)).cpu()
+    exact = _ref_wgrad(_tf32(x), _tf32(g))                   # same operand bits: only the float32 accumulation order differs
+    scale = float(exact.abs().max())
+    assert float((out.double() - exact).abs().max()) <= 2e-5 * scale + 1e-6
+    full = _ref_wgrad(x, g)                                  # against untruncated operands: TF32's 2^-10 per operand
+    assert float((out.double() - full).abs().max()) <= 3e-3 * float(full.abs().max())
+
+
+def test_wgrad_one_hot_isolates_taps():
+    """x one-hot at (y0, x0, ci), g one-hot at (y1, x1, co): the only non-zero entry is [y0 - y1 + 1][x0 - x1 + 1][ci][co]."""
+    B, H, W, Cin, Cout = 1, 12, 20, 32, 16
+    for (y0, x0, ci), (y1, x1, co) in [((3, 4, 5), (3, 4, 6)), ((0, 0, 31), (1, 1, 0)), ((11, 19, 0), (10, 18, 15)), ((5, 16, 7), (6, 15, 3)),
+                                       ((7, 8, 9), (7, 10, 2))]:
+        x = torch.zeros(B, H, W, Cin)
+        g = torch.zeros(B, H, W, Cout)
+        x[0, y0, x0, ci] = 2.0
+        g[0, y1, x1, co] = 3.0
+        out = ops.conv3x3_wgrad(x.to(DEV), g.to(DEV)).cpu()
+        want = torch.zeros(3, 3, Cin, Cout)
+        ky, kx = y0 - y1 + 1, x0 - x1 + 1
+        if 0 <= ky < 3 and 0 <= kx < 3:
+            want[ky, kx, ci, co] = 6.0
+        assert torch.equal(out, want), ((y0, x0, ci), (y1, x1, co), out.nonzero().tolist())
+
+
+def test_wgrad_is_deterministic_and_rejects_bad_shapes():
+    x = torch.randn(2, 40, 64, 32, device=DEV)
+    g = torch.randn(2, 40, 64, 16, device=DEV)
+    a, b = ops.conv3x3_wgrad(x, g), ops.conv3x3_wgrad(x, g)
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        ops.conv3x3_wgrad(torch.randn(1, 4, 4, 66, device=DEV), torch.randn(1, 4, 4, 16, device=DEV))
+    with pytest.raises(ValueError):
+        ops.conv3x3_wgrad(torch.randn(1, 4, 4, 32, device=DEV), torch.randn(1, 4, 5, 16, device=DEV))
