@@ -10,7 +10,6 @@ std::atomic<uint64_t> g_launches{0};   // process-wide: autograd runs backward o
 std::atomic<int> g_fwd_threads{0}, g_bwd_threads{0};
 std::atomic<int> g_tune_head_impl{0};        // fused head forward: 0 = TMA-staged (default), 1 = register-staged loads
 std::atomic<int> g_tune_concat_impl{0};      // concat forward: 0 = staged kernel (default), 1 = chunked kernel where it applies (experiment)
-std::atomic<int> g_tune_wgrad_impl{0};       // 3x3 weight gradient: 0 = one gradient copy, kernel columns as shifted N blocks (default), 1 = three shifted copies
 std::atomic<int> g_tune_depthconv_impl{0};   // last-convolution forward: 0 = tensor-core phase 1 (default), 1 = FP32-pipe phase 1
 
 int fail(int code, const char *fmt, ...) {

@@ -17,7 +17,7 @@ extern thread_local char tl_error[512];
 extern thread_local char tl_kernel[128];
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_fwd_threads, g_bwd_threads;
-extern std::atomic<int> g_tune_head_impl, g_tune_concat_impl, g_tune_depthconv_impl, g_tune_wgrad_impl;
+extern std::atomic<int> g_tune_head_impl, g_tune_concat_impl, g_tune_depthconv_impl;
 
 int fail(int code, const char *fmt, ...);
 

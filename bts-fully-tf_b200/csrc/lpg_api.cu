@@ -261,7 +261,6 @@ void btslpg_set_tuning(int key, int value) {
         case 7: g_tune_head_impl.store(value); break; // fused head forward: 0 TMA-staged, 1 register-staged
         case 10: g_tune_concat_impl.store(value); break;     // concat forward: 0 staged (default), 1 chunked where it applies
         case 9: g_tune_depthconv_impl.store(value); break;   // last-convolution forward: 0 tensor-core phase 1 (3xTF32), 1 FP32 pipe
-        case 11: g_tune_wgrad_impl.store(value); break;      // 3x3 weight gradient: 0 one gradient copy + shifted N blocks, 1 three shifted copies
         case 6: g_tune_r2_px.store(value); break;     // float32 r=2: coarse pixels per thread (2 or 4)
         default: break;
     }

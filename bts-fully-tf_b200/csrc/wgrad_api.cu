@@ -58,8 +58,8 @@ int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_ke
     if (xv.B != gv.B || xv.H != gv.H || xv.W != gv.W) return fail(BTSLPG_ESHAPE, "g: expected (B,H,W,Cout) over the same pixels as x");
     if (xv.dev != gv.dev) return fail(BTSLPG_EDEVICE, "g: on a different device than x");
     const int64_t Cin = xv.C, Cout = gv.C;
-    if (Cin < 4 || Cin > 64 || Cin % 4) return fail(BTSLPG_ESHAPE, "x: %lld channels; a multiple of 4 in [4, 64] is required", (long long)Cin);
-    if (Cout < 4 || Cout > 32 || Cout % 4) return fail(BTSLPG_ESHAPE, "g: %lld channels; a multiple of 4 in [4, 32] is required", (long long)Cout);
+    if (Cin < 4 || Cin > 256 || Cin % 4) return fail(BTSLPG_ESHAPE, "x: %lld channels; a multiple of 4 in [4, 256] is required", (long long)Cin);
+    if (Cout < 4 || Cout > 128 || Cout % 4) return fail(BTSLPG_ESHAPE, "g: %lld channels; a multiple of 4 in [4, 128] is required", (long long)Cout);
     float *out = nullptr;
     if (int e = parse_f32_vec(g_kernel, "g_kernel", 9 * Cin * Cout, xv.dev, out)) return e;
     if (xv.B * xv.H * xv.W == 0) return fail(BTSLPG_ESHAPE, "x: empty tensor");
@@ -69,11 +69,10 @@ int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_ke
 
     DeviceGuard guard(xv.dev);
     if (guard.err != cudaSuccess) return fail(BTSLPG_ECUDA, "cudaSetDevice(%d): %s", xv.dev, cudaGetErrorString(guard.err));
-    const bool shift = g_tune_wgrad_impl.load(std::memory_order_relaxed) == 0;
-    const int T = (shift && Cin <= 32) ? 16 : 8, gw = shift ? kWgTW + 2 : kWgTW;      // WgradCfg::kT, kGW
+    const int T = (Cin <= 32 && Cout <= 32) ? 16 : 8;                     // WgradCfg::kT of the pass shapes used below
     CUtensorMap map_x, map_g;
     if (int e = make_map(xv, "x", kWgTW, T + 2, map_x)) return e;
-    if (int e = make_map(gv, "g", gw, T, map_g)) return e;
+    if (int e = make_map(gv, "g", kWgTW + 2, T, map_g)) return e;
 
     WgradParams p;
     p.partial = static_cast<float *>(workspace);
@@ -95,24 +94,36 @@ int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_ke
     });
     uint32_t blocks = p.items < (uint32_t)sms ? p.items : (uint32_t)sms;
     if (blocks > (uint32_t)kWgMaxBlocks) blocks = kWgMaxBlocks;
-    auto go = [&](auto cinb_tag, auto shift_tag) -> int {
-        constexpr int CINB = decltype(cinb_tag)::value;
-        constexpr bool SHIFT = decltype(shift_tag)::value != 0;
-        constexpr int smem = WgradCfg<CINB, SHIFT>::kSmemBytes;
+    auto go = [&](auto cinb_tag, auto coutb_tag, auto t_tag) -> int {
+        constexpr int CINB = decltype(cinb_tag)::value, COUTB = decltype(coutb_tag)::value, TT = decltype(t_tag)::value;
+        constexpr int smem = WgradCfg<CINB, COUTB, TT>::kSmemBytes;
         static PerDevice per_dev;
         per_dev.get([&] {
-            cudaFuncSetAttribute(conv3x3_wgrad_kernel<CINB, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(conv3x3_wgrad_kernel<CINB, COUTB, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             return 1;
         });
-        conv3x3_wgrad_kernel<CINB, SHIFT><<<blocks, kWgThreads, smem, st>>>(map_x, map_g, p);
-        if (int e = check_launch("btslpg_conv3x3_wgrad")) return e;
-        const uint32_t n = (uint32_t)(9 * Cin * Cout);
-        wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.partial, out, n, blocks);
-        snprintf(tl_kernel, sizeof(tl_kernel), "conv3x3_wgrad_tcgen05<f32/tf32,Cin%d,Cout%d,%s>", p.Cin, p.Cout, SHIFT ? "one copy" : "three copies");
+        conv3x3_wgrad_kernel<CINB, COUTB, TT><<<blocks, kWgThreads, smem, st>>>(map_x, map_g, p);
         return check_launch("btslpg_conv3x3_wgrad");
     };
-    if (shift) return Cin <= 32 ? go(IntC<1>{}, IntC<1>{}) : go(IntC<2>{}, IntC<1>{});
-    return Cin <= 32 ? go(IntC<1>{}, IntC<0>{}) : go(IntC<2>{}, IntC<0>{});
+    // channels in passes of up to 64 x 64 (two 32-channel blocks each: the accumulators of a pass must fit the 512 TMEM columns; every
+    // pass stages its own operands, so an operand with more than 64 channels makes the other one be read again)
+    const bool small = Cin <= 32 && Cout <= 32;
+    for (int ci0 = 0; ci0 < (int)Cin; ci0 += 64)
+        for (int co0 = 0; co0 < (int)Cout; co0 += 64) {
+            p.ci0 = ci0; p.ci_n = (int)Cin - ci0 < 64 ? (int)Cin - ci0 : 64;
+            p.co0 = co0; p.co_n = (int)Cout - co0 < 64 ? (int)Cout - co0 : 64;
+            // one shape per call (the tensor maps' boxes are per call): 1 x 1 blocks only when both operands are narrow
+            const bool two_in = !small && p.ci_n > 32, two_out = !small && p.co_n > 32;
+            int e;
+            if (small) e = go(IntC<1>{}, IntC<1>{}, IntC<16>{});
+            else if (two_in) e = two_out ? go(IntC<2>{}, IntC<2>{}, IntC<8>{}) : go(IntC<2>{}, IntC<1>{}, IntC<8>{});
+            else e = two_out ? go(IntC<1>{}, IntC<2>{}, IntC<8>{}) : go(IntC<1>{}, IntC<1>{}, IntC<8>{});
+            if (e) return e;
+        }
+    const uint32_t n = (uint32_t)(9 * Cin * Cout);
+    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.partial, out, n, blocks);
+    snprintf(tl_kernel, sizeof(tl_kernel), "conv3x3_wgrad_tcgen05<f32/tf32,Cin%d,Cout%d>", p.Cin, p.Cout);
+    return check_launch("btslpg_conv3x3_wgrad");
 }
 
 }  // extern "C"

@@ -11,8 +11,10 @@
 //   A = activations of FOUR consecutive input rows (CIN <= 32: M = 4 x 32) or two (CIN <= 64: M = 2 x 64), pixels as K: the rows
 //       y-1, y, y+1 that pair with output row y are the kernel rows ky = 0, 1, 2 -- three of the four M blocks of one instruction (the
 //       fourth accumulates a row pairing that is not part of the convolution and is dropped);
-//   B = the gradient of output row y, loaded three times with its columns shifted by kx - 1 (TMA zero-fills outside the image, which
-//       is exactly padding='same').
+//   B = the gradient of output row y, N = 96 = the three kernel columns kx x 32 output channels: the three N blocks are the SAME staged
+//       row started one pixel (128 bytes) apart (descriptor LBO = 128 B), so the gradient is staged once with one halo pixel per side
+//       (TMA zero-fills outside the image, which is exactly padding='same').  Staging three shifted copies instead (one instruction
+//       of N = 32 per kernel column) measured 463 us against 277 us at B = 32, 416x544, 32 -> 16 channels.
 // Both operands are "MN-major" (the channel index is the contiguous one: NHWC as it lies in memory, no transposition anywhere), which
 // for 32-bit operands means the 128-byte-span / 32-byte-atom swizzle: TMA writes the tiles in that pattern (CU_TENSOR_MAP_SWIZZLE_128B_
 // ATOM_32B) and the shared-memory descriptors name it (layout type 1).  One TMA producer thread, one MMA issuer thread, accumulators
@@ -34,27 +36,31 @@ namespace btslpg {
 constexpr int kWgTW = 16;                   // output columns of a work item
 constexpr int kWgThreads = 192;             // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (TMEM lane quarters 2, 3, 0, 1)
 
-// CINB: 32-channel blocks of the input (1: Cin <= 32, 2: Cin <= 64).  SHIFT: the three kernel columns come from ONE copy of the
-// gradient rows, as three N blocks of one instruction that start one pixel (128 bytes) apart; otherwise from three shifted copies.
-template <int CINB, bool SHIFT> struct WgradCfg {
-    static constexpr int kT = (SHIFT && CINB == 1) ? 16 : 8;                   // output rows of a work item
+// CINB / COUTB: 32-channel blocks of the input and of the gradient handled by one pass (<= 64 channels each)
+template <int CINB, int COUTB, int T_> struct WgradCfg {
+    static constexpr int kT = T_;                                              // output rows of a work item (16 when both operands have one block)
     static constexpr int kXTile = kWgTW * 128;                                 // one row of one 32-channel block: 16 pixels x 128 B
     static constexpr int kXBlock = (kT + 3) * kXTile;                          // rows y-1 .. y+T of a block + the row slot the last instruction touches
     static constexpr int kXBytes = CINB * kXBlock;
-    static constexpr int kGW = SHIFT ? kWgTW + 2 : kWgTW;                      // gradient pixels per staged row
+    static constexpr int kGW = kWgTW + 2;                                      // gradient pixels per staged row: one halo pixel on either side
     static constexpr int kGRow = kGW * 128;
-    static constexpr int kGBytes = ((SHIFT ? 1 : 3) * kT * kGRow + 128 * 2 + 1023) / 1024 * 1024;      // + the two pixels the shifted blocks run over
+    static constexpr int kGBlock = (kT * kGRow + 2 * 128 + 1023) / 1024 * 1024;     // + the two pixels the shifted N blocks of the last row run over
+    static constexpr int kGBytes = COUTB * kGBlock;
     static constexpr int kStageBytes = kXBytes + kGBytes;
-    static constexpr int kTxBytes = CINB * (kT + 2) * kXTile + (SHIFT ? 1 : 3) * kT * kGRow;
+    static constexpr int kTxBytes = CINB * (kT + 2) * kXTile + COUTB * kT * kGRow;
     static constexpr int kStages = (220 * 1024) / kStageBytes;
-    static constexpr int kTmemCols = CINB == 1 ? 128 : 256;                    // CINB accumulators of 96 columns (kernel column, co)
+    static constexpr int kAccCols = CINB * COUTB * 96;                         // per (input block, gradient block): 3 kernel columns x 32 channels
+    static constexpr int kTmemCols = kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;      // + alignment slack + barriers
     static_assert(kStages >= 2, "the pipeline needs two stages");
+    static_assert(kAccCols <= 512, "accumulators exceed TMEM");
 };
 
 struct WgradParams {
     float *partial;            // [gridDim.x][9 * Cin][Cout]
-    int B, H, W, Cin, Cout;
+    int B, H, W, Cin, Cout;    // Cout: all gradient channels (row length of the partials)
+    int co0, co_n;             // this pass: gradient channels [co0, co0 + co_n)
+    int ci0, ci_n;             //            input channels [ci0, ci0 + ci_n)
     uint32_t items, bands, ctiles;
     FastDiv div_ct, div_band;
 };
@@ -72,11 +78,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t smem_addr, uint32_t 
            (1ull << 46) | (1ull << 61);
 }
 
-// map_x: boxes of (32 channels, kWgTW pixels, kT + 2 rows); map_g: boxes of (32 channels, kGW pixels, kT rows)
-template <int CINB, bool SHIFT>
+// map_x: boxes of (32 channels, kWgTW pixels, kT + 2 rows); map_g: boxes of (32 channels, kWgTW + 2 pixels, kT rows)
+template <int CINB, int COUTB, int T_>
 __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                                                                       const __grid_constant__ WgradParams prm) {
-    using Cfg = WgradCfg<CINB, SHIFT>;
+    using Cfg = WgradCfg<CINB, COUTB, T_>;
     constexpr int T = Cfg::kT;
     extern __shared__ unsigned char wg_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
     const uint32_t smem_base = smem_u32(smem);
 
     if (warp == 0) {
-        // ================= TMA producer: 1 + CINB (or 3 + CINB) boxes per work item =================
+        // ================= TMA producer: CINB + COUTB boxes per work item =================
         if (lane == 0) {
             uint32_t k = 0;
             for (uint32_t item = blockIdx.x; item < prm.items; item += gridDim.x, ++k) {
@@ -114,20 +120,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
                 const uint32_t xs = smem_base + s * Cfg::kStageBytes, gs = xs + Cfg::kXBytes;
                 mbar_arrive_expect_tx(full + s, Cfg::kTxBytes);
 #pragma unroll
-                for (int c = 0; c < CINB; ++c) tma_load_4d(xs + c * Cfg::kXBlock, &map_x, c * 32, x0, y0 - 1, (int)b, full + s);
-                if (SHIFT) {
-                    tma_load_4d(gs, &map_g, 0, x0 - 1, y0, (int)b, full + s);
-                } else {
+                for (int c = 0; c < CINB; ++c) tma_load_4d(xs + c * Cfg::kXBlock, &map_x, prm.ci0 + c * 32, x0, y0 - 1, (int)b, full + s);
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) tma_load_4d(gs + j * T * Cfg::kGRow, &map_g, 0, x0 - (j - 1), y0, (int)b, full + s);
-                }
+                for (int cb = 0; cb < COUTB; ++cb) tma_load_4d(gs + cb * Cfg::kGBlock, &map_g, prm.co0 + cb * 32, x0 - 1, y0, (int)b, full + s);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // instruction descriptor: D float32, A / B TF32, both MN-major (bits 15, 16), M = 128, N = 96 (SHIFT) or 32
-        constexpr uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
-        constexpr uint32_t idesc = idesc0 | (((SHIFT ? 96u : 32u) >> 3) << 17);
+        // instruction descriptor: D float32, A / B TF32, both MN-major (bits 15, 16), M = 128, N = 96
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
         uint32_t elected;
         asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(elected));
         uint32_t k = 0;
@@ -141,22 +142,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
 #pragma unroll
                     for (int kb = 0; kb < kWgTW / 8; ++kb) {
                         const uint32_t acc = (k | y | kb) != 0;
-                        if (SHIFT) {
-                            // N block n' starts n' pixels further: B[(n', co)][k] = g[x + n' - 1] -> kernel column kx = 2 - n'
-                            const uint64_t bdesc = umma_desc_mn32(gs + y * Cfg::kGRow + kb * 1024, 128, 512);
+#pragma unroll
+                        for (int cb = 0; cb < COUTB; ++cb) {
+                            // N block n' starts n' pixels (n' * 128 bytes) further: B[(n', co)][k] = g[x + n' - 1], kernel column kx = 2 - n'
+                            const uint64_t bdesc = umma_desc_mn32(gs + cb * Cfg::kGBlock + y * Cfg::kGRow + kb * 1024, 128, 512);
 #pragma unroll
                             for (int c = 0; c < CINB; ++c)
-                                umma_tf32(tmem_base + c * 96, umma_desc_mn32(xs + c * Cfg::kXBlock + y * Cfg::kXTile + kb * 1024, Cfg::kXTile, 512), bdesc,
-                                          idesc, acc);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                const uint64_t bdesc = umma_desc_mn32(gs + (j * T + y) * Cfg::kGRow + kb * 1024, Cfg::kGRow, 512);
-#pragma unroll
-                                for (int c = 0; c < CINB; ++c)
-                                    umma_tf32(tmem_base + c * 96 + j * 32, umma_desc_mn32(xs + c * Cfg::kXBlock + y * Cfg::kXTile + kb * 1024, Cfg::kXTile, 512),
-                                              bdesc, idesc, acc);
-                            }
+                                umma_tf32(tmem_base + (c * COUTB + cb) * 96, umma_desc_mn32(xs + c * Cfg::kXBlock + y * Cfg::kXTile + kb * 1024, Cfg::kXTile, 512),
+                                          bdesc, idesc, acc);
                         }
                     }
                 tc_commit(empty + s);
@@ -176,16 +169,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
         for (int c = 0; c < CINB; ++c) {
             const int ci = c * 32 + lane;
 #pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                uint32_t v[32];
-                tmem_ld_row<32>(tmem_base + ((uint32_t)(q * 32) << 16) + c * 96 + n * 32, v);
-                tmem_ld_wait();
-                const int kx = SHIFT ? 2 - n : n;
-                if (q < 3 && ci < prm.Cin) {
-                    float *d = dst0 + ((size_t)(q * 3 + kx) * prm.Cin + ci) * prm.Cout;
-                    for (int co = 0; co < prm.Cout; ++co) d[co] = __uint_as_float(v[co]);
+            for (int cb = 0; cb < COUTB; ++cb)
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    uint32_t v[32];
+                    tmem_ld_row<32>(tmem_base + ((uint32_t)(q * 32) << 16) + (c * COUTB + cb) * 96 + n * 32, v);
+                    tmem_ld_wait();
+                    if (q < 3 && ci < prm.ci_n) {
+                        float *d = dst0 + ((size_t)(q * 3 + (2 - n)) * prm.Cin + prm.ci0 + ci) * prm.Cout + prm.co0 + cb * 32;
+                        const int nco = min(32, prm.co_n - cb * 32);
+                        for (int co = 0; co < nco; ++co) d[co] = __uint_as_float(v[co]);
+                    }
                 }
-            }
         }
         tc_fence_before();
     }

@@ -282,8 +282,9 @@ BTSLPG_API int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor
  *  -- the d kernel of upconv1 / iconv1 (bts_decoder.py:98, :100), the part of their backward the library runs at 4-9
  * times its traffic floor:
  *     g_kernel[ky][kx][ci][co] = sum_{b,y,x} x[b, y+ky-1, x+kx-1, ci] * g[b, y, x, co]          (x = 0 outside the image)
- *   x         (B,H,W,Cin)  float32 contiguous NHWC, Cin a multiple of 4 in [4, 64]: the convolution's INPUT
- *   g         (B,H,W,Cout) float32 contiguous NHWC, Cout a multiple of 4 in [4, 32]: gradient of its (linear) output
+ *   x         (B,H,W,Cin)  float32 contiguous NHWC, Cin a multiple of 4 in [4, 256]: the convolution's INPUT
+ *   g         (B,H,W,Cout) float32 contiguous NHWC, Cout a multiple of 4 in [4, 128]: gradient of its (linear) output
+ *             (channels beyond 64 on either side are handled in passes of 64 x 64 that stage their operands again)
  *   g_kernel  float32 [3][3][Cin][Cout], the Keras HWIO layout of layer.kernel
  * TF32 operands (the tensor core ignores the low 13 mantissa bits of the float32 inputs), float32 accumulation; deterministic
  * (per-CTA partials summed in a fixed order).  workspace: btslpg_conv3x3_wgrad_workspace_bytes(Cin, Cout) bytes, 16-byte aligned.

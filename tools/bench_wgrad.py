@@ -22,6 +22,14 @@ CASES = [  # name, B, H, W, Cin, Cout
     ("cfg4 upconv1 (densenet161 KITTI 352x1216)", 32, 352, 1216, 64, 32),
     ("cfg4 iconv1", 32, 352, 1216, 36, 32),
     ("cfg5 at per-GPU batch 4, upconv1", 4, 416, 544, 32, 16),
+    ("cfg5 upconv1 as sub-pixel conv on H/2 (32 -> 4x16)", 32, 208, 272, 32, 64),
+    ("cfg4 upconv1 as sub-pixel conv on H/2 (64 -> 4x32)", 32, 176, 608, 64, 128),
+    ("cfg5 conv_block 2 upconv on H/2 (64 -> 32)", 32, 208, 272, 64, 32),
+    ("cfg5 conv_block 2 iconv on H/2 (100 -> 32)", 32, 208, 272, 100, 32),
+    ("cfg5 conv_block 3 upconv on H/4 (64 -> 64)", 32, 104, 136, 64, 64),
+    ("cfg4 conv_block 2 upconv on H/2 (128 -> 64)", 32, 176, 608, 128, 64),
+    ("cfg4 conv_block 2 iconv on H/2 (164 -> 64)", 32, 176, 608, 164, 64),
+    ("cfg4 conv_block 3 upconv on H/4 (128 -> 128)", 32, 88, 304, 128, 128),
 ]
 
 
@@ -60,6 +68,4 @@ def collect(device=None, library=True):
 
 
 if __name__ == "__main__":
-    if os.environ.get("BTSLPG_WGRAD_IMPL"):
-        ops.set_tuning(11, int(os.environ["BTSLPG_WGRAD_IMPL"]))
     print(json.dumps(collect(library="--no-library" not in sys.argv)))
