@@ -50,10 +50,54 @@ def _to_nchw(x_nhwc):
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+TENSOR_CORE_WGRAD = True     # training: d kernel of the 3x3 convolutions with few channels on ops.conv3x3_wgrad (module-wide switch)
+
+
+class Conv3x3Function(torch.autograd.Function):
+    """Conv2D(3x3, stride 1, padding='same', no bias): forward and d input from the library, d kernel from the tcgen05 kernel
+    (ops.conv3x3_wgrad) -- the library's weight-gradient kernels run at 2-8 times its time when the output has few channels and the
+    reduction runs over millions of pixels (profiles/r02_wgrad_tcgen05.json)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return F.conv2d(x, weight, None, 1, 1, 1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous(memory_format=torch.channels_last)
+        g_x = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_x = torch.ops.aten.convolution_backward(g, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            hwio = ops.conv3x3_wgrad(_nhwc_view(x.contiguous(memory_format=torch.channels_last)), _nhwc_view(g))
+            g_w = hwio.permute(3, 2, 0, 1)                                   # HWIO -> OIHW (a view; AccumulateGrad adds it into .grad)
+        return g_x, g_w
+
+
+def _tc_wgrad_applies(x, weight):
+    """TF32 like the library kernel it replaces (so only while torch's own cuDNN TF32 switch is on); channel counts the kernel takes and
+    at which it measured faster than the library (Cin * Cout <= 12288: not 128 x 128), enough pixels to fill the machine."""
+    cout, cin, kh, kw = weight.shape
+    return (TENSOR_CORE_WGRAD and torch.is_grad_enabled() and weight.requires_grad and x.is_cuda and x.dtype == torch.float32
+            and torch.backends.cudnn.allow_tf32 and (kh, kw) == (3, 3) and cin % 4 == 0 and cout % 4 == 0 and cin <= 256 and cout <= 128
+            and cin * cout <= 12288 and x.shape[0] * x.shape[2] * x.shape[3] >= 32768)
+
+
+def _conv3x3(x_nchw, weight):
+    if _tc_wgrad_applies(x_nchw, weight):
+        return Conv3x3Function.apply(x_nchw, weight)
+    return F.conv2d(x_nchw, weight, None, 1, 1, 1)
+
+
 def _conv_padded_input(conv, x_nchw, pad):
     """conv(x) for an input that carries `pad` extra zero channels: the kernel gets matching zero input channels
     (identical result; the gradient of the padding is dropped by autograd's slice)."""
     w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad)) if pad else conv.weight
+    if conv.kernel_size == (3, 3) and conv.dilation == (1, 1) and conv.stride == (1, 1) and conv.padding == (1, 1):
+        return _conv3x3(x_nchw, w)
     return F.conv2d(x_nchw, w, None, conv.stride, conv.padding, conv.dilation)
 
 
@@ -92,7 +136,7 @@ class _ConvBlock(nn.Module):
             cat = ops.concat_forward(_nhwc_view(up.contiguous(memory_format=torch.channels_last)), planes, skip_nhwc.contiguous(), act=True,
                                      pad=self.pad, scale=scale, shift=shift, a_subpixel=self.subpixel_inference)
             return F.elu(_conv_padded_input(self.iconv, _to_nchw(cat), self.pad))
-        raw = self.upconv(_upsample2x(x))
+        raw = _conv3x3(_upsample2x(x), self.upconv.weight)
         nf = raw.shape[1]
         if self.training and self.fused_training_glue and ops.bn_glue_supported(nf, nf + skip_nhwc.shape[-1] + len(planes) + self.pad, raw.dtype):
             # training: ELU + BatchNormalization (batch statistics, moving averages) + concat as a statistics pass and ONE fused pass,
@@ -426,7 +470,7 @@ class BtsDecoder(nn.Module):
             return ops.depthconv_forward(x, ops.kernel9c(self.depth_conv.weight), act_in=True,
                                          sigmoid_scale=None if return_logit else self.max_depth)
         if nf1 % 4 == 0:
-            up4 = F.conv2d(iconv2, ops.subpixel_kernel(self.upconv1.weight), padding=1)       # (B, 4*nf1, H/2, W/2)
+            up4 = _conv3x3(iconv2, ops.subpixel_kernel(self.upconv1.weight))                  # (B, 4*nf1, H/2, W/2)
             up4_nhwc = _nhwc_view(up4.contiguous(memory_format=torch.channels_last))
             concat1 = _to_nchw(ops.concat_nhwc(up4_nhwc, [d2, d4, d8], act=True, pad=pad1, a_subpixel=True))
         else:

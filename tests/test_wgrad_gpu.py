@@ -67,3 +67,36 @@ def test_wgrad_is_deterministic_and_rejects_bad_shapes():
         ops.conv3x3_wgrad(torch.randn(1, 4, 4, 32, device=DEV), torch.randn(1, 4, 4, 132, device=DEV))
     with pytest.raises(ValueError):
         ops.conv3x3_wgrad(torch.randn(1, 4, 4, 32, device=DEV), torch.randn(1, 4, 5, 16, device=DEV))
+
+
+def test_decoder_training_gradients_with_and_without_the_tensor_core_wgrad():
+    """A training step of the decoder with the tcgen05 weight gradients (the default while torch's TF32 switch is on) against the same
+    step with the library's TF32 kernels: every parameter gradient agrees to TF32 accuracy."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
+    from bts_fully_tf_b200.decoder import BtsDecoder
+    assert torch.backends.cudnn.allow_tf32
+    torch.manual_seed(3)
+    B, H, W, F = 4, 128, 256, 128
+    chans = [24, 8, 8, 12, 16]
+    feats = [torch.randn(B, H // s, W // s, c, device=DEV) for s, c in zip((32, 2, 4, 8, 16), chans)]
+    gt = torch.rand(B, H, W, 1, device=DEV) * 10.0
+    dec = BtsDecoder(chans, 10.0, num_filters=F).to(DEV).train()
+    grads = []
+    used = []
+    real = ops.conv3x3_wgrad
+    try:
+        for on in (True, False):
+            decoder_mod.TENSOR_CORE_WGRAD = on
+            ops.conv3x3_wgrad = lambda x, g, out=None: (used.append((x.shape[-1], g.shape[-1])), real(x, g, out))[1]
+            dec.zero_grad(set_to_none=True)
+            _, loss = dec.forward_loss(feats, gt, "nyu")
+            loss.backward()
+            grads.append({n: p.grad.clone() for n, p in dec.named_parameters()})
+    finally:
+        decoder_mod.TENSOR_CORE_WGRAD = True
+        ops.conv3x3_wgrad = real
+    assert len(used) >= 3, used                     # up4 (sub-pixel upconv1), iconv1 and conv block 2 at least
+    for n, ga in grads[0].items():
+        gb = grads[1][n]
+        scale = float(gb.abs().max())
+        assert float((ga - gb).abs().max()) <= 1e-2 * scale + 1e-8, n
