@@ -32,7 +32,7 @@ void reduce_launch_shape(uint64_t npix, uint32_t C, int &threads, int &blocks) {
     const uint32_t vpp = C / 4;
     threads = (int)((kBnrMaxThreads / vpp) * vpp);
     const uint32_t ppp = threads / vpp;
-    uint64_t b = (npix + (uint64_t)ppp * 8 - 1) / ((uint64_t)ppp * 8);          // at least 8 passes per CTA
+    uint64_t b = (npix + (uint64_t)ppp * 16 - 1) / ((uint64_t)ppp * 16);        // at least 16 passes per CTA
     if (b > (uint64_t)kBnrMaxBlocks) b = kBnrMaxBlocks;
     blocks = b < 1 ? 1 : (int)b;
 }
@@ -80,7 +80,7 @@ int btslpg_bn_moments(const BtsTensor *x, BtsTensor *mean, BtsTensor *var, void 
     reduce_launch_shape(p.npix, p.C, threads, blocks);
     bnr_reduce_kernel<0><<<blocks, threads, threads * 8 * sizeof(double), st>>>(p);
     if (int e = check_launch("btslpg_bn_moments")) return e;
-    bnr_finalize_kernel<0><<<(p.C + 31) / 32, 256, 0, st>>>(p, (uint32_t)blocks);
+    bnr_finalize_kernel<0><<<(p.C + 7) / 8, 256, 0, st>>>(p, (uint32_t)blocks);
     snprintf(tl_kernel, sizeof(tl_kernel), "bn_moments<f32,C%u>", p.C);
     return check_launch("btslpg_bn_moments");
 }
@@ -152,7 +152,7 @@ int btslpg_bn_act_backward_stats(const BtsTensor *g, const BtsTensor *g2, const 
     reduce_launch_shape(p.npix, p.C, threads, blocks);
     bnr_reduce_kernel<1><<<blocks, threads, threads * 8 * sizeof(double), st>>>(p);
     if (int e = check_launch("btslpg_bn_act_backward_stats")) return e;
-    bnr_finalize_kernel<1><<<(p.C + 31) / 32, 256, 0, st>>>(p, (uint32_t)blocks);
+    bnr_finalize_kernel<1><<<(p.C + 7) / 8, 256, 0, st>>>(p, (uint32_t)blocks);
     snprintf(tl_kernel, sizeof(tl_kernel), "bn_act_bwd_stats<f32,C%u,%s>", p.C, relu ? "relu" : "id");
     return check_launch("btslpg_bn_act_backward_stats");
 }

@@ -112,24 +112,24 @@ template <int MODE> __global__ void __launch_bounds__(kBnrMaxThreads) bnr_reduce
     }
 }
 
-// CTA rows -> result: 32 channels per CTA, 8 row slices per channel, slices combined in slice order (fixed order, no atomics)
+// CTA rows -> result: 8 channels per CTA, 32 row slices per channel, slices combined in slice order (fixed order, no atomics)
 template <int MODE> __global__ void __launch_bounds__(256) bnr_finalize_kernel(const __grid_constant__ BnrReduceParams prm, uint32_t nrows) {
-    __shared__ double comb[8][32][2];
-    const uint32_t C = prm.C, cl = threadIdx.x % 32, sl = threadIdx.x / 32, c = blockIdx.x * 32 + cl;
+    __shared__ double comb[32][8][2];
+    const uint32_t C = prm.C, cl = threadIdx.x % 8, sl = threadIdx.x / 8, c = blockIdx.x * 8 + cl;
     double a1 = 0.0, a2 = 0.0;
     if (c < C) {
         uint32_t b = sl;
-        for (; b + 24 < nrows; b += 32) {
+        for (; b + 96 < nrows; b += 128) {
             double u[4], w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                u[k] = __ldcg(prm.partial + (size_t)(b + 8 * k) * 2 * C + c);
-                w[k] = __ldcg(prm.partial + (size_t)(b + 8 * k) * 2 * C + C + c);
+                u[k] = __ldcg(prm.partial + (size_t)(b + 32 * k) * 2 * C + c);
+                w[k] = __ldcg(prm.partial + (size_t)(b + 32 * k) * 2 * C + C + c);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) { a1 += u[k]; a2 += w[k]; }
         }
-        for (; b < nrows; b += 8) {
+        for (; b < nrows; b += 32) {
             a1 += __ldcg(prm.partial + (size_t)b * 2 * C + c);
             a2 += __ldcg(prm.partial + (size_t)b * 2 * C + C + c);
         }
@@ -139,7 +139,7 @@ template <int MODE> __global__ void __launch_bounds__(256) bnr_finalize_kernel(c
     __syncthreads();
     if (sl != 0 || c >= C) return;
 #pragma unroll
-    for (int q = 1; q < 8; ++q) { a1 += comb[q][cl][0]; a2 += comb[q][cl][1]; }
+    for (int q = 1; q < 32; ++q) { a1 += comb[q][cl][0]; a2 += comb[q][cl][1]; }
     if (MODE == 0) {
         const double n = (double)prm.npix, mean = a1 / n;
         double var = a2 / n - mean * mean;                               // biased: what training-mode normalisation uses

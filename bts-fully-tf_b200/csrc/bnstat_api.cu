@@ -12,7 +12,7 @@ bool bn_channels_ok(int64_t C) { return C >= 4 && C <= 1024 && (C & (C - 1)) == 
 
 int bn_blocks(uint64_t npix, uint32_t C) {
     const uint32_t px_per_pass = kBnThreads / (C / 4);
-    uint64_t b = (npix + (uint64_t)px_per_pass * 8 - 1) / ((uint64_t)px_per_pass * 8);      // at least 8 passes per CTA
+    uint64_t b = (npix + (uint64_t)px_per_pass * 16 - 1) / ((uint64_t)px_per_pass * 16);    // at least 16 passes per CTA
     if (b > (uint64_t)kBnMaxBlocks) b = kBnMaxBlocks;
     return b < 1 ? 1 : (int)b;
 }
@@ -60,7 +60,7 @@ int btslpg_bn_elu_stats(const BtsTensor *raw, int act, const BtsTensor *gamma, c
     const int blocks = bn_blocks(npix, p.C);
     bn_stats_kernel<false><<<blocks, kBnThreads, kBnThreads * 8 * sizeof(double), st>>>(p);
     if (int e = check_launch("btslpg_bn_elu_stats")) return e;
-    bn_finalize_kernel<false><<<(p.C + 31) / 32, 256, 0, st>>>(p, (uint32_t)blocks);
+    bn_finalize_kernel<false><<<(p.C + 7) / 8, 256, 0, st>>>(p, (uint32_t)blocks);
     snprintf(tl_kernel, sizeof(tl_kernel), "bn_elu_stats<f32,C%u>", p.C);
     return check_launch("btslpg_bn_elu_stats");
 }
@@ -99,7 +99,7 @@ int btslpg_bn_elu_backward_stats(const BtsTensor *g_out, const BtsTensor *y, int
     const int blocks = bn_blocks(npix, p.C);
     bn_stats_kernel<true><<<blocks, kBnThreads, kBnThreads * 8 * sizeof(double), st>>>(p);
     if (int e = check_launch("btslpg_bn_elu_backward_stats")) return e;
-    bn_finalize_kernel<true><<<(p.C + 31) / 32, 256, 0, st>>>(p, (uint32_t)blocks);
+    bn_finalize_kernel<true><<<(p.C + 7) / 8, 256, 0, st>>>(p, (uint32_t)blocks);
     snprintf(tl_kernel, sizeof(tl_kernel), "bn_elu_bwd_stats<f32,C%u>", p.C);
     return check_launch("btslpg_bn_elu_backward_stats");
 }

@@ -116,25 +116,25 @@ template <bool BWD> __global__ void __launch_bounds__(kBnThreads) bn_stats_kerne
 }
 
 // CTAs -> result.  A second, wide launch instead of a last-CTA tail: up to 592 rows x 2C columns of float64 partials would be a
-// chain of dependent L2 round trips for one CTA (tens of microseconds at C = 512); here 32 channels per CTA, 8 row slices per
+// chain of dependent L2 round trips for one CTA (tens of microseconds at C = 512); here 8 channels per CTA, 32 row slices per
 // channel, four loads in flight per thread, slices combined in slice order through shared memory: fixed order, no atomics.
 template <bool BWD> __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ BnStatParams prm, uint32_t nrows) {
-    __shared__ double comb[8][32][2];
-    const uint32_t C = prm.C, cl = threadIdx.x % 32, sl = threadIdx.x / 32, c = blockIdx.x * 32 + cl;
+    __shared__ double comb[32][8][2];
+    const uint32_t C = prm.C, cl = threadIdx.x % 8, sl = threadIdx.x / 8, c = blockIdx.x * 8 + cl;
     double a1 = 0.0, a2 = 0.0;
     if (c < C) {
         uint32_t b = sl;
-        for (; b + 24 < nrows; b += 32) {
+        for (; b + 96 < nrows; b += 128) {
             double u[4], w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                u[k] = __ldcg(prm.partial + (size_t)(b + 8 * k) * 2 * C + c);
-                w[k] = __ldcg(prm.partial + (size_t)(b + 8 * k) * 2 * C + C + c);
+                u[k] = __ldcg(prm.partial + (size_t)(b + 32 * k) * 2 * C + c);
+                w[k] = __ldcg(prm.partial + (size_t)(b + 32 * k) * 2 * C + C + c);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) { a1 += u[k]; a2 += w[k]; }
         }
-        for (; b < nrows; b += 8) {
+        for (; b < nrows; b += 32) {
             a1 += __ldcg(prm.partial + (size_t)b * 2 * C + c);
             a2 += __ldcg(prm.partial + (size_t)b * 2 * C + C + c);
         }
@@ -144,7 +144,7 @@ template <bool BWD> __global__ void __launch_bounds__(256) bn_finalize_kernel(co
     __syncthreads();
     if (sl != 0 || c >= C) return;
 #pragma unroll
-    for (int q = 1; q < 8; ++q) { a1 += comb[q][cl][0]; a2 += comb[q][cl][1]; }
+    for (int q = 1; q < 32; ++q) { a1 += comb[q][cl][0]; a2 += comb[q][cl][1]; }
     const double n = (double)prm.npix;
     if (BWD) {
         prm.g_beta[c] = (float)a1;                                   // d loss / d beta

@@ -8,6 +8,7 @@ using namespace btslpg_api;
 
 namespace {
 
+constexpr int kWgHeaderBytes = 256;   // the workspace's first 256 bytes belong to the kernels that keep counters there (always left zero)
 constexpr int kWgMaxBlocks = 160;      // partial rows the workspace holds (>= SMs of the device; the launch uses min(items, SMs))
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -45,7 +46,7 @@ extern "C" {
 size_t btslpg_conv3x3_wgrad_workspace_bytes(int cin, int cout) {
     if (cin < 1) cin = 1;
     if (cout < 1) cout = 1;
-    return (size_t)kWgMaxBlocks * 9 * cin * cout * sizeof(float);
+    return (size_t)kWgHeaderBytes + (size_t)kWgMaxBlocks * 9 * cin * cout * sizeof(float);
 }
 
 int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_kernel, void *workspace, size_t workspace_bytes, void *stream) {
@@ -75,7 +76,7 @@ int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_ke
     if (int e = make_map(gv, "g", kWgTW + 2, T, map_g)) return e;
 
     WgradParams p;
-    p.partial = static_cast<float *>(workspace);
+    p.partial = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWgHeaderBytes);
     p.B = (int)xv.B; p.H = (int)xv.H; p.W = (int)xv.W; p.Cin = (int)Cin; p.Cout = (int)Cout;
     p.bands = (uint32_t)((xv.H + T - 1) / T);
     p.ctiles = (uint32_t)((xv.W + kWgTW - 1) / kWgTW);
@@ -121,7 +122,7 @@ int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_ke
             if (e) return e;
         }
     const uint32_t n = (uint32_t)(9 * Cin * Cout);
-    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.partial, out, n, blocks);
+    wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(p.partial, out, n, blocks);
     snprintf(tl_kernel, sizeof(tl_kernel), "conv3x3_wgrad_tcgen05<f32/tf32,Cin%d,Cout%d>", p.Cin, p.Cout);
     return check_launch("btslpg_conv3x3_wgrad");
 }

@@ -191,19 +191,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
     }
 }
 
-// partial rows -> g_w, fixed order
+// partial rows -> g_w in a fixed order: a warp owns 32 consecutive elements and every 8th row (coalesced 128-byte loads, four in
+// flight), the eight row slices are combined in slice order through shared memory
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, uint32_t n, uint32_t rows) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+    __shared__ float comb[8][32];
+    const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
     float acc = 0.0f;
-    uint32_t r = 0;
-    for (; r + 4 <= rows; r += 4) {
-        const float a0 = __ldcg(partial + (size_t)r * n + i), a1 = __ldcg(partial + (size_t)(r + 1) * n + i);
-        const float a2 = __ldcg(partial + (size_t)(r + 2) * n + i), a3 = __ldcg(partial + (size_t)(r + 3) * n + i);
-        acc += a0; acc += a1; acc += a2; acc += a3;
+    if (i < n) {
+        uint32_t r = sl;
+        for (; r + 24 < rows; r += 32) {
+            const float a0 = __ldcg(partial + (size_t)r * n + i), a1 = __ldcg(partial + (size_t)(r + 8) * n + i);
+            const float a2 = __ldcg(partial + (size_t)(r + 16) * n + i), a3 = __ldcg(partial + (size_t)(r + 24) * n + i);
+            acc += a0; acc += a1; acc += a2; acc += a3;
+        }
+        for (; r < rows; r += 8) acc += __ldcg(partial + (size_t)r * n + i);
     }
-    for (; r < rows; ++r) acc += __ldcg(partial + (size_t)r * n + i);
-    out[i] = acc;
+    comb[sl][lane] = acc;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) acc += comb[q][lane];
+        out[i] = acc;
+    }
 }
 
 }  // namespace btslpg

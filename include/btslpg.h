@@ -287,7 +287,8 @@ BTSLPG_API int btslpg_concat_backward_bn(const BtsTensor *g_out, const BtsTensor
  *             (channels beyond 64 on either side are handled in passes of 64 x 64 that stage their operands again)
  *   g_kernel  float32 [3][3][Cin][Cout], the Keras HWIO layout of layer.kernel
  * TF32 operands (the tensor core ignores the low 13 mantissa bits of the float32 inputs), float32 accumulation; deterministic
- * (per-CTA partials summed in a fixed order).  workspace: btslpg_conv3x3_wgrad_workspace_bytes(Cin, Cout) bytes, 16-byte aligned.
+ * (per-CTA partials summed in a fixed order).  workspace: btslpg_conv3x3_wgrad_workspace_bytes(Cin, Cout) bytes, 16-byte aligned; like
+ * the other workspaces of this library it may be shared with them: its first 256 bytes (their counters) are never touched.
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API size_t btslpg_conv3x3_wgrad_workspace_bytes(int cin, int cout);
 BTSLPG_API int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsTensor *g_kernel, void *workspace, size_t workspace_bytes,

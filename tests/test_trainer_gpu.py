@@ -18,6 +18,14 @@ DEV = "cuda:0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(autouse=True)
+def _restore_tf32():
+    """Some tests here switch the library's TF32 convolutions off; leave the process as it was found."""
+    old = torch.backends.cudnn.allow_tf32
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
 def _setup(seed=0, F=256, B=2, H=64, W=96):
     chans = [64, 8, 8, 16, 24]
     torch.manual_seed(seed)

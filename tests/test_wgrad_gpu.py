@@ -74,7 +74,8 @@ def test_decoder_training_gradients_with_and_without_the_tensor_core_wgrad():
     step with the library's TF32 kernels: every parameter gradient agrees to TF32 accuracy."""
     from bts_fully_tf_b200 import decoder as decoder_mod
     from bts_fully_tf_b200.decoder import BtsDecoder
-    assert torch.backends.cudnn.allow_tf32
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True              # the switch the tensor-core path follows (another test module may have left it off)
     torch.manual_seed(3)
     B, H, W, F = 4, 128, 256, 128
     chans = [24, 8, 8, 12, 16]
@@ -95,8 +96,30 @@ def test_decoder_training_gradients_with_and_without_the_tensor_core_wgrad():
     finally:
         decoder_mod.TENSOR_CORE_WGRAD = True
         ops.conv3x3_wgrad = real
+        torch.backends.cudnn.allow_tf32 = old_tf32
     assert len(used) >= 3, used                     # up4 (sub-pixel upconv1), iconv1 and conv block 2 at least
     for n, ga in grads[0].items():
         gb = grads[1][n]
         scale = float(gb.abs().max())
         assert float((ga - gb).abs().max()) <= 1e-2 * scale + 1e-8, n
+
+
+def test_wgrad_leaves_the_shared_workspace_header_alone():
+    """ops shares one scratch buffer per stream between the kernels that need one; its first 256 bytes hold the counters of the
+    last-CTA reductions (always left zero).  A fused head backward before and after a weight gradient gives identical bits."""
+    gen = torch.Generator().manual_seed(0)
+    feat = torch.randn(2, 24, 32, 32, generator=gen).to(DEV)
+    kernel = (torch.randn(32, 3, generator=gen) * 0.3).to(DEV)
+
+    def head_grads():
+        f, k = feat.clone().requires_grad_(True), kernel.clone().requires_grad_(True)
+        _, full, ds = ops.reduce_lpg(f, k, 4, 2)
+        (full.sum() * 0.5 + (ds * ds).sum()).backward()
+        return f.grad.clone(), k.grad.clone()
+
+    before = head_grads()
+    ops.conv3x3_wgrad(torch.randn(2, 40, 64, 32, device=DEV), torch.randn(2, 40, 64, 16, device=DEV))
+    ws = ops._workspace(torch.device(DEV), 256)
+    assert int(ws[:256].to(torch.int32).abs().sum()) == 0
+    after = head_grads()
+    assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1])
