@@ -284,6 +284,14 @@ def iconv_context():
     return bench_iconv.collect()
 
 
+def wgrad_context():
+    """Weight gradient of the full-resolution / few-channel 3x3 convolutions (bts_decoder.py:98, :100, :38-44): the tcgen05 kernel against
+    the library's weight-gradient kernels at the decoder's shapes."""
+    _tools()
+    import bench_wgrad
+    return bench_wgrad.collect()
+
+
 def tail_context():
     """silog fwd/bwd, the nine metrics, fused ELU + concat1 fwd/bwd, the last convolution fwd/bwd at B=32, 480x640, float32."""
     _tools()
@@ -543,7 +551,8 @@ def main():
 
     # ---- the kernels the decoder actually launches (fused heads) and the decoder-tail kernels, same hygiene (N = 1 only)
     if not a.skip_extras and world == 1 and a.dtype == "f32":
-        for key, fn in (("heads", lambda: heads_context(peak)), ("tail", tail_context), ("iconv1_tcgen05", iconv_context)):
+        for key, fn in (("heads", lambda: heads_context(peak)), ("tail", tail_context), ("iconv1_tcgen05", iconv_context),
+                        ("wgrad_tcgen05", wgrad_context)):
             try:
                 extras[key] = fn()
             except Exception as exc:  # noqa: BLE001

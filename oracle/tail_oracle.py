@@ -211,3 +211,39 @@ def conv_block_glue(raw, skip, planes, gamma, beta, eps, pad=0):
     if pad:
         parts.append(np.zeros(x.shape[:3] + (pad,)))
     return np.concatenate(parts, axis=3), mean, var
+
+
+def conv3x3_wgrad(x, g, tf32_operands=False):
+    """d kernel (HWIO) of Conv2D(3x3, strides 1, padding='same', use_bias=False) -- bts_decoder.py:98, :100 -- in float64:
+    dW[ky][kx][ci][co] = sum_{b,y,x} x[b, y+ky-1, x+kx-1, ci] * g[b, y, x, co], x zero outside the image.
+    tf32_operands: cut both operands to TF32 first (the tensor core ignores the low 13 mantissa bits of float32 inputs)."""
+    x = np.asarray(x, np.float32)
+    g = np.asarray(g, np.float32)
+    if tf32_operands:
+        x = (x.view(np.int32) & np.int32(-8192)).view(np.float32)
+        g = (g.view(np.int32) & np.int32(-8192)).view(np.float32)
+    x, g = x.astype(np.float64), g.astype(np.float64)
+    B, H, W, _ = x.shape
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    out = np.empty((3, 3, x.shape[3], g.shape[3]))
+    for ky in range(3):
+        for kx in range(3):
+            out[ky, kx] = np.einsum("bhwi,bhwo->io", xp[:, ky:ky + H, kx:kx + W, :], g)
+    return out
+
+
+def bn_relu_backward(g, x, gamma, beta, eps, g2=None):
+    """Backward of y = relu(BatchNormalization(x)) with the batch's own statistics (bts_decoder.py:47-48, :51-52 with is_training), float64:
+    returns (d x, d gamma, d beta).  g2: a gradient that reaches the normalised value directly (no ReLU)."""
+    x = np.asarray(x, np.float64)
+    g = np.asarray(g, np.float64)
+    ax = tuple(range(x.ndim - 1))
+    n = x.size // x.shape[-1]
+    mean, var = x.mean(axis=ax), x.var(axis=ax)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xhat = (x - mean) * rstd
+    z = xhat * gamma + beta
+    gm = np.where(z > 0, g, 0.0) + (0.0 if g2 is None else np.asarray(g2, np.float64))
+    d_beta, d_gamma = gm.sum(axis=ax), (gm * xhat).sum(axis=ax)
+    d_x = gamma * rstd * (gm - d_beta / n - xhat * d_gamma / n)
+    return d_x, d_gamma, d_beta

@@ -1,0 +1,50 @@
+"""CPU pins of the oracle restatements behind the training-glue kernels (oracle/tail_oracle.py: conv_block_glue, bn_relu_backward,
+conv3x3_wgrad) against the framework's own layers with autograd in float64 -- the same layer semantics the reference builds with
+Keras (bts_decoder.py:30-54, :98-100: Conv2D, BatchNormalization(training), ELU / ReLU, Concatenate)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import tail_oracle
+
+
+def test_conv3x3_wgrad_oracle_matches_conv2d_autograd():
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 7, 9, 5, generator=gen, dtype=torch.float64)
+    g = torch.randn(2, 7, 9, 3, generator=gen, dtype=torch.float64)
+    w = torch.zeros(3, 5, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).backward(g.permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 1, 0).numpy()                                   # OIHW -> HWIO
+    np.testing.assert_allclose(tail_oracle.conv3x3_wgrad(x.float().numpy(), g.float().numpy()), ref, rtol=1e-5, atol=1e-5)
+    # TF32 operands: the low 13 mantissa bits are cut
+    cut = tail_oracle.conv3x3_wgrad(x.float().numpy(), g.float().numpy(), tf32_operands=True)
+    assert 0 < np.abs(cut - ref).max() <= 4e-3 * np.abs(ref).max()
+
+
+def test_bn_relu_backward_oracle_matches_autograd():
+    gen = torch.Generator().manual_seed(1)
+    x = (torch.randn(3, 5, 6, 8, generator=gen, dtype=torch.float64) * 2 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(8, generator=gen, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = torch.randn(8, generator=gen, dtype=torch.float64).requires_grad_(True)
+    z = F.batch_norm(x.permute(0, 3, 1, 2), None, None, gamma, beta, training=True, eps=1.1e-5).permute(0, 2, 3, 1)
+    g = torch.randn(3, 5, 6, 8, generator=gen, dtype=torch.float64)
+    g2 = torch.randn(3, 5, 6, 8, generator=gen, dtype=torch.float64)
+    ((torch.relu(z) * g).sum() + (z * g2).sum()).backward()
+    d_x, d_gamma, d_beta = tail_oracle.bn_relu_backward(g.numpy(), x.detach().numpy(), gamma.detach().numpy(), beta.detach().numpy(), 1.1e-5,
+                                                        g2=g2.numpy())
+    np.testing.assert_allclose(d_x, x.grad.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(d_gamma, gamma.grad.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(d_beta, beta.grad.numpy(), rtol=1e-9, atol=1e-10)
+
+
+def test_conv_block_glue_oracle_matches_framework_layers():
+    gen = torch.Generator().manual_seed(2)
+    raw = torch.randn(2, 4, 5, 8, generator=gen, dtype=torch.float64)
+    skip = torch.randn(2, 4, 5, 3, generator=gen, dtype=torch.float64)
+    plane = torch.rand(2, 4, 5, 1, generator=gen, dtype=torch.float64)
+    gamma, beta = torch.rand(8, generator=gen, dtype=torch.float64) + 0.5, torch.randn(8, generator=gen, dtype=torch.float64)
+    up = F.batch_norm(F.elu(raw).permute(0, 3, 1, 2), None, None, gamma, beta, training=True, eps=1.1e-5).permute(0, 2, 3, 1)
+    ref = torch.cat([up, skip, plane, torch.zeros(2, 4, 5, 4, dtype=torch.float64)], 3).numpy()
+    out, mean, var = tail_oracle.conv_block_glue(raw.numpy(), skip.numpy(), [plane.numpy()], gamma.numpy(), beta.numpy(), 1.1e-5, pad=4)
+    np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(mean, F.elu(raw).reshape(-1, 8).mean(0).numpy(), rtol=1e-12)

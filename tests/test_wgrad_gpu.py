@@ -1,28 +1,15 @@
 """GPU parity of the tcgen05 weight gradient of the full-resolution 3x3 convolutions (bts_decoder.py:98, :100) against the float64
-definition (and, structurally, against one-hot inputs that isolate single taps)."""
+oracle (oracle/tail_oracle.conv3x3_wgrad, pinned to conv2d's own autograd in tests/test_train_glue_oracle_cpu.py) and, structurally,
+against one-hot inputs that isolate single taps."""
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
 from bts_fully_tf_b200 import ops
+from oracle import tail_oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-
-
-def _ref_wgrad(x, g):
-    """HWIO d kernel in float64: conv2d's own autograd on the CPU."""
-    xd = x.double().permute(0, 3, 1, 2).contiguous()
-    w = torch.zeros(g.shape[-1], x.shape[-1], 3, 3, dtype=torch.float64, requires_grad=True)
-    y = F.conv2d(xd, w, padding=1)
-    y.backward(g.double().permute(0, 3, 1, 2).contiguous())
-    return w.grad.permute(2, 3, 1, 0).contiguous()           # OIHW -> HWIO
-
-
-def _tf32(t):
-    """Truncate to TF32 (what the tensor core reads)."""
-    return (t.view(torch.int32) & -8192).view(torch.float32)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 32, 32), (2, 11, 37, 32, 16), (1, 16, 48, 20, 16), (2, 9, 33, 64, 32), (1, 24, 40, 36, 32),
@@ -32,11 +19,11 @@ def test_wgrad_matches_float64_definition(B, H, W, Cin, Cout):
     x = torch.randn(B, H, W, Cin, generator=gen)
     g = torch.randn(B, H, W, Cout, generator=gen)
     out = ops.conv3x3_wgrad(x.to(DEV), g.to(DEV)).cpu()
-    exact = _ref_wgrad(_tf32(x), _tf32(g))                   # same operand bits: only the float32 accumulation order differs
-    scale = float(exact.abs().max())
-    assert float((out.double() - exact).abs().max()) <= 2e-5 * scale + 1e-6
-    full = _ref_wgrad(x, g)                                  # against untruncated operands: TF32's 2^-10 per operand
-    assert float((out.double() - full).abs().max()) <= 3e-3 * float(full.abs().max())
+    out = out.double().numpy()
+    exact = tail_oracle.conv3x3_wgrad(x.numpy(), g.numpy(), tf32_operands=True)       # same operand bits: only float32 accumulation differs
+    assert np.abs(out - exact).max() <= 2e-5 * np.abs(exact).max() + 1e-6
+    full = tail_oracle.conv3x3_wgrad(x.numpy(), g.numpy())                            # untruncated operands: TF32's 2^-10 per operand
+    assert np.abs(out - full).max() <= 3e-3 * np.abs(full).max()
 
 
 def test_wgrad_one_hot_isolates_taps():

@@ -59,7 +59,7 @@ def collect(device=None, library=True):
             def lib(k):
                 torch.ops.aten.convolution_backward(gs[k].permute(0, 3, 1, 2), xs[k].permute(0, 3, 1, 2), w, None, [1, 1], [1, 1], [1, 1], False,
                                                     [0, 0], 1, [False, True, False])
-            t = timed(lib, nsets, reps=4)
+            t = timed(lib, nsets, reps=3)
             pt["library_us"] = round(t, 1)
             pt["speedup"] = round(t / ours, 2)
         out["points"].append(pt)
