@@ -376,3 +376,37 @@ def reduction_lpg(feat, kernel, upratio, ds_stride=0):  # pragma: no cover
 
     coef, full, ds = op(feat, kernel)
     return coef, full, (ds if d else None)
+
+
+def conv3x3_tensor_core_wgrad(inputs, kernel):  # pragma: no cover
+    """Conv2D(kernel_size=3, strides=1, padding='same', use_bias=False) -- upconv1 / iconv1 / conv block 2 of
+    bts_decoder.py:38-44, :96-101 built with activation=None -- whose kernel gradient comes from the tcgen05 kernel
+    (btslpg_conv3x3_wgrad) while the forward and the input gradient stay TensorFlow's.
+    inputs (B,H,W,Cin), Cin a multiple of 4 up to 256; kernel: the layer's (3,3,Cin,Cout) variable, Cout a multiple of 4 up to 128."""
+    _require_tf()
+    lib = _cabi.load()
+
+    @tf.custom_gradient
+    def op(x, k):
+        y = tf.nn.conv2d(x, k, strides=1, padding="SAME")
+
+        def grad(g_out):
+            g_x = tf.compat.v1.nn.conv2d_backprop_input(tf.shape(x), k, g_out, strides=[1, 1, 1, 1], padding="SAME")
+
+            def wgrad(x_, g_):
+                cin, cout = int(x_.shape[3]), int(g_.shape[3])
+                with tf.device(x_.device):
+                    g_k = tf.zeros([3, 3, cin, cout], tf.float32)
+                    ws = tf.zeros([int(lib.btslpg_conv3x3_wgrad_workspace_bytes(cin, cout))], tf.uint8)
+                rx, rg, rk, rw = _ref(x_), _ref(g_), _ref(g_k), _ref(ws)
+                _sync(rx)
+                _cabi.check(lib.btslpg_conv3x3_wgrad(rx.ptr, rg.ptr, rk.ptr, ctypes.c_void_p(rw.struct.data), int(ws.shape[0]), ctypes.c_void_p(0)))
+                _sync(rx)
+                return g_k
+            g_k = _gpu_py_function(wgrad, [x, g_out], tf.float32)
+            g_k.set_shape(k.shape)
+            return g_x, g_k
+
+        return y, grad
+
+    return op(inputs, kernel)
