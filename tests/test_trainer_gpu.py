@@ -85,6 +85,35 @@ def test_cuda_graph_step_equals_eager_step():
     assert float((params[0] - params[1]).abs().max()) <= 2e-3 * float(scale)
 
 
+def test_cuda_graph_step_with_tensor_core_weight_gradients():
+    """The captured step with torch's TF32 switch on -- the tcgen05 weight gradients (TMA tensor maps as kernel parameters) and the
+    training-mode glue inside the graph -- follows the eager trajectory."""
+    from bts_fully_tf_b200 import ops
+    torch.backends.cudnn.allow_tf32 = True
+    calls = []
+    real = ops.conv3x3_wgrad
+    ops.conv3x3_wgrad = lambda x, g, out=None: (calls.append(tuple(x.shape)), real(x, g, out))[1]
+    try:
+        losses, params = [], []
+        for use_graph in (False, True):
+            dec, feats, gt = _setup(seed=3, F=128, B=4, H=128, W=256)
+            eng = trainer.DataParallelStep(dec, feats, gt, dataset="nyu", base_lr=1e-3, use_graph=use_graph)
+            if use_graph:
+                eng.capture()
+            ls = [float(eng.step()) for _ in range(3)]
+            torch.cuda.synchronize()
+            assert eng.completed_updates() == 3
+            losses.append(ls)
+            params.append(eng.flat.param.clone())
+            eng.close()
+    finally:
+        ops.conv3x3_wgrad = real
+    assert len(calls) >= 6, calls                                       # several layers per step, eager steps and the capture
+    np.testing.assert_allclose(losses[0], losses[1], rtol=5e-3)
+    scale = params[0].abs().max()
+    assert float((params[0] - params[1]).abs().max()) <= 5e-3 * float(scale)
+
+
 def test_new_batches_flow_through_static_buffers():
     dec, feats, gt = _setup(seed=2)
     eng = trainer.DataParallelStep(dec, feats, gt, dataset="nyu", base_lr=1e-4).warmup_and_capture(2)
