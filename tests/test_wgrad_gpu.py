@@ -110,3 +110,41 @@ def test_wgrad_leaves_the_shared_workspace_header_alone():
     assert int(ws[:256].to(torch.int32).abs().sum()) == 0
     after = head_grads()
     assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1])
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(32, 416, 544, 20, 16), (16, 176, 608, 64, 128)])
+def test_wgrad_at_benchmark_sizes(B, H, W, Cin, Cout):
+    """BASELINE-size launches (config 5's iconv1, config 4's sub-pixel upconv1 at half the batch), where the float64 oracle would take
+    minutes: against the library's float32 (TF32 off) weight gradient, and linearity in the gradient operand."""
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    g1 = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    g2 = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        w = torch.zeros(Cout, Cin, 3, 3, device=DEV)
+        ref = torch.ops.aten.convolution_backward(g1.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                  [False, True, False])[1].permute(2, 3, 1, 0)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    a = ops.conv3x3_wgrad(x, g1)
+    scale = float(ref.abs().max())
+    assert float((a - ref).abs().max()) <= 3e-3 * scale
+    # linearity: exact products, float32 accumulation -> the sum of two launches equals the launch on the sum up to accumulation rounding
+    # (g1 + g2 is rounded to float32 and then cut to TF32, so allow TF32's own 2^-10 on the operand)
+    b = ops.conv3x3_wgrad(x, g2)
+    c = ops.conv3x3_wgrad(x, g1 + g2)
+    assert float((a + b - c).abs().max()) <= 3e-3 * float(c.abs().max())
+    # border handling at full size: zero the interior of g, only the outermost ring contributes
+    ring = torch.zeros_like(g1)
+    ring[:, 0], ring[:, -1], ring[:, :, 0], ring[:, :, -1] = g1[:, 0], g1[:, -1], g1[:, :, 0], g1[:, :, -1]
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref_ring = torch.ops.aten.convolution_backward(ring.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w, None, [1, 1], [1, 1], [1, 1], False,
+                                                       [0, 0], 1, [False, True, False])[1].permute(2, 3, 1, 0)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    d = ops.conv3x3_wgrad(x, ring)
+    assert float((d - ref_ring).abs().max()) <= 3e-3 * float(ref_ring.abs().max())
