@@ -164,7 +164,8 @@ class _DenseAspp(nn.Module):
         if self.bn_first is not None:
             x = self.bn_first(x)
         x = self.conv1(F.relu(x))
-        return self.conv2(F.relu(self.bn2(x)))
+        x = F.relu(self.bn2(x)).contiguous(memory_format=torch.channels_last)
+        return _to_nchw(_conv_nhwc(_nhwc_view(x), self.conv2))
 
     def tail_inference(self, x_relu_nchw):
         """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode:
@@ -174,17 +175,57 @@ class _DenseAspp(nn.Module):
         x = self.conv1(x_relu_nchw).contiguous(memory_format=torch.channels_last)
         x_nhwc = _nhwc_view(x)
         ops.affine_act(x_nhwc, dst=x_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU)
-        return self.conv2(x)
+        return _to_nchw(_conv_nhwc(x_nhwc, self.conv2))
 
 
-def _conv_backward(g_nhwc, x_nhwc, conv):
-    """(d input, d weight) of a bias-free stride-1 convolution, NHWC tensors in and out (cuDNN through the framework's own entry)."""
-    g_in, g_w, _ = torch.ops.aten.convolution_backward(_to_nchw(g_nhwc), _to_nchw(x_nhwc), conv.weight, None, [1, 1], list(conv.padding),
-                                                       list(conv.dilation), False, [0, 0], 1, [True, True, False])
-    return _nhwc_view(g_in.contiguous(memory_format=torch.channels_last)), g_w
+SPLIT_DILATION_FROM = 16     # dilation rates from here on run as 2 x 2 interleaved sub-grids of half the rate (see _dilation_split)
 
 
-def _conv_nhwc(x_nhwc, conv):
+def _dilation_split(conv, H, W):
+    """The library's fast convolution kernels stop at a dilation rate between 12 and 18: the DenseASPP convolutions of rate 18 and 24
+    (bts_decoder.py:53, :70, :73) fall to kernels 3.5x (forward) / 4.6x (weight gradient) slower than those of rate 3-12
+    (tools/exp_dilated_wgrad.py).  A rate-d convolution is exactly s x s independent rate-d/s convolutions on the interleaved
+    sub-grids x[:, i::s, j::s] (what TensorFlow's atrous convolution does with space_to_batch): with s = 2 the rates become 9 and 12.
+    Returns s (1: run the layer as it is)."""
+    d = conv.dilation[0]
+    return 2 if (d >= SPLIT_DILATION_FROM and d % 2 == 0 and H % 2 == 0 and W % 2 == 0 and conv.dilation[1] == d) else 1
+
+
+def _s2b(x_nhwc, s):
+    """(B,H,W,C) -> (B*s*s, H/s, W/s, C): sub-grid (i, j) of image b becomes image (b*s + i)*s + j."""
+    B, H, W, C = x_nhwc.shape
+    return x_nhwc.reshape(B, H // s, s, W // s, s, C).permute(0, 2, 4, 1, 3, 5).reshape(B * s * s, H // s, W // s, C)
+
+
+def _b2s(y_nhwc, s):
+    Bs, h, w, C = y_nhwc.shape
+    return y_nhwc.reshape(Bs // (s * s), s, s, h, w, C).permute(0, 3, 1, 4, 2, 5).reshape(Bs // (s * s), h * s, w * s, C)
+
+
+def _conv_backward(g_nhwc, x_nhwc, conv, x_split=0):
+    """(d input, d weight) of a bias-free stride-1 convolution, NHWC tensors in and out (cuDNN through the framework's own entry).
+    x_split = s: x_nhwc is already in the sub-grid form _s2b(x, s) (saved that way by the forward)."""
+    s = x_split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
+    if s > 1:
+        g_nhwc = _s2b(g_nhwc, s)
+        if not x_split:
+            x_nhwc = _s2b(x_nhwc, s)
+    dil = [conv.dilation[0] // s, conv.dilation[1] // s]
+    pad = list(conv.padding) if s == 1 else dil
+    g_in, g_w, _ = torch.ops.aten.convolution_backward(_to_nchw(g_nhwc), _to_nchw(x_nhwc), conv.weight, None, [1, 1], pad, dil, False, [0, 0], 1,
+                                                       [True, True, False])
+    g_in = _nhwc_view(g_in.contiguous(memory_format=torch.channels_last))
+    return (_b2s(g_in, s) if s > 1 else g_in), g_w
+
+
+def _conv_nhwc(x_nhwc, conv, x_split=0):
+    """conv(x) for a bias-free stride-1 'same' convolution on an NHWC tensor; differentiable (plain framework ops).
+    x_split = s: x_nhwc is already _s2b(x, s); the result comes back in the normal layout either way."""
+    s = x_split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
+    if s > 1:
+        d = conv.dilation[0] // s
+        y = F.conv2d(_to_nchw(x_nhwc if x_split else _s2b(x_nhwc, s)), conv.weight, None, 1, d, d)
+        return _b2s(_nhwc_view(y.contiguous(memory_format=torch.channels_last)), s)
     return _nhwc_view(F.conv2d(_to_nchw(x_nhwc), conv.weight, None, 1, conv.padding, conv.dilation).contiguous(memory_format=torch.channels_last))
 
 
@@ -230,7 +271,10 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             ops.bn_moments(t, m2, v2)
             v2k = fold(blk.bn2, m2, v2)
             r2 = ops.affine_act(t, scale=v2k[0], shift=v2k[1], act=ops.ACT_RELU)
-            d = _conv_nhwc(r2, blk.conv2)
+            s2 = _dilation_split(blk.conv2, h, w)
+            if s2 > 1:
+                r2 = _s2b(r2, s2)                 # kept in the sub-grid form the convolution (and its backward) read
+            d = _conv_nhwc(r2, blk.conv2, x_split=s2 if s2 > 1 else 0)
             ops.affine_act(d, dst=buf[..., ck:ck + half])
             if k + 1 < len(blocks):
                 ops.bn_moments(d, mean[ck:ck + half], var[ck:ck + half])
@@ -275,7 +319,8 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             xk, t, r2, v2k, vk = per_block[k]
             ck = nf + half * k
             g_d = ops.affine_act(gbuf[..., ck:ck + half])                               # contiguous copy of the block's complete gradient
-            g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2)
+            s2 = _dilation_split(blk.conv2, h, w)
+            g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2, x_split=s2 if s2 > 1 else 0)
             gg2, gb2 = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
             g_t = ops.bn_act_backward(g_r2, t, v2k, gg2, gb2, torch.empty_like(t))
             grads[blk.bn2.weight], grads[blk.bn2.bias] = gg2, gb2

@@ -35,8 +35,11 @@ def _decoder(num_filters, seed):
     return dec.train()
 
 
-@pytest.mark.parametrize("num_filters,B,h,w", [(64, 2, 7, 9), (128, 1, 12, 16), (32, 3, 5, 6)])
-def test_daspp_training_matches_framework_layers(num_filters, B, h, w):
+@pytest.mark.parametrize("num_filters,B,h,w", [(64, 2, 7, 9), (128, 1, 12, 16), (32, 3, 5, 6), (64, 2, 52, 68)])
+def test_daspp_training_matches_framework_layers(num_filters, B, h, w, monkeypatch):
+    """Even map sizes also cover the rate-18 / rate-24 convolutions run as 2 x 2 interleaved sub-grids (decoder._dilation_split); the
+    float64 reference runs every layer as the framework defines it."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
     dec = _decoder(num_filters, seed=num_filters)
     ref = copy.deepcopy(dec).double()
     ref.fused_training_glue = False
@@ -46,7 +49,10 @@ def test_daspp_training_matches_framework_layers(num_filters, B, h, w):
     x_gpu = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     x_ref = x.double().requires_grad_(True)
     out = dec._daspp(x_gpu)
+    assert (decoder_mod._dilation_split(dec.daspp_24.conv2, h, w) == 2) == (h % 2 == 0 and w % 2 == 0)
+    monkeypatch.setattr(decoder_mod, "SPLIT_DILATION_FROM", 10 ** 9)            # the reference: no splitting
     out_ref = ref._daspp(x_ref)
+    monkeypatch.undo()
     g = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(2))
     out.backward(g.to(DEV))
     out_ref.backward(g.double())
@@ -140,3 +146,22 @@ def test_bn_slice_argument_checks():
         ops.bn_moments(buf[..., 1:9], torch.empty(8, device=DEV), torch.empty(8, device=DEV))   # misaligned slice
     assert not ops.bn_slices_supported(36, torch.float32) and ops.bn_slices_supported(128, torch.float32)
     assert not ops.bn_slices_supported(128, torch.bfloat16)
+
+
+@pytest.mark.parametrize("rate,H,W", [(18, 12, 20), (24, 44, 152), (24, 6, 8)])
+def test_split_dilated_convolution_equals_the_layer(rate, H, W, monkeypatch):
+    """Forward, d input and d kernel of a high-rate dilated convolution through the sub-grid form against the layer as it is."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
+    torch.manual_seed(rate)
+    conv = decoder_mod._conv(16, 8, k=3, dilation=rate).to(DEV)
+    x = torch.randn(2, H, W, 16, device=DEV)
+    g = torch.randn(2, H, W, 8, device=DEV)
+    assert decoder_mod._dilation_split(conv, H, W) == 2
+    y = decoder_mod._conv_nhwc(x, conv)
+    g_x, g_w = decoder_mod._conv_backward(g, x, conv)
+    monkeypatch.setattr(decoder_mod, "SPLIT_DILATION_FROM", 10 ** 9)
+    y0 = decoder_mod._conv_nhwc(x, conv)
+    g_x0, g_w0 = decoder_mod._conv_backward(g, x, conv)
+    for a, b in ((y, y0), (g_x, g_x0), (g_w, g_w0)):
+        a, b = a.detach(), b.detach()
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-6
