@@ -100,6 +100,7 @@ SYMBOLS = {
     "btslpg_upsample2x_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_upsample2x_backward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),
     "btslpg_affine_act": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_void_p]),
+    "btslpg_affine_act_split": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "btslpg_depthconv_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "btslpg_depthconv_backward": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_int, _TP, _TP, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "btslpg_depthconv_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_int, ctypes.c_int, ctypes.c_float, _TP, ctypes.c_void_p]),

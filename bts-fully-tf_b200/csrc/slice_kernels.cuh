@@ -31,7 +31,23 @@ template <typename T> struct SliceParams {
     int64_t s_src, s_dst; // pixel strides in elements
     FastDiv div_pp;
     int act;
+    // sub-grid ("space to batch") addressing of ONE side: 0 none, 1 src, 2 dst.  That side is a (B*s*s, H/s, W/s, C) tensor whose image
+    // (b*s + i)*s + j is the sub-grid [i::s, j::s] of image b of the other side's (B,H,W,C) pixels (decoder._s2b).
+    int split;
+    uint32_t s, H, W;
+    FastDiv div_hw, div_w, div_s;
 };
+
+// pixel p = (b, y, x) of the (B,H,W) side -> its pixel index on the sub-grid side
+template <typename T> __device__ __forceinline__ uint32_t slice_split_pixel(const SliceParams<T> &prm, uint32_t p) {
+    uint32_t b, rem, y, x, ys, yi, xs, xi;
+    prm.div_hw.divmod(p, b, rem);
+    prm.div_w.divmod(rem, y, x);
+    prm.div_s.divmod(y, ys, yi);
+    prm.div_s.divmod(x, xs, xi);
+    const uint32_t hs = prm.H / prm.s, ws = prm.W / prm.s;
+    return (((b * prm.s + yi) * prm.s + xi) * hs + ys) * ws + xs;
+}
 
 __device__ __forceinline__ float slice_apply(float x, float sc, float sh, int act) {
     x = fmaf(x, sc, sh);
@@ -45,7 +61,10 @@ template <typename T> __global__ void __launch_bounds__(kSliceThreads) slice_aff
     uint32_t p, v;
     prm.div_pp.divmod((uint32_t)i, p, v);
     float x[N];
-    load_elems<T, N, 4>(prm.src + (int64_t)p * prm.s_src + v * N, x);
+    uint32_t ps = p, pd = p;
+    if (prm.split == 1) ps = slice_split_pixel(prm, p);
+    else if (prm.split == 2) pd = slice_split_pixel(prm, p);
+    load_elems<T, N, 4>(prm.src + (int64_t)ps * prm.s_src + v * N, x);
     if (prm.scale) {
 #pragma unroll
         for (int e = 0; e < N; ++e) x[e] = slice_apply(x[e], __ldg(prm.scale + v * N + e), __ldg(prm.shift + v * N + e), prm.act);
@@ -53,7 +72,7 @@ template <typename T> __global__ void __launch_bounds__(kSliceThreads) slice_aff
 #pragma unroll
         for (int e = 0; e < N; ++e) x[e] = slice_apply(x[e], 1.0f, 0.0f, prm.act);
     }
-    store_elems<T, N, 4>(prm.dst + (int64_t)p * prm.s_dst + v * N, x);
+    store_elems<T, N, 4>(prm.dst + (int64_t)pd * prm.s_dst + v * N, x);
 }
 
 template <typename T> __global__ void __launch_bounds__(kSliceThreads) slice_affine_act_scalar_kernel(const __grid_constant__ SliceParams<T> prm) {
@@ -62,7 +81,10 @@ template <typename T> __global__ void __launch_bounds__(kSliceThreads) slice_aff
     uint32_t p, c;
     prm.div_pp.divmod((uint32_t)i, p, c);
     const float sc = prm.scale ? __ldg(prm.scale + c) : 1.0f, sh = prm.scale ? __ldg(prm.shift + c) : 0.0f;
-    store1(prm.dst + (int64_t)p * prm.s_dst + c, slice_apply(load1(prm.src + (int64_t)p * prm.s_src + c), sc, sh, prm.act));
+    uint32_t ps = p, pd = p;
+    if (prm.split == 1) ps = slice_split_pixel(prm, p);
+    else if (prm.split == 2) pd = slice_split_pixel(prm, p);
+    store1(prm.dst + (int64_t)pd * prm.s_dst + c, slice_apply(load1(prm.src + (int64_t)ps * prm.s_src + c), sc, sh, prm.act));
 }
 
 }  // namespace btslpg

@@ -168,14 +168,20 @@ class _DenseAspp(nn.Module):
         return _to_nchw(_conv_nhwc(_nhwc_view(x), self.conv2))
 
     def tail_inference(self, x_relu_nchw):
-        """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode:
+        """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode; returns (NHWC, split):
         the second BatchNormalization (folded to an affine) and the ReLU are ONE in-place ops.affine_act pass over the
         1x1 conv's output (the framework's bias add + ReLU after a folded kernel take 156 us per block, this 26 us)."""
         scale, shift = _bn_affine(self.bn2)
         x = self.conv1(x_relu_nchw).contiguous(memory_format=torch.channels_last)
         x_nhwc = _nhwc_view(x)
+        s2 = _dilation_split(self.conv2, x_nhwc.shape[1], x_nhwc.shape[2])
+        if s2 > 1:
+            # rate 18 / 24: the same pass writes the sub-grid form the split convolution reads; the caller's copy into the DenseASPP
+            # buffer reads the result back from that form (returns (NHWC tensor in sub-grid form, s))
+            r = ops.affine_act(x_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU, dst_split=s2)
+            return _conv_nhwc(r, self.conv2, split=s2), s2
         ops.affine_act(x_nhwc, dst=x_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU)
-        return _to_nchw(_conv_nhwc(x_nhwc, self.conv2))
+        return _conv_nhwc(x_nhwc, self.conv2), 0
 
 
 SPLIT_DILATION_FROM = 16     # dilation rates from here on run as 2 x 2 interleaved sub-grids of half the rate (see _dilation_split)
@@ -202,30 +208,29 @@ def _b2s(y_nhwc, s):
     return y_nhwc.reshape(Bs // (s * s), s, s, h, w, C).permute(0, 3, 1, 4, 2, 5).reshape(Bs // (s * s), h * s, w * s, C)
 
 
-def _conv_backward(g_nhwc, x_nhwc, conv, x_split=0):
+def _conv_backward(g_nhwc, x_nhwc, conv, split=0):
     """(d input, d weight) of a bias-free stride-1 convolution, NHWC tensors in and out (cuDNN through the framework's own entry).
-    x_split = s: x_nhwc is already in the sub-grid form _s2b(x, s) (saved that way by the forward)."""
-    s = x_split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
-    if s > 1:
-        g_nhwc = _s2b(g_nhwc, s)
-        if not x_split:
-            x_nhwc = _s2b(x_nhwc, s)
+    split = s: g_nhwc, x_nhwc and the returned d input are all in the sub-grid form of _s2b(., s) (the caller re-orders inside passes
+    it runs anyway, ops.affine_act(..., src_split / dst_split)); split = 0: normal layout, split internally where it pays."""
+    s = split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
+    if s > 1 and not split:
+        g_nhwc, x_nhwc = _s2b(g_nhwc, s), _s2b(x_nhwc, s)
     dil = [conv.dilation[0] // s, conv.dilation[1] // s]
     pad = list(conv.padding) if s == 1 else dil
     g_in, g_w, _ = torch.ops.aten.convolution_backward(_to_nchw(g_nhwc), _to_nchw(x_nhwc), conv.weight, None, [1, 1], pad, dil, False, [0, 0], 1,
                                                        [True, True, False])
     g_in = _nhwc_view(g_in.contiguous(memory_format=torch.channels_last))
-    return (_b2s(g_in, s) if s > 1 else g_in), g_w
+    return (_b2s(g_in, s) if (s > 1 and not split) else g_in), g_w
 
 
-def _conv_nhwc(x_nhwc, conv, x_split=0):
+def _conv_nhwc(x_nhwc, conv, split=0):
     """conv(x) for a bias-free stride-1 'same' convolution on an NHWC tensor; differentiable (plain framework ops).
-    x_split = s: x_nhwc is already _s2b(x, s); the result comes back in the normal layout either way."""
-    s = x_split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
+    split = s: x_nhwc and the result are in the sub-grid form of _s2b(., s); split = 0: normal layout, split internally where it pays."""
+    s = split or _dilation_split(conv, x_nhwc.shape[1], x_nhwc.shape[2])
     if s > 1:
         d = conv.dilation[0] // s
-        y = F.conv2d(_to_nchw(x_nhwc if x_split else _s2b(x_nhwc, s)), conv.weight, None, 1, d, d)
-        return _b2s(_nhwc_view(y.contiguous(memory_format=torch.channels_last)), s)
+        y = _nhwc_view(F.conv2d(_to_nchw(x_nhwc if split else _s2b(x_nhwc, s)), conv.weight, None, 1, d, d).contiguous(memory_format=torch.channels_last))
+        return y if split else _b2s(y, s)
     return _nhwc_view(F.conv2d(_to_nchw(x_nhwc), conv.weight, None, 1, conv.padding, conv.dilation).contiguous(memory_format=torch.channels_last))
 
 
@@ -270,14 +275,14 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             m2, v2 = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
             ops.bn_moments(t, m2, v2)
             v2k = fold(blk.bn2, m2, v2)
-            r2 = ops.affine_act(t, scale=v2k[0], shift=v2k[1], act=ops.ACT_RELU)
             s2 = _dilation_split(blk.conv2, h, w)
-            if s2 > 1:
-                r2 = _s2b(r2, s2)                 # kept in the sub-grid form the convolution (and its backward) read
-            d = _conv_nhwc(r2, blk.conv2, x_split=s2 if s2 > 1 else 0)
-            ops.affine_act(d, dst=buf[..., ck:ck + half])
+            s2 = s2 if s2 > 1 else 0
+            # relu(BN(conv1)); for the split rate-18 / 24 convolutions written in the sub-grid form they read (and their backward reads)
+            r2 = ops.affine_act(t, scale=v2k[0], shift=v2k[1], act=ops.ACT_RELU, dst_split=s2)
+            d = _conv_nhwc(r2, blk.conv2, split=s2)
+            ops.affine_act(d, dst=buf[..., ck:ck + half], src_split=s2)
             if k + 1 < len(blocks):
-                ops.bn_moments(d, mean[ck:ck + half], var[ck:ck + half])
+                ops.bn_moments(d, mean[ck:ck + half], var[ck:ck + half])      # per-channel sums: the pixel order does not matter
             saved += [xk, t, r2, *v2k] + ([] if k == 0 else list(vk))
         ops.affine_act(x4, dst=buf[..., :nf], scale=vec4[0], shift=vec4[1])                          # concat4_daspp starts with iconv4_bn (:75)
         ctx.save_for_backward(*saved)
@@ -318,9 +323,12 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             blk = blocks[k]
             xk, t, r2, v2k, vk = per_block[k]
             ck = nf + half * k
-            g_d = ops.affine_act(gbuf[..., ck:ck + half])                               # contiguous copy of the block's complete gradient
             s2 = _dilation_split(blk.conv2, h, w)
-            g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2, x_split=s2 if s2 > 1 else 0)
+            s2 = s2 if s2 > 1 else 0
+            g_d = ops.affine_act(gbuf[..., ck:ck + half], dst_split=s2)                 # contiguous copy of the block's complete gradient
+            g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2, split=s2)
+            if s2:
+                g_r2 = ops.affine_act(g_r2, src_split=s2)                               # back to the pixel order of conv1's output
             gg2, gb2 = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
             g_t = ops.bn_act_backward(g_r2, t, v2k, gg2, gb2, torch.empty_like(t))
             grads[blk.bn2.weight], grads[blk.bn2.bias] = gg2, gb2
@@ -440,14 +448,14 @@ class BtsDecoder(nn.Module):
         ops.affine_act(_nhwc_view(iconv4.contiguous(memory_format=torch.channels_last)), dst=buf[..., :nf])
         s4_, t4_ = _bn_affine(self.bn4)
         x = ops.affine_act(buf[..., :nf], scale=s4_, shift=t4_, act=ops.ACT_RELU)                    # relu(iconv4_bn)
-        ops.affine_act(_nhwc_view(self.daspp_3.tail_inference(_to_nchw(x)).contiguous(memory_format=torch.channels_last)),
-                       dst=buf[..., nf:nf + half])
+        d, s2 = self.daspp_3.tail_inference(_to_nchw(x))
+        ops.affine_act(d, dst=buf[..., nf:nf + half], src_split=s2)
         for k, blk in enumerate((self.daspp_6, self.daspp_12, self.daspp_18, self.daspp_24)):
             ck = nf + half * (k + 1)
             sc, sh = _bn_affine(blk.bn_first)
             x = ops.affine_act(buf[..., :ck], scale=sc, shift=sh, act=ops.ACT_RELU)                  # relu(BN(concat4_k)), contiguous
-            d = blk.tail_inference(_to_nchw(x))
-            ops.affine_act(_nhwc_view(d.contiguous(memory_format=torch.channels_last)), dst=buf[..., ck:ck + half])
+            d, s2 = blk.tail_inference(_to_nchw(x))
+            ops.affine_act(d, dst=buf[..., ck:ck + half], src_split=s2)
         ops.affine_act(buf[..., :nf], dst=buf[..., :nf], scale=s4_, shift=t4_)                       # concat4_daspp starts with iconv4_bn (:75)
         return F.elu(self.daspp_feat(_to_nchw(buf)))
 

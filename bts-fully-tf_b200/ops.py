@@ -624,14 +624,22 @@ def upsample2x_nhwc(x):
 ACT_NONE, ACT_ELU, ACT_RELU = 0, 1, 2
 
 
-def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE):
+def affine_act(src, dst=None, scale=None, shift=None, act=ACT_NONE, src_split=0, dst_split=0):
     """dst[..., c] = act(src[..., c] * scale[c] + shift[c]); src / dst are (B,H,W,C) views with channel stride 1 and
-    uniformly strided pixels (channel slices of wider NHWC buffers), may alias.  No autograd (inference glue)."""
+    uniformly strided pixels (channel slices of wider NHWC buffers), may alias.  No autograd (inference glue).
+    src_split / dst_split = s > 1: that side is in sub-grid form, (B*s*s, H/s, W/s, C) with image (b*s + i)*s + j = [i::s, j::s] of
+    image b (what the split dilated convolutions of the DenseASPP read and write; decoder._dilation_split)."""
     lib = load()
+    s = int(src_split or dst_split or 1)
+    if src_split and dst_split:
+        raise ValueError("affine_act: only one side can be in sub-grid form")
     if dst is None:
-        dst = torch.empty(src.shape, dtype=src.dtype, device=src.device)
+        B, H, W, C = src.shape
+        shape = (B * s * s, H // s, W // s, C) if dst_split else (B // (s * s), H * s, W * s, C) if src_split else src.shape
+        dst = torch.empty(shape, dtype=src.dtype, device=src.device)
     rs, rd, rsc, rsh = as_ref(src), as_ref(dst), as_ref(scale), as_ref(shift)
-    check(lib.btslpg_affine_act(rs.ptr, ptr_or_null(rsc), ptr_or_null(rsh), int(act), rd.ptr, current_stream_ptr(src.device)))
+    check(lib.btslpg_affine_act_split(rs.ptr, ptr_or_null(rsc), ptr_or_null(rsh), int(act), rd.ptr, 1 if src_split else 2 if dst_split else 0, s,
+                                      current_stream_ptr(src.device)))
     return dst
 
 

@@ -344,6 +344,12 @@ BTSLPG_API int btslpg_upsample2x_backward(const BtsTensor *g_out, BtsTensor *g_i
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API int btslpg_affine_act(const BtsTensor *src, const BtsTensor *scale, const BtsTensor *shift, int act,
                                  BtsTensor *dst, void *stream);
+/* The same pass with ONE side in sub-grid ("space to batch") form: split_side 1 = src, 2 = dst (0: btslpg_affine_act).  That side is a
+ * (B*s*s, H/s, W/s, C) tensor whose image (b*s + i)*s + j is the sub-grid [i::s, j::s] of image b of the other side's (B,H,W,C)
+ * pixels.  The DenseASPP convolutions of rate 18 / 24 (bts_decoder.py:53) run as 2 x 2 sub-grids of rate 9 / 12 (the library's fast
+ * kernels stop below rate 18); their input is produced and their output consumed by this pass anyway, so the re-ordering is free. */
+BTSLPG_API int btslpg_affine_act_split(const BtsTensor *src, const BtsTensor *scale, const BtsTensor *shift, int act, BtsTensor *dst,
+                                       int split_side, int s, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward of the decoder's last convolution -- bts_decoder.py:102

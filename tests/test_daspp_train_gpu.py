@@ -165,3 +165,23 @@ def test_split_dilated_convolution_equals_the_layer(rate, H, W, monkeypatch):
     for a, b in ((y, y0), (g_x, g_x0), (g_w, g_w0)):
         a, b = a.detach(), b.detach()
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("s,B,H,W,CT,c0,C", [(2, 2, 6, 8, 24, 4, 16), (2, 1, 44, 152, 128, 0, 128), (3, 2, 6, 9, 7, 2, 5)])
+def test_affine_act_sub_grid_forms(s, B, H, W, CT, c0, C):
+    """ops.affine_act with one side in sub-grid form == the plain pass followed / preceded by the re-ordering copy."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
+    gen = torch.Generator().manual_seed(s * 100 + C)
+    buf = torch.randn(B, H, W, CT, generator=gen).to(DEV)
+    scale, shift = (torch.rand(C, generator=gen) + 0.5).to(DEV), torch.randn(C, generator=gen).to(DEV)
+    src = buf[..., c0:c0 + C]
+    plain = ops.affine_act(src, scale=scale, shift=shift, act=ops.ACT_RELU)
+    to_split = ops.affine_act(src, scale=scale, shift=shift, act=ops.ACT_RELU, dst_split=s)
+    assert to_split.shape == (B * s * s, H // s, W // s, C)
+    assert torch.equal(to_split, decoder_mod._s2b(plain, s))
+    back = torch.full((B, H, W, CT), -7.0, device=DEV)
+    ops.affine_act(to_split, dst=back[..., c0:c0 + C], src_split=s)
+    assert torch.equal(back[..., c0:c0 + C], plain)
+    assert bool((back[..., :c0] == -7.0).all()) and bool((back[..., c0 + C:] == -7.0).all())
+    with pytest.raises(ValueError):
+        ops.affine_act(src, dst=torch.empty(B * s * s, H // s, W // s + 1, C, device=DEV), dst_split=s)
