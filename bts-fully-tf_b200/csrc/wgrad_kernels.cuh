@@ -2,15 +2,15 @@
 // (tcgen05.mma kind::tf32, TMA-fed, accumulators in TMEM; sm_100a).  SURVEY 8(f) N1.
 //
 // bts_decoder.py:96-101: upconv1 = Conv2D(F/16, 3)(upsample(iconv2)) and iconv1 = Conv2D(F/16, 3)(concat1) run at FULL resolution with
-// 16-64 channels.  Their weight gradient  dW[ky][kx][ci][co] = sum_{b,y,x} in[b, y+ky-1, x+kx-1, ci] * g[b, y, x, co]  is a GEMM with a
+// 16-64 channels (and conv block 2 at half resolution).  Their weight gradient  dW[ky][kx][ci][co] = sum_{b,y,x} in[b, y+ky-1, x+kx-1, ci] * g[b, y, x, co]  is a GEMM with a
 // tiny output (9*Cin x Cout <= 576 x 32) and a reduction over every pixel of the batch (7-14 million): the library's kernels for it
 // (64x64 output tiles) run at 4-9 times the time it takes to read the two operands once (profiles/r01_tail_convs_cudnn_vs_fused.json:
 // 2.0-2.6 ms against floors of 0.4-0.6 ms at B = 32, 480x640).
 //
-// The GEMM here:  D[M = (input row r, ci)][N = co] += A[M][K = 8 pixels] * B[K][N]   per kernel column kx, with
-//   A = activations of FOUR consecutive input rows (CIN <= 32: M = 4 x 32) or two (CIN <= 64: M = 2 x 64), pixels as K: the rows
-//       y-1, y, y+1 that pair with output row y are the kernel rows ky = 0, 1, 2 -- three of the four M blocks of one instruction (the
-//       fourth accumulates a row pairing that is not part of the convolution and is dropped);
+// The GEMM here:  D[M = (input row r, ci)][N = (kx, co)] += A[M][K = 8 pixels] * B[K][N]   per 32-channel block of either operand, with
+//   A = activations of FOUR consecutive input rows x 32 channels (M = 128), pixels as K: the rows y-1, y, y+1 that pair with output
+//       row y are the kernel rows ky = 0, 1, 2 -- three of the four M blocks of one instruction (the fourth accumulates a row pairing
+//       that is not part of the convolution and is dropped);
 //   B = the gradient of output row y, N = 96 = the three kernel columns kx x 32 output channels: the three N blocks are the SAME staged
 //       row started one pixel (128 bytes) apart (descriptor LBO = 128 B), so the gradient is staged once with one halo pixel per side
 //       (TMA zero-fills outside the image, which is exactly padding='same').  Staging three shifted copies instead (one instruction
