@@ -48,3 +48,31 @@ def test_conv_block_glue_oracle_matches_framework_layers():
     out, mean, var = tail_oracle.conv_block_glue(raw.numpy(), skip.numpy(), [plane.numpy()], gamma.numpy(), beta.numpy(), 1.1e-5, pad=4)
     np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(mean, F.elu(raw).reshape(-1, 8).mean(0).numpy(), rtol=1e-12)
+
+
+def test_sub_grid_form_of_a_dilated_convolution_is_the_same_convolution():
+    """decoder._dilation_split: Conv2D(kernel_size=3, dilation_rate=d, padding='same') (bts_decoder.py:53) == 2 x 2 independent rate-d/2
+    convolutions on the interleaved sub-grids, forward and both gradients, in float64 on the CPU (host logic, no kernel involved)."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
+    for rate, H, W in ((18, 10, 14), (24, 12, 8), (24, 44, 20)):
+        torch.manual_seed(rate + H)
+        conv = decoder_mod._conv(6, 4, k=3, dilation=rate).double()
+        x = torch.randn(2, H, W, 6, dtype=torch.float64)
+        g = torch.randn(2, H, W, 4, dtype=torch.float64)
+        assert decoder_mod._dilation_split(conv, H, W) == 2
+        assert decoder_mod._dilation_split(conv, H + 1, W) == 1 and decoder_mod._dilation_split(decoder_mod._conv(6, 4, k=3, dilation=12), H, W) == 1
+        xs = x.clone().requires_grad_(True)
+        y = decoder_mod._conv_nhwc(xs, conv)
+        y.backward(g)
+        gw_split, gx_split = conv.weight.grad.clone(), xs.grad.clone()
+        conv.weight.grad = None
+        xr = x.clone().requires_grad_(True)
+        y_ref = F.conv2d(xr.permute(0, 3, 1, 2), conv.weight, None, 1, rate, rate).permute(0, 2, 3, 1)
+        y_ref.backward(g)
+        np.testing.assert_allclose(y.detach().numpy(), y_ref.detach().numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gx_split.numpy(), xr.grad.numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gw_split.numpy(), conv.weight.grad.numpy(), rtol=1e-12, atol=1e-12)
+        # the sub-grid re-ordering itself
+        s = decoder_mod._s2b(x, 2)
+        assert torch.equal(s[1], x[0, 0::2, 1::2]) and torch.equal(s[2], x[0, 1::2, 0::2]) and torch.equal(s[4], x[1, 0::2, 0::2])
+        assert torch.equal(decoder_mod._b2s(s, 2), x)

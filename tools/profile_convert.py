@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=5)
     ap.add_argument("--per-gpu-batch", type=int, default=32)
+    ap.add_argument("--inference", action="store_true", help="one eval-mode forward under no_grad instead of a training step")
     a = ap.parse_args()
     cfg = bench_decoder.CONFIGS[a.config]
     chans, F = bench_decoder.TAPS[cfg["encoder"]]
@@ -31,12 +32,20 @@ def main():
     dec = BtsDecoder(chans, cfg["max_depth"], num_filters=F).to(dev)
     feats = [torch.relu(torch.randn(b, H // s, W // s, c, device=dev)) for s, c in zip((32, 2, 4, 8, 16), chans)]
     gt = torch.rand(b, H, W, 1, device=dev) * cfg["max_depth"]
-    eng = trainer.DataParallelStep(dec, feats, gt, dataset=cfg["dataset"], use_graph=False)
+    if a.inference:
+        dec.eval()
+
+        def step():
+            with torch.no_grad():
+                dec(feats)
+    else:
+        eng = trainer.DataParallelStep(dec, feats, gt, dataset=cfg["dataset"], use_graph=False)
+        step = eng.step
     for _ in range(3):
-        eng.step()
+        step()
     torch.cuda.synchronize()
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU], record_shapes=True) as prof:
-        eng.step()
+        step()
         torch.cuda.synchronize()
     # attribute each kernel to the innermost CPU op that encloses its launch
     events = prof.events()
