@@ -94,7 +94,7 @@ SYMBOLS = {
     "btslpg_bn_fold": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, _TP, ctypes.c_float, ctypes.c_float, ctypes.c_int64, _TP, _TP, _TP, ctypes.c_void_p]),
     "btslpg_bn_act_backward_stats": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, _TP, _TP, ctypes.c_int, _TP, _TP, ctypes.c_void_p, ctypes.c_size_t,
                                                     ctypes.c_void_p]),
-    "btslpg_bn_act_backward": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, _TP, _TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_int, ctypes.c_void_p]),
+    "btslpg_bn_act_backward": (ctypes.c_int, [_TP, _TP, _TP, _TP, _TP, _TP, _TP, _TP, _TP, ctypes.c_int, _TP, ctypes.c_int, _TP, ctypes.c_void_p]),
     "btslpg_conv3x3_wgrad_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "btslpg_conv3x3_wgrad": (ctypes.c_int, [_TP, _TP, _TP, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "btslpg_upsample2x_forward": (ctypes.c_int, [_TP, _TP, ctypes.c_void_p]),

@@ -159,13 +159,20 @@ int btslpg_bn_act_backward_stats(const BtsTensor *g, const BtsTensor *g2, const 
 
 int btslpg_bn_act_backward(const BtsTensor *g, const BtsTensor *g2, const BtsTensor *x, const BtsTensor *scale, const BtsTensor *shift,
                            const BtsTensor *mean, const BtsTensor *rstd, const BtsTensor *g_gamma, const BtsTensor *g_beta, int relu,
-                           BtsTensor *dst, int accumulate, void *stream) {
-    View gv, hv, xv, dv;
+                           BtsTensor *dst, int accumulate, const BtsTensor *dst_init, void *stream) {
+    View gv, hv, xv, dv, iv;
+    if (dst_init) {
+        if (accumulate) return fail(BTSLPG_EINVAL, "dst_init (dst = dst_init + value) and accumulate (dst += value) exclude each other");
+        if (int e = parse_slice(dst_init, "dst_init", iv)) return e;
+    }
     if (int e = parse_slice(g, "g", gv)) return e;
     if (int e = parse_slice(x, "x", xv)) return e;
     if (int e = parse_slice(dst, "dst", dv)) return e;
     if (int e = same_pixels(gv, xv, "x")) return e;
     if (int e = same_pixels(gv, dv, "dst")) return e;
+    if (dst_init) {
+        if (int e = same_pixels(gv, iv, "dst_init")) return e;
+    }
     if (g2) {
         if (int e = parse_slice(g2, "g2", hv)) return e;
         if (int e = same_pixels(gv, hv, "g2")) return e;
@@ -187,6 +194,7 @@ int btslpg_bn_act_backward(const BtsTensor *g, const BtsTensor *g2, const BtsTen
     if (g2) { p.g2 = reinterpret_cast<const float *>(hv.ptr); p.sg2 = px_stride(hv); }
     p.x = reinterpret_cast<const float *>(xv.ptr); p.sx = px_stride(xv);
     p.dst = reinterpret_cast<float *>(dv.ptr); p.sd = px_stride(dv);
+    if (dst_init) { p.init = reinterpret_cast<const float *>(iv.ptr); p.si = px_stride(iv); }
     p.scale = vc.scale; p.shift = vc.shift; p.mean = vc.mean; p.rstd = vc.rstd; p.g_beta = gb; p.g_gamma = gg;
     p.inv_n = (float)(1.0 / (double)npix);
     p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;

@@ -181,6 +181,7 @@ struct BnrApplyParams {
     const float *g2;  int64_t sg2;   // nullable
     const float *x;   int64_t sx;
     float *dst;       int64_t sd;
+    const float *init; int64_t si;   // nullable: dst = init + value (the first contribution to a gradient slice that already has an upstream part)
     const float *scale, *shift, *mean, *rstd, *g_beta, *g_gamma;
     float inv_n;
     int relu, accumulate;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(256) bnr_apply_kernel(const __grid_constant__ 
     if (prm.g2) hv = __ldg(reinterpret_cast<const float4 *>(prm.g2 + (int64_t)p * prm.sg2 + c));
     float4 *dptr = reinterpret_cast<float4 *>(prm.dst + (int64_t)p * prm.sd + c);
     if (prm.accumulate) dv = *dptr;
+    else if (prm.init) dv = __ldg(reinterpret_cast<const float4 *>(prm.init + (int64_t)p * prm.si + c));
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(prm.scale + c)), sh = __ldg(reinterpret_cast<const float4 *>(prm.shift + c));
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(prm.mean + c)), rs = __ldg(reinterpret_cast<const float4 *>(prm.rstd + c));
     const float4 gb = __ldg(reinterpret_cast<const float4 *>(prm.g_beta + c)), gg = __ldg(reinterpret_cast<const float4 *>(prm.g_gamma + c));

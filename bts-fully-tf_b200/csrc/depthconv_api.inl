@@ -56,7 +56,7 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
         p.counter = reinterpret_cast<unsigned int *>(workspace);
         p.partial = workspace ? reinterpret_cast<float *>(static_cast<char *>(workspace) + kDcHeaderBytes) : nullptr;
         p.B = (uint32_t)xv.B; p.H = (uint32_t)xv.H; p.W = (uint32_t)xv.W;
-        p.col_blocks = (uint32_t)((xv.W + kDcTileW - 1) / kDcTileW);
+        p.col_blocks = (uint32_t)((xv.W + dc_tile_w<CC>() - 1) / dc_tile_w<CC>());
         p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
         p.div_cb = FastDiv(p.col_blocks);
         p.div_h = FastDiv(p.H);

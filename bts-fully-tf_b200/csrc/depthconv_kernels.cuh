@@ -26,7 +26,10 @@ __device__ __forceinline__ float load_smem1(const float *p) { return *p; }
 __device__ __forceinline__ float load_smem1(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 
 constexpr int kDcThreads = 256;
-constexpr int kDcTileW = 128;            // pixels of one image row per work item
+constexpr int kDcTileW = 128;            // pixels of one image row per work item (C = 32)
+// 16 channels: twice the pixels, i.e. the same 16 KB of x per stage (the per-item barriers and the strip set-up weigh twice as much on
+// half the bytes otherwise)
+template <int C> __host__ __device__ constexpr int dc_tile_w() { return C <= 16 ? 2 * kDcTileW : kDcTileW; }
 constexpr int kDcHeaderBytes = 256;
 constexpr int kDcMaxBlocks = 148 * 4;
 
@@ -79,8 +82,9 @@ __device__ __forceinline__ void dc_reduce_partials(const float *partial, uint32_
 // The first version loaded the g strip, synchronised, loaded x into registers and only then computed: two exposed DRAM round
 // trips per 128-pixel item and CTA (0.45 of the HBM peak at C = 32, 0.34 at C = 16, profiles/r02 bench extras.tail).
 template <typename T, int C> struct DcBwdStage {
-    static constexpr int kXBytes = kDcTileW * C * (int)sizeof(T);             // 16 KB (float32, C = 32)
-    static constexpr int kGFloats = 3 * (kDcTileW + 2);
+    static constexpr int kTW = dc_tile_w<C>();
+    static constexpr int kXBytes = kTW * C * (int)sizeof(T);                  // 16 KB (float32)
+    static constexpr int kGFloats = 3 * (kTW + 2);
     static constexpr int kGBytes = (kGFloats * (int)sizeof(T) + 15) / 16 * 16;
     static constexpr int kBytes = kXBytes + kGBytes;
 };
@@ -114,14 +118,14 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
         uint32_t rowi, xb, b, y;
         prm.div_cb.divmod(item, rowi, xb);     // rowi = b * H + y
         prm.div_h.divmod(rowi, b, y);
-        const uint32_t x0 = xb * kDcTileW;
-        const uint32_t npx = min((uint32_t)kDcTileW, prm.W - x0);
+        const uint32_t x0 = xb * St::kTW;
+        const uint32_t npx = min((uint32_t)St::kTW, prm.W - x0);
         const uint32_t sbase = smem_u32(dcb_smem) + stage * St::kBytes;
         const T *xsrc = prm.x + ((size_t)rowi * prm.W + x0) * C;
         for (uint32_t i = threadIdx.x; i < npx * C / EPV; i += kDcThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(xsrc + (size_t)i * EPV) : "memory");
-        for (uint32_t i = threadIdx.x; i < 3 * (kDcTileW + 2); i += kDcThreads) {
-            const uint32_t r = i / (kDcTileW + 2), j = i % (kDcTileW + 2);
+        for (uint32_t i = threadIdx.x; i < 3 * (St::kTW + 2); i += kDcThreads) {
+            const uint32_t r = i / (St::kTW + 2), j = i % (St::kTW + 2);
             const int yy = (int)y + (int)r - 1, xx = (int)x0 + (int)j - 1;
             const bool in = yy >= 0 && yy < (int)prm.H && xx >= 0 && xx < (int)prm.W && j <= npx + 1;
             const T *gsrc = in ? prm.g + ((size_t)b * prm.H + yy) * prm.W + xx : prm.g;
@@ -144,10 +148,10 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
         __syncthreads();
         uint32_t rowi, xb;
         prm.div_cb.divmod(item, rowi, xb);
-        const uint32_t x0 = xb * kDcTileW;
-        const uint32_t npx = min((uint32_t)kDcTileW, prm.W - x0);
+        const uint32_t x0 = xb * St::kTW;
+        const uint32_t npx = min((uint32_t)St::kTW, prm.W - x0);
         const T *xs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes);
-        const T *gs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes + St::kXBytes);       // [3][kDcTileW + 2]
+        const T *gs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes + St::kXBytes);       // [3][St::kTW + 2]
         const size_t row0 = ((size_t)rowi * prm.W + x0);
         for (uint32_t px = wid * PPW + pl; px < npx; px += NW * PPW) {
             float xv[4];
@@ -169,7 +173,7 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int tp = (dy + 1) * 3 + (dx + 1);
-                    const float gv = load_smem1(gs + (1 - dy) * (kDcTileW + 2) + px + 1 - dx);          // g at pixel q - (dy, dx)
+                    const float gv = load_smem1(gs + (1 - dy) * (St::kTW + 2) + px + 1 - dx);          // g at pixel q - (dy, dx)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         out[e] = fmaf(gv, wr[tp][e], out[e]);

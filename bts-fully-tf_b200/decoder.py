@@ -311,7 +311,11 @@ class DenseAsppTrainFunction(torch.autograd.Function):
         nf = x4.shape[-1]
         half = nf // 2
         dev = buf.device
-        gbuf = g_out.contiguous().clone()              # gradient of concat4_daspp; the blocks' contributions are added into its slices
+        # g_out, the gradient of concat4_daspp, is only READ; the blocks' contributions to the appended pieces d3 .. d18 are gathered in
+        # gacc (channels [nf, nf + 4 half) of the buffer), started by the last block as g_out's slice + its contribution (dst_init)
+        g_out = g_out.contiguous()
+        last = len(blocks) - 1
+        gacc = torch.empty((B, h, w, last * half), dtype=torch.float32, device=dev)
         g4 = torch.empty_like(x4)                      # d loss / d iconv4
         g4_written = False
         grads = {}
@@ -325,7 +329,8 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             ck = nf + half * k
             s2 = _dilation_split(blk.conv2, h, w)
             s2 = s2 if s2 > 1 else 0
-            g_d = ops.affine_act(gbuf[..., ck:ck + half], dst_split=s2)                 # contiguous copy of the block's complete gradient
+            g_slot = g_out[..., ck:ck + half] if k == last else gacc[..., ck - nf:ck - nf + half]
+            g_d = ops.affine_act(g_slot, dst_split=s2)                                  # contiguous copy of the block's complete gradient
             g_r2, grads[blk.conv2.weight] = _conv_backward(g_d, r2, blk.conv2, split=s2)
             if s2:
                 g_r2 = ops.affine_act(g_r2, src_split=s2)                               # back to the pixel order of conv1's output
@@ -336,13 +341,14 @@ class DenseAsppTrainFunction(torch.autograd.Function):
             if k == 0:
                 # iconv4_bn feeds relu -> conv1 of daspp_3 AND concat4_daspp directly (:58-59, :75): one BatchNormalization backward
                 gg, gb = torch.empty(nf, dtype=torch.float32, device=dev), torch.empty(nf, dtype=torch.float32, device=dev)
-                ops.bn_act_backward(g_xk, x4, vec4, gg, gb, g4, accumulate=g4_written, g2=gbuf[..., :nf])
+                ops.bn_act_backward(g_xk, x4, vec4, gg, gb, g4, accumulate=g4_written, g2=g_out[..., :nf])
                 grads[dec.bn4.weight], grads[dec.bn4.bias] = gg, gb
             else:
                 gg, gb = torch.empty(ck, dtype=torch.float32, device=dev), torch.empty(ck, dtype=torch.float32, device=dev)
                 ops.bn_act_backward(g_xk[..., :nf], x4, vec_slice(vk, 0, nf), gg[:nf], gb[:nf], g4, accumulate=g4_written)
                 g4_written = True
-                ops.bn_act_backward(g_xk[..., nf:], buf[..., nf:ck], vec_slice(vk, nf, ck), gg[nf:], gb[nf:], gbuf[..., nf:ck], accumulate=True)
+                ops.bn_act_backward(g_xk[..., nf:], buf[..., nf:ck], vec_slice(vk, nf, ck), gg[nf:], gb[nf:], gacc[..., :ck - nf],
+                                    accumulate=k != last, dst_init=g_out[..., nf:ck] if k == last else None)
                 grads[blk.bn_first.weight], grads[blk.bn_first.bias] = gg, gb
         g_iconv4 = _to_nchw(g4) if ctx.needs_input_grad[0] else None
         return (g_iconv4, None) + tuple(grads[p] for p in dec._daspp_params())

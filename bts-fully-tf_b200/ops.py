@@ -677,19 +677,20 @@ def bn_fold(mean, var, gamma, beta, running_mean, running_var, momentum, eps, co
     return scale, shift, mean, rstd
 
 
-def bn_act_backward(g, x, vecs, g_gamma, g_beta, dst, relu=True, accumulate=False, g2=None):
+def bn_act_backward(g, x, vecs, g_gamma, g_beta, dst, relu=True, accumulate=False, g2=None, dst_init=None):
     """Backward of y = act(x * scale + shift) with batch statistics, over one channel slice: fills g_gamma / g_beta [C] and writes or
-    adds d loss / d x into `dst`.  vecs = (scale, shift, mean, rstd) slices; g2: gradient reaching the normalised value directly."""
+    adds d loss / d x into `dst` (dst_init: dst = dst_init + d loss / d x).  vecs = (scale, shift, mean, rstd) slices; g2: gradient
+    reaching the normalised value directly."""
     lib = load()
     wp, wn = _bn_ws(g.device, g.shape[-1])
-    rg, rh, rx, rd = as_ref(g), as_ref(g2), as_ref(x), as_ref(dst)
+    rg, rh, rx, rd, ri = as_ref(g), as_ref(g2), as_ref(x), as_ref(dst), as_ref(dst_init)
     rv = [as_ref(v) for v in vecs]
     rgg, rgb = as_ref(g_gamma), as_ref(g_beta)
     st = current_stream_ptr(g.device)
     check(lib.btslpg_bn_act_backward_stats(rg.ptr, ptr_or_null(rh), rx.ptr, rv[0].ptr, rv[1].ptr, rv[2].ptr, rv[3].ptr, 1 if relu else 0,
                                            rgg.ptr, rgb.ptr, wp, wn, st))
     check(lib.btslpg_bn_act_backward(rg.ptr, ptr_or_null(rh), rx.ptr, rv[0].ptr, rv[1].ptr, rv[2].ptr, rv[3].ptr, rgg.ptr, rgb.ptr,
-                                     1 if relu else 0, rd.ptr, 1 if accumulate else 0, st))
+                                     1 if relu else 0, rd.ptr, 1 if accumulate else 0, ptr_or_null(ri), st))
     return dst
 
 

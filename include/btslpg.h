@@ -306,7 +306,9 @@ BTSLPG_API int btslpg_conv3x3_wgrad(const BtsTensor *x, const BtsTensor *g, BtsT
  *   btslpg_bn_act_backward_stats  y = act(x * scale + shift); gm = g * [y > 0] (relu) (+ g2, nullable: a gradient that reaches the
  *                                 NORMALISED value directly): g_beta = sum gm, g_gamma = sum gm * xhat, xhat = (x - mean) * rstd
  *   btslpg_bn_act_backward        dst (+)= scale * (gm - g_beta / n - xhat * g_gamma / n): d loss / d x, written or ACCUMULATED into a
- *                                 slice of the shared gradient buffer (the concat's backward is that accumulation)
+ *                                 slice of the shared gradient buffer (the concat's backward is that accumulation); dst_init
+ *                                 (nullable, accumulate = 0): dst = dst_init + value, the first contribution to a slice whose
+ *                                 upstream part lives in another tensor (no copy of the upstream gradient is made)
  * Every tensor argument is float32, channel stride 1, uniformly strided 16-byte aligned pixels, C a multiple of 4 in [4, 1024];
  * per-channel vectors are contiguous float32 [C], 16-byte aligned.  Deterministic (fixed-order sums, no atomics).
  * workspace: btslpg_bn_workspace_bytes(C) bytes, 16-byte aligned, no initialisation needed.
@@ -320,7 +322,8 @@ BTSLPG_API int btslpg_bn_act_backward_stats(const BtsTensor *g, const BtsTensor 
                                             BtsTensor *g_gamma, BtsTensor *g_beta, void *workspace, size_t workspace_bytes, void *stream);
 BTSLPG_API int btslpg_bn_act_backward(const BtsTensor *g, const BtsTensor *g2, const BtsTensor *x, const BtsTensor *scale,
                                       const BtsTensor *shift, const BtsTensor *mean, const BtsTensor *rstd, const BtsTensor *g_gamma,
-                                      const BtsTensor *g_beta, int relu, BtsTensor *dst, int accumulate, void *stream);
+                                      const BtsTensor *g_beta, int relu, BtsTensor *dst, int accumulate, const BtsTensor *dst_init,
+                                      void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Nearest-neighbour x2 up-sampling of an NHWC map -- replaces the
