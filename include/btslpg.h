@@ -264,7 +264,10 @@ BTSLPG_API int btslpg_concat_backward(const BtsTensor *g_out, const BtsTensor *y
  *                                  Writes g_gamma = sum g * xhat, g_beta = sum g (xhat = (y - beta) / gamma: recovered from the output,
  *                                  nothing else is kept alive) and pack[6..7] = their means.
  *   btslpg_concat_backward_bn      btslpg_concat_backward with the pack: g_a = scale * (g - c1 - xhat * c2) * elu'(elu).
- * float32, C a power of two in [4, 1024], CT a multiple of 4.  Deterministic (fixed-order sums, no atomics).
+ * float32, C a power of two in [4, 1024], CT a multiple of 4.  Deterministic (fixed-order sums, no atomics).  Because xhat is recovered
+ * from the output, a channel whose gamma is exactly 0 has no recoverable xhat (1/gamma): the backward then yields non-finite values for
+ * that channel.  Keras initialises gamma = 1 and nothing in the reference's training drives it to exactly 0; a caller that prunes
+ * channels by zeroing gamma must use the framework's layers for that block (the host code's fallback path).
  * workspace: btslpg_bn_workspace_bytes(C) bytes, 16-byte aligned, no initialisation needed.
  * ------------------------------------------------------------------------------------------- */
 BTSLPG_API size_t btslpg_bn_workspace_bytes(int channels);
