@@ -103,13 +103,15 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cg = lane % LPP, pl = lane / LPP;
 
-    float wr[9][4], acc[9][4];
+    // the 36 weights of the thread's four channels and its 36 partial sums of g_w as packed float32 pairs: the 72 FMAs per pixel
+    // issue as 36 FFMA2 (the kernel is bound by instruction issue: ncu 65 % of the issue slots at 16 warps per SM)
+    F2 wr[9][2], acc[9][2];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            wr[t][e] = __ldg(prm.w + t * C + 4 * cg + e);
-            acc[t][e] = 0.0f;
+        for (int h = 0; h < 2; ++h) {
+            wr[t][h] = f2(__ldg(prm.w + t * C + 4 * cg + 2 * h), __ldg(prm.w + t * C + 4 * cg + 2 * h + 1));
+            acc[t][h] = f2(0.0f);
         }
 
     // copies of one work item into a stage: the x tile (16-byte pieces) and the 3-row strip of g with its one-pixel halo
@@ -156,7 +158,7 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
         for (uint32_t px = wid * PPW + pl; px < npx; px += NW * PPW) {
             float xv[4];
             lds_elems<T, 4>(xs + (size_t)px * C + 4 * cg, xv);
-            float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            F2 out2[2] = {f2(0.0f), f2(0.0f)};
             float dact[4];
             if constexpr (ELU) {
                 // x is the PRE-activation of iconv1 (bts_decoder.py:100): the layer input is elu(x), d elu / d x = x > 0 ? 1 : exp(x)
@@ -168,18 +170,22 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
                     xv[e] = xv[e] > 0.0f ? xv[e] : ex - 1.0f;
                 }
             }
+            const F2 xv2[2] = {f2(xv[0], xv[1]), f2(xv[2], xv[3])};
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int tp = (dy + 1) * 3 + (dx + 1);
-                    const float gv = load_smem1(gs + (1 - dy) * (St::kTW + 2) + px + 1 - dx);          // g at pixel q - (dy, dx)
+                    const F2 gv = f2(load_smem1(gs + (1 - dy) * (St::kTW + 2) + px + 1 - dx));      // g at pixel q - (dy, dx)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        out[e] = fmaf(gv, wr[tp][e], out[e]);
-                        acc[tp][e] = fmaf(gv, xv[e], acc[tp][e]);
+                    for (int h = 0; h < 2; ++h) {
+                        out2[h] = fma2(gv, wr[tp][h], out2[h]);
+                        acc[tp][h] = fma2(gv, xv2[h], acc[tp][h]);
                     }
                 }
+            float out[4];
+            unpack(out2[0], out[0], out[1]);
+            unpack(out2[1], out[2], out[3]);
             if constexpr (ELU) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) out[e] *= dact[e];
@@ -196,7 +202,7 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float v = acc[t][e];
+            float v = (e & 1) ? hi(acc[t][e >> 1]) : lo(acc[t][e >> 1]);
 #pragma unroll
             for (int m = LPP; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
             if (pl == 0) red[wid][t * C + 4 * cg + e] = v;
