@@ -76,3 +76,37 @@ def test_sub_grid_form_of_a_dilated_convolution_is_the_same_convolution():
         s = decoder_mod._s2b(x, 2)
         assert torch.equal(s[1], x[0, 0::2, 1::2]) and torch.equal(s[2], x[0, 1::2, 0::2]) and torch.equal(s[4], x[1, 0::2, 0::2])
         assert torch.equal(decoder_mod._b2s(s, 2), x)
+
+
+def test_dispatch_predicates_of_the_training_paths():
+    """Host logic only: which layers take the hand-written training paths (and which fall back to the framework's)."""
+    from bts_fully_tf_b200 import decoder as decoder_mod
+    from bts_fully_tf_b200 import ops
+    # conv-block glue: float32, power-of-two channel count, concat width a multiple of 4
+    assert ops.bn_glue_supported(64, 64 + 96 + 1 + 3, torch.float32)
+    assert not ops.bn_glue_supported(48, 48 + 16, torch.float32) and not ops.bn_glue_supported(64, 161, torch.float32)
+    assert not ops.bn_glue_supported(64, 164, torch.bfloat16)
+    # DenseASPP glue: half-width pieces must be whole 16-byte vectors, slices at most 1024 channels
+    assert ops.bn_slices_supported(256, torch.float32) and ops.bn_slices_supported(128, torch.float32)
+    assert not ops.bn_slices_supported(100, torch.float32) and not ops.bn_slices_supported(1024, torch.float32)
+    # tensor-core weight gradient: never on the CPU / without grad / for wide layers / with the TF32 switch off
+    w = torch.zeros(16, 20, 3, 3, requires_grad=True)
+    x = torch.zeros(32, 20, 64, 64)
+    assert not decoder_mod._tc_wgrad_applies(x, w)                         # CPU tensor
+    class _Cuda:                                                           # shape / flag logic without a device
+        is_cuda, dtype = True, torch.float32
+        def __init__(self, shape): self.shape = shape
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        assert decoder_mod._tc_wgrad_applies(_Cuda((32, 20, 64, 64)), w)
+        assert not decoder_mod._tc_wgrad_applies(_Cuda((1, 20, 64, 64)), w)                                          # too few pixels
+        assert not decoder_mod._tc_wgrad_applies(_Cuda((32, 128, 64, 64)), torch.zeros(128, 128, 3, 3, requires_grad=True))   # wide: library
+        assert not decoder_mod._tc_wgrad_applies(_Cuda((32, 20, 64, 64)), torch.zeros(16, 20, 1, 1, requires_grad=True))      # not 3x3
+        assert not decoder_mod._tc_wgrad_applies(_Cuda((32, 20, 64, 64)), w.detach())                                # no gradient wanted
+        with torch.no_grad():
+            assert not decoder_mod._tc_wgrad_applies(_Cuda((32, 20, 64, 64)), w)
+        torch.backends.cudnn.allow_tf32 = False
+        assert not decoder_mod._tc_wgrad_applies(_Cuda((32, 20, 64, 64)), w)                                         # float32 convolutions asked for
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
