@@ -167,21 +167,23 @@ class _DenseAspp(nn.Module):
         x = F.relu(self.bn2(x)).contiguous(memory_format=torch.channels_last)
         return _to_nchw(_conv_nhwc(_nhwc_view(x), self.conv2))
 
-    def tail_inference(self, x_relu_nchw):
-        """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode; returns (NHWC, split):
-        the second BatchNormalization (folded to an affine) and the ReLU are ONE in-place ops.affine_act pass over the
-        1x1 conv's output (the framework's bias add + ReLU after a folded kernel take 156 us per block, this 26 us)."""
+    def tail_inference(self, x_relu_nhwc, split=0):
+        """conv1 -> BN -> ReLU -> dilated conv2 on an input that already went through (BN and) ReLU, inference mode.
+        The 1x1 convolution, the folded second BatchNormalization and the ReLU are ONE library call (cuDNN's fused convolution +
+        bias + ReLU with the BatchNormalization scale folded into the kernel: 55-111 us per block at B = 32, 60x80, where the plain
+        convolution followed by one in-place ops.affine_act pass took 114-167 us, tools/exp_conv_bias_relu.py).
+        split = s: x_relu_nhwc is in the sub-grid form of _s2b(., s) (the 1x1 convolution is pointwise, so its output is too) and so is
+        the returned tensor -- the rate-18 / 24 convolutions, see _dilation_split."""
         scale, shift = _bn_affine(self.bn2)
-        x = self.conv1(x_relu_nchw).contiguous(memory_format=torch.channels_last)
-        x_nhwc = _nhwc_view(x)
-        s2 = _dilation_split(self.conv2, x_nhwc.shape[1], x_nhwc.shape[2])
-        if s2 > 1:
-            # rate 18 / 24: the same pass writes the sub-grid form the split convolution reads; the caller's copy into the DenseASPP
-            # buffer reads the result back from that form (returns (NHWC tensor in sub-grid form, s))
-            r = ops.affine_act(x_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU, dst_split=s2)
-            return _conv_nhwc(r, self.conv2, split=s2), s2
-        ops.affine_act(x_nhwc, dst=x_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU)
-        return _conv_nhwc(x_nhwc, self.conv2), 0
+        x = _to_nchw(x_relu_nhwc)
+        if x.is_cuda and hasattr(torch, "cudnn_convolution_relu"):
+            wf = (self.conv1.weight * scale[:, None, None, None]).contiguous(memory_format=torch.channels_last)
+            y = torch.cudnn_convolution_relu(x, wf, shift, [1, 1], [0, 0], [1, 1], 1).contiguous(memory_format=torch.channels_last)
+            y_nhwc = _nhwc_view(y)
+        else:
+            y_nhwc = _nhwc_view(self.conv1(x).contiguous(memory_format=torch.channels_last))
+            ops.affine_act(y_nhwc, dst=y_nhwc, scale=scale, shift=shift, act=ops.ACT_RELU)
+        return _conv_nhwc(y_nhwc, self.conv2, split=split)
 
 
 SPLIT_DILATION_FROM = 16     # dilation rates from here on run as 2 x 2 interleaved sub-grids of half the rate (see _dilation_split)
@@ -453,14 +455,15 @@ class BtsDecoder(nn.Module):
         buf = torch.empty((B, h, w, nf + 5 * half), dtype=iconv4.dtype, device=iconv4.device)       # [iconv4 | d3 | d6 | d12 | d18 | d24]
         ops.affine_act(_nhwc_view(iconv4.contiguous(memory_format=torch.channels_last)), dst=buf[..., :nf])
         s4_, t4_ = _bn_affine(self.bn4)
-        x = ops.affine_act(buf[..., :nf], scale=s4_, shift=t4_, act=ops.ACT_RELU)                    # relu(iconv4_bn)
-        d, s2 = self.daspp_3.tail_inference(_to_nchw(x))
-        ops.affine_act(d, dst=buf[..., nf:nf + half], src_split=s2)
-        for k, blk in enumerate((self.daspp_6, self.daspp_12, self.daspp_18, self.daspp_24)):
-            ck = nf + half * (k + 1)
-            sc, sh = _bn_affine(blk.bn_first)
-            x = ops.affine_act(buf[..., :ck], scale=sc, shift=sh, act=ops.ACT_RELU)                  # relu(BN(concat4_k)), contiguous
-            d, s2 = blk.tail_inference(_to_nchw(x))
+        blocks = self._daspp_blocks()
+        for k, blk in enumerate(blocks):
+            ck = nf + half * k
+            sc, sh = (s4_, t4_) if k == 0 else _bn_affine(blk.bn_first)
+            s2 = _dilation_split(blk.conv2, h, w)
+            s2 = s2 if s2 > 1 else 0
+            # relu(iconv4_bn) / relu(BN(concat4_k)), contiguous -- in sub-grid form for the blocks whose dilated convolution is split
+            x = ops.affine_act(buf[..., :ck], scale=sc, shift=sh, act=ops.ACT_RELU, dst_split=s2)
+            d = blk.tail_inference(x, split=s2)
             ops.affine_act(d, dst=buf[..., ck:ck + half], src_split=s2)
         ops.affine_act(buf[..., :nf], dst=buf[..., :nf], scale=s4_, shift=t4_)                       # concat4_daspp starts with iconv4_bn (:75)
         return F.elu(self.daspp_feat(_to_nchw(buf)))
