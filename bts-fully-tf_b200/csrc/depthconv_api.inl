@@ -60,6 +60,7 @@ int btslpg_depthconv_backward(const BtsTensor *x, const BtsTensor *kernel, const
         p.items = (uint32_t)(xv.B * xv.H) * p.col_blocks;
         p.div_cb = FastDiv(p.col_blocks);
         p.div_h = FastDiv(p.H);
+        p.vec_g = (sizeof(T) == 4 && xv.W % 4 == 0 && gv.aligned(16)) ? 1 : 0;
         constexpr int smem = depthconv_bwd_smem_bytes<T, CC>();
         static PerDevice per_dev; const int resident = per_dev.get([&] { return occupancy_blocks_smem(depthconv_bwd_kernel<T, CC, ELU>, kDcThreads, smem); });
         uint32_t blocks = p.items < (uint32_t)resident ? p.items : (uint32_t)resident;

@@ -43,6 +43,7 @@ template <typename T> struct DepthConvBwdParams {
     unsigned int *counter;
     uint32_t B, H, W, col_blocks, items;
     FastDiv div_cb, div_h;
+    int vec_g;           // float32 g rows start on 16-byte boundaries (W % 4 == 0): 16-byte strip copies
 };
 
 // the last CTA adds the per-CTA partial rows in a fixed order: float4 columns x slices of the CTA range, 8 loads in flight
@@ -84,7 +85,10 @@ __device__ __forceinline__ void dc_reduce_partials(const float *partial, uint32_
 template <typename T, int C> struct DcBwdStage {
     static constexpr int kTW = dc_tile_w<C>();
     static constexpr int kXBytes = kTW * C * (int)sizeof(T);                  // 16 KB (float32)
-    static constexpr int kGFloats = 3 * (kTW + 2);
+    // a strip row: left halo pixel at index 3, the tile's own kTW pixels at 4 .. kTW + 3 (16-byte aligned: float32 rows whose width
+    // is a multiple of 4 are copied as 16-byte pieces), right halo pixel at kTW + 4
+    static constexpr int kGRow = kTW + 8;
+    static constexpr int kGFloats = 3 * kGRow;
     static constexpr int kGBytes = (kGFloats * (int)sizeof(T) + 15) / 16 * 16;
     static constexpr int kBytes = kXBytes + kGBytes;
 };
@@ -126,15 +130,42 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
         const T *xsrc = prm.x + ((size_t)rowi * prm.W + x0) * C;
         for (uint32_t i = threadIdx.x; i < npx * C / EPV; i += kDcThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(xsrc + (size_t)i * EPV) : "memory");
+        if (sizeof(T) == 4 && prm.vec_g) {
+            // float32, W a multiple of 4: one 16-byte copy per thread for the three rows' own pixels (the source size trims the piece
+            // at the right image border, 0 bytes = all zeros), six 4-byte copies for the halo pixels
+            constexpr int NV = St::kTW / 4;
+            static_assert(3 * NV <= kDcThreads - 6, "one strip copy per thread");
+            if (threadIdx.x < 3 * NV) {
+                const int r = threadIdx.x / NV, v = threadIdx.x % NV;
+                const int yy = (int)y + r - 1, xx = (int)x0 + 4 * v;
+                uint32_t nbytes = 0;
+                const T *gsrc = prm.g;
+                if (yy >= 0 && yy < (int)prm.H && xx < (int)prm.W) {
+                    nbytes = 4u * (uint32_t)min(4, (int)prm.W - xx);
+                    gsrc = prm.g + ((size_t)b * prm.H + yy) * prm.W + xx;
+                }
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + St::kXBytes + (r * St::kGRow + 4 + 4 * v) * 4), "l"(gsrc),
+                             "r"(nbytes) : "memory");
+            } else if (threadIdx.x >= kDcThreads - 6) {
+                const int hidx = threadIdx.x - (kDcThreads - 6), r = hidx >> 1, right = hidx & 1;
+                const int yy = (int)y + r - 1, xx = right ? (int)x0 + St::kTW : (int)x0 - 1;
+                const bool in = yy >= 0 && yy < (int)prm.H && xx >= 0 && xx < (int)prm.W;
+                const T *gsrc = in ? prm.g + ((size_t)b * prm.H + yy) * prm.W + xx : prm.g;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + St::kXBytes + (r * St::kGRow + (right ? St::kTW + 4 : 3)) * 4),
+                             "l"(gsrc), "r"(in ? 4 : 0) : "memory");
+            }
+            return;
+        }
         for (uint32_t i = threadIdx.x; i < 3 * (St::kTW + 2); i += kDcThreads) {
             const uint32_t r = i / (St::kTW + 2), j = i % (St::kTW + 2);
             const int yy = (int)y + (int)r - 1, xx = (int)x0 + (int)j - 1;
             const bool in = yy >= 0 && yy < (int)prm.H && xx >= 0 && xx < (int)prm.W && j <= npx + 1;
             const T *gsrc = in ? prm.g + ((size_t)b * prm.H + yy) * prm.W + xx : prm.g;
+            const uint32_t slot = r * St::kGRow + j + 3;
             if constexpr (sizeof(T) == 4) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + St::kXBytes + i * 4), "l"(gsrc), "r"(in ? 4 : 0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + St::kXBytes + slot * 4), "l"(gsrc), "r"(in ? 4 : 0) : "memory");
             } else {                            // 2-byte elements: below cp.async's granularity, a plain store of the loaded value
-                reinterpret_cast<T *>(dcb_smem + stage * St::kBytes + St::kXBytes)[i] = in ? *gsrc : T(0.0f);
+                reinterpret_cast<T *>(dcb_smem + stage * St::kBytes + St::kXBytes)[slot] = in ? *gsrc : T(0.0f);
             }
         }
     };
@@ -153,7 +184,7 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
         const uint32_t x0 = xb * St::kTW;
         const uint32_t npx = min((uint32_t)St::kTW, prm.W - x0);
         const T *xs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes);
-        const T *gs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes + St::kXBytes);       // [3][St::kTW + 2]
+        const T *gs = reinterpret_cast<const T *>(dcb_smem + stage * St::kBytes + St::kXBytes);       // [3][St::kGRow]
         const size_t row0 = ((size_t)rowi * prm.W + x0);
         for (uint32_t px = wid * PPW + pl; px < npx; px += NW * PPW) {
             float xv[4];
@@ -176,7 +207,7 @@ template <typename T, int C, bool ELU> __global__ void __launch_bounds__(kDcThre
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int tp = (dy + 1) * 3 + (dx + 1);
-                    const F2 gv = f2(load_smem1(gs + (1 - dy) * (St::kTW + 2) + px + 1 - dx));      // g at pixel q - (dy, dx)
+                    const F2 gv = f2(load_smem1(gs + (1 - dy) * St::kGRow + px + 4 - dx));      // g at pixel q - (dy, dx)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         out2[h] = fma2(gv, wr[tp][h], out2[h]);
