@@ -81,7 +81,9 @@ __device__ __forceinline__ void dc_reduce_partials(const float *partial, uint32_
 
 // Two stages of (x tile, 3-row strip of g) in shared memory, filled with cp.async one work item ahead of the arithmetic.
 // The first version loaded the g strip, synchronised, loaded x into registers and only then computed: two exposed DRAM round
-// trips per 128-pixel item and CTA (0.45 of the HBM peak at C = 32, 0.34 at C = 16, profiles/r02 bench extras.tail).
+// trips per 128-pixel item and CTA (0.45 of the HBM peak at C = 32, 0.34 at C = 16).  With the stages: 0.72 / 0.54; with 256-pixel tiles
+// at C = 16, packed FMAs and the strip copied as 16-byte pieces (the 4-byte copies with per-element bounds logic were a quarter of the
+// kernel's instructions): 0.78 / 0.71 (profiles/r02_tail_f32.json).
 template <typename T, int C> struct DcBwdStage {
     static constexpr int kTW = dc_tile_w<C>();
     static constexpr int kXBytes = kTW * C * (int)sizeof(T);                  // 16 KB (float32)
